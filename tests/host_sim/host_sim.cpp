@@ -1,0 +1,122 @@
+// host_sim.cpp -- CPU build of the product's host+device traversal logic
+// (nerfacc_b200/csrc/{lattice,march,expand,occ_pack}.cuh), for tests only.
+//
+// The kernels in nerfacc_b200/csrc/traverse.cu are thin thread/warp mappings
+// around these headers; running the same headers on the CPU lets the
+// `-m "not gpu"` suite check the closed-form lattice and the lazy march against
+// the oracle's serial restatement of the reference.  This library is never
+// loaded by the nerfacc_b200 package (there is no CPU fallback in the product).
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../nerfacc_b200/csrc/occ_pack.cuh"
+#include "../../nerfacc_b200/csrc/expand.cuh"
+
+using namespace nfa;
+
+extern "C" {
+
+// serial reference chain: k steps of t += dt
+float sim_chain(float t, float dt, uint32_t k)
+{
+    for (uint32_t i = 0; i < k; ++i) t = t + dt;
+    return t;
+}
+
+// closed-form seek; returns ok flag
+int sim_seek(float t0, float dt, float target, float* t_out, uint32_t* k_out)
+{
+    Lattice L = lat_make(dt);
+    float t = t0;
+    uint32_t k = 0;
+    bool ok = lat_seek(L, t, target, k);
+    *t_out = t;
+    *k_out = k;
+    return ok ? 1 : 0;
+}
+
+// expand one run into starts/ends
+void sim_expand_run(float t_first, float dt, uint32_t n, float* starts, float* ends)
+{
+    Lattice L = lat_make(dt);
+    RunIter it{t_first, n};
+    uint32_t w = 0;
+    while (it.left > 0) {
+        LatPiece p;
+        uint32_t c = run_next_piece(L, it, p);
+        for (uint32_t j = 0; j < c; ++j) {
+            starts[w] = piece_start(p, j);
+            ends[w] = starts[w] + dt;
+            ++w;
+        }
+    }
+}
+
+int64_t sim_occ_words(int n_grids, int rx, int ry, int rz) { return (int64_t)n_grids * occ_geom(n_grids, rx, ry, rz).wpl; }
+int64_t sim_occ_coarse_words(int n_grids, int rx, int ry, int rz) { return occ_coarse_words(occ_geom(n_grids, rx, ry, rz)); }
+
+void sim_occ_pack(int n_grids, int rx, int ry, int rz, const uint8_t* binaries, uint64_t* words, uint32_t* coarse)
+{
+    OccGeom g = occ_geom(n_grids, rx, ry, rz);
+    memset(coarse, 0, sizeof(uint32_t) * occ_coarse_words(g));
+    const int64_t cells = (int64_t)rx * ry * rz;
+    for (int l = 0; l < n_grids; ++l)
+        for (int bx = 0; bx < g.nb[0]; ++bx)
+            for (int by = 0; by < g.nb[1]; ++by)
+                for (int bz = 0; bz < g.nb[2]; ++bz) {
+                    const int b = (bx * g.nb[1] + by) * g.nb[2] + bz + l * g.wpl;
+                    const uint64_t w = occ_brick_word(binaries + l * cells, g, bx, by, bz);
+                    words[b] = w;
+                    if (w) coarse[b >> 5] |= 1u << (b & 31);
+                }
+}
+
+struct VecSink {
+    std::vector<float>* t;
+    std::vector<uint32_t>* n;
+    void push(uint32_t, float t_first, uint32_t cnt) { t->push_back(t_first); n->push_back(cnt); }
+};
+
+// March all rays; per ray: n_samples, n_runs, terminate plane; runs appended to
+// flat arrays (caller passes capacity; returns total runs or -1 on overflow).
+int64_t sim_march(int32_t n_rays, const float* rays_o, const float* rays_d,
+                  const float* near_planes, const float* far_planes,
+                  int n_grids, int rx, int ry, int rz, const uint64_t* words, const uint32_t* coarse,
+                  const float* aabbs,
+                  const float* t_sorted, const int64_t* t_indices, const uint8_t* hits,  // NULL => single level inline
+                  float step_size,
+                  int64_t* n_samples, int64_t* n_runs, float* terminate, int32_t* ok_flags,
+                  float* run_t, uint32_t* run_n, int64_t run_capacity)
+{
+    OccView occ;
+    occ.words = words;
+    occ.coarse = coarse;
+    occ.g = occ_geom(n_grids, rx, ry, rz);
+    const Lattice L = lat_make(step_size);
+    int64_t total = 0;
+    std::vector<float> vt;
+    std::vector<uint32_t> vn;
+    for (int32_t r = 0; r < n_rays; ++r) {
+        vt.clear();
+        vn.clear();
+        VecSink sink{&vt, &vn};
+        RayMarch m;
+        float term;
+        if (t_sorted == nullptr)
+            term = march_ray_single(m, sink, occ, rays_o + 3 * r, rays_d + 3 * r, near_planes[r], far_planes[r], aabbs, L, true);
+        else
+            term = march_ray_sorted(m, sink, occ, rays_o + 3 * r, rays_d + 3 * r, near_planes[r], far_planes[r], aabbs,
+                                    n_grids, t_sorted + (int64_t)r * 2 * n_grids, t_indices + (int64_t)r * 2 * n_grids,
+                                    hits + (int64_t)r * n_grids, L, true);
+        n_samples[r] = m.n_samples;
+        n_runs[r] = m.n_runs;
+        terminate[r] = term;
+        ok_flags[r] = m.ok ? 1 : 0;
+        if (total + (int64_t)vt.size() > run_capacity) return -1;
+        for (size_t q = 0; q < vt.size(); ++q) { run_t[total] = vt[q]; run_n[total] = vn[q]; ++total; }
+    }
+    return total;
+}
+
+}  // extern "C"
