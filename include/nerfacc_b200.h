@@ -1,0 +1,216 @@
+/*
+ * nerfacc_b200.h -- C ABI of libnerfacc_b200.so (hand-written sm_100a CUDA).
+ *
+ * This is the drop-in boundary for nerfacc's sampling + compositing hot path.
+ * Each entry point replaces one function of the reference's pybind11 module
+ * `nerfacc.csrc` / `nerfacc_cuda` (/root/reference/nerfacc/cuda/csrc/nerfacc.cpp:126-163)
+ * or one ATen composition in the reference's Python layer; the replaced
+ * interface is cited above every declaration (paths relative to /root/reference).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter says "host-visible";
+ *   - the library never allocates, frees or synchronises: the caller (PyTorch)
+ *     owns all inputs, outputs and workspaces and passes the stream to launch on;
+ *   - return value: 0 ok, < 0 argument error (NFA_ERR_*), > 0 a cudaError_t from
+ *     the launch.  Nothing is thrown or printed across the ABI;
+ *   - all index outputs are int64 (the reference's public dtype), floats are IEEE binary32.
+ */
+#ifndef NERFACC_B200_H_
+#define NERFACC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NFA_OK 0
+#define NFA_ERR_ARG (-1)         /* null pointer / negative size / inconsistent sizes */
+#define NFA_ERR_UNSUPPORTED (-2) /* valid request outside what this build implements */
+
+#define NFA_ABI_VERSION 1
+/* runs kept inline per ray by nfa_march(); rays with more are finished by nfa_march_fill() */
+#define NFA_RUN_SLOTS 8
+
+typedef void* nfa_stream_t; /* cudaStream_t */
+
+int32_t nfa_version(void);
+const char* nfa_error_string(int32_t code);
+
+/* ----------------------------------------------------------------------- */
+/* Ray / box intersection                                                   */
+/* ----------------------------------------------------------------------- */
+
+/* replaces: ray_aabb_intersect(rays_o, rays_d, aabbs, near, far, miss)
+ *   nerfacc/cuda/csrc/nerfacc.cpp:68-74, grid.cu:477-519 (kernel :284-313).
+ * t_mins, t_maxs: [n_rays, n_aabbs] f32; hits: [n_rays, n_aabbs] bool bytes. */
+int32_t nfa_ray_aabb_intersect(int32_t n_rays, const float* rays_o, const float* rays_d,
+                               int32_t n_aabbs, const float* aabbs,
+                               float near_plane, float far_plane, float miss_value,
+                               float* t_mins, float* t_maxs, uint8_t* hits, nfa_stream_t stream);
+
+/* replaces: the ray_aabb_intersect + torch.cat + torch.sort sequence of
+ *   nerfacc/grid.py:156-162 in one pass.  t_sorted: [n_rays, 2*n_aabbs] f32
+ *   ascending, t_indices: [n_rays, 2*n_aabbs] i64 (position in cat([t_mins, t_maxs])),
+ *   hits: [n_rays, n_aabbs].  n_aabbs <= 32. */
+int32_t nfa_intersect_sorted(int32_t n_rays, const float* rays_o, const float* rays_d,
+                             int32_t n_aabbs, const float* aabbs,
+                             float* t_sorted, int64_t* t_indices, uint8_t* hits, nfa_stream_t stream);
+
+/* ----------------------------------------------------------------------- */
+/* Occupancy grid: bool bytes -> 4x4x4 brick words                          */
+/* ----------------------------------------------------------------------- */
+
+/* Derived cache of OccGridEstimator.binaries (nerfacc/estimators/occ_grid.py:73-76):
+ * words  [nfa_occ_words()]        uint64, one per 4x4x4-cell brick,
+ * coarse [nfa_occ_coarse_words()] uint32, one bit per brick ("any cell set"). */
+int64_t nfa_occ_words(int32_t n_grids, int32_t rx, int32_t ry, int32_t rz);
+int64_t nfa_occ_coarse_words(int32_t n_grids, int32_t rx, int32_t ry, int32_t rz);
+int32_t nfa_occ_pack(int32_t n_grids, int32_t rx, int32_t ry, int32_t rz, const uint8_t* binaries,
+                     uint64_t* words, uint32_t* coarse, nfa_stream_t stream);
+
+/* ----------------------------------------------------------------------- */
+/* Grid traversal, constant step (cone_angle == 0, step_size > 0)           */
+/* ----------------------------------------------------------------------- */
+
+/* replaces: traverse_grids(...) nerfacc/cuda/csrc/nerfacc.cpp:75-96, grid.cu:320-474
+ *   (kernel :68-282) for the two-pass (exact allocation) mode.
+ *
+ * nfa_march: one DDA pass per ray.  Writes per-ray sample counts and the runs
+ *   (t_first, n) of consecutive samples into `workspace`, and the totals
+ *   totals[0] = n_samples, [1] = n_runs, [2] = rays with > NFA_RUN_SLOTS runs,
+ *   [3] = rays whose marching variable stopped advancing (reference would hang)
+ *   into `totals` (4 x int64; device memory or host-visible pinned memory).
+ *   t_sorted / t_indices / hits may be NULL when n_grids == 1 (crossings are
+ *   then computed in the kernel).  terminate_planes [n_rays] may be NULL.
+ *   workspace: nfa_march_workspace_bytes(n_rays) bytes, zero-filled once when
+ *   allocated (the kernels leave it reusable). */
+int64_t nfa_march_workspace_bytes(int32_t n_rays);
+int32_t nfa_march(int32_t n_rays, const float* rays_o, const float* rays_d,
+                  const float* near_planes, const float* far_planes,
+                  int32_t n_grids, int32_t rx, int32_t ry, int32_t rz,
+                  const uint64_t* words, const uint32_t* coarse, const float* aabbs,
+                  const float* t_sorted, const int64_t* t_indices, const uint8_t* hits,
+                  float step_size, void* workspace, int64_t* totals, float* terminate_planes,
+                  nfa_stream_t stream);
+
+/* nfa_expand_samples: runs -> packed (ray_indices, t_starts, t_ends) + packed_info.
+ *   replaces the fill pass plus `vals[is_left]`, `vals[is_right]` of
+ *   nerfacc/estimators/occ_grid.py:174-177.  Elements at index >= capacity are
+ *   not written (the caller re-runs with a larger buffer). packed_info: [n_rays, 2]. */
+int32_t nfa_expand_samples(int32_t n_rays, const void* workspace, float step_size, int64_t capacity,
+                           int64_t* packed_info, int64_t* ray_indices, float* t_starts, float* t_ends,
+                           nfa_stream_t stream);
+
+/* nfa_expand_intervals: runs -> the RaySegmentsSpec pair traverse_grids returns
+ *   (nerfacc/cuda/csrc/include/data_spec.hpp:6-16, nerfacc/data_specs.py:12-180):
+ *   intervals {vals, ray_indices, is_left, is_right, packed_info} with n_samples + n_runs
+ *   edges, samples {vals = midpoints, ray_indices, is_valid, packed_info}. */
+int32_t nfa_expand_intervals(int32_t n_rays, const void* workspace, float step_size,
+                             int64_t edge_capacity, int64_t sample_capacity,
+                             int64_t* iv_packed_info, float* iv_vals, int64_t* iv_ray_indices,
+                             uint8_t* iv_is_left, uint8_t* iv_is_right,
+                             int64_t* sm_packed_info, float* sm_vals, int64_t* sm_ray_indices,
+                             uint8_t* sm_is_valid, nfa_stream_t stream);
+
+/* nfa_march_fill: second DDA pass for the rays nfa_march flagged (more than
+ *   NFA_RUN_SLOTS runs); writes their samples / edges at the offsets the expand
+ *   call stored in packed_info.  Pass NULL for the output group not wanted. */
+int32_t nfa_march_fill(int32_t n_rays, const float* rays_o, const float* rays_d,
+                       const float* near_planes, const float* far_planes,
+                       int32_t n_grids, int32_t rx, int32_t ry, int32_t rz,
+                       const uint64_t* words, const uint32_t* coarse, const float* aabbs,
+                       const float* t_sorted, const int64_t* t_indices, const uint8_t* hits,
+                       float step_size, const void* workspace,
+                       int64_t sample_capacity, const int64_t* sm_packed_info,
+                       int64_t* ray_indices, float* t_starts, float* t_ends,
+                       int64_t edge_capacity, const int64_t* iv_packed_info,
+                       float* iv_vals, int64_t* iv_ray_indices, uint8_t* iv_is_left, uint8_t* iv_is_right,
+                       float* sm_vals, int64_t* sm_ray_indices, uint8_t* sm_is_valid,
+                       nfa_stream_t stream);
+
+/* ----------------------------------------------------------------------- */
+/* Volume rendering over the packed layout                                  */
+/* ----------------------------------------------------------------------- */
+
+/* replaces: the ATen composition of nerfacc/volrend.py:79-164 --
+ *   render_weight_from_density (:326-376 -> :219-278 -> exclusive_sum, scan.py:80-145,
+ *   native exclusive_sum / exclusive_sum_cub, nerfacc.cpp:15-21,49-53) or
+ *   render_weight_from_alpha (:281-323 -> exclusive_prod*, nerfacc.cpp:30-39,62-65),
+ *   followed by accumulate_along_rays x3 (:145-156,497-561), expected-depth
+ *   normalisation (:157-158) and background blend (:161-162).
+ * from_alpha == 0: `sigmas_or_alphas` holds sigmas and t_starts/t_ends are required;
+ * from_alpha != 0: it holds alphas (t_starts/t_ends only needed for depths).
+ * Nullable: rgbs, prefix_trans, bkgd[3], every output.  Per-sample outputs [N]
+ * (weights, trans, alphas), per-ray outputs colors [R,3], opacities [R], depths [R];
+ * raw [R,5] keeps the un-normalised (colour, opacity, depth) sums for the backward. */
+int32_t nfa_composite_fwd(int32_t n_rays, const int64_t* packed_info,
+                          const float* t_starts, const float* t_ends,
+                          const float* sigmas_or_alphas, int32_t from_alpha,
+                          const float* rgbs, const float* prefix_trans, const float* bkgd,
+                          int32_t expected_depths,
+                          float* weights, float* trans, float* alphas,
+                          float* colors, float* opacities, float* depths, float* raw,
+                          nfa_stream_t stream);
+
+/* replaces: the autograd graph of the above -- index_add_ backward (gather), mul
+ *   backward, _ExclusiveSumCUB.backward / _ExclusiveSum.backward (nerfacc/scan.py:307-337,
+ *   403-424; native exclusive_sum[_cub](..., backward=true)), the product-scan backwards
+ *   (nerfacc.cpp:26-39,57-65; scan.cu:167-304), exp/mul backward.
+ * Upstream gradients (all nullable): g_colors [R,3], g_opacities [R], g_depths [R] on the
+ * values nfa_composite_fwd returned (needs `raw`), g_weights / g_trans / g_alphas [N] on
+ * the per-sample outputs.  Outputs: g_in [N] (d/dsigma or d/dalpha), g_rgbs [N,3] (nullable). */
+int32_t nfa_composite_bwd(int32_t n_rays, const int64_t* packed_info,
+                          const float* t_starts, const float* t_ends,
+                          const float* sigmas_or_alphas, int32_t from_alpha,
+                          const float* rgbs, const float* prefix_trans, const float* bkgd,
+                          int32_t expected_depths, const float* raw,
+                          const float* g_colors, const float* g_opacities, const float* g_depths,
+                          const float* g_weights, const float* g_trans, const float* g_alphas,
+                          float* g_in, float* g_rgbs, nfa_stream_t stream);
+
+/* replaces: accumulate_along_rays (nerfacc/volrend.py:497-561): out[r, :] = sum_i w_i v_i.
+ *   _fwd: segmented (grouped samples, packed_info), deterministic, out fully written.
+ *   _atomic: any ray_indices order, float atomics into a zero-filled (or, for the
+ *            in-place variant volrend.py:564-587, pre-filled) `out`.
+ *   _bwd: g_weights [N] and g_values [N,dim] (nullable) from g_out [R,dim].
+ * values == NULL means accumulate the weights themselves (dim must be 1). */
+int32_t nfa_accumulate_fwd(int32_t n_rays, const int64_t* packed_info, const float* weights,
+                           const float* values, int32_t dim, float* out, nfa_stream_t stream);
+int32_t nfa_accumulate_atomic(int64_t n, const int64_t* ray_indices, const float* weights,
+                              const float* values, int32_t dim, float* out, nfa_stream_t stream);
+int32_t nfa_accumulate_bwd(int64_t n, const int64_t* ray_indices, const float* weights,
+                           const float* values, int32_t dim, const float* g_out,
+                           float* g_weights, float* g_values, nfa_stream_t stream);
+
+/* ----------------------------------------------------------------------- */
+/* Segmented scans and pack_info                                            */
+/* ----------------------------------------------------------------------- */
+
+/* replaces: inclusive_sum / exclusive_sum (chunk_starts, chunk_cnts, inputs, normalize, backward)
+ *   and {in,ex}clusive_prod_forward  -- nerfacc/cuda/csrc/nerfacc.cpp:8-39, scan.cu:9-304.
+ *   reverse != 0 scans every chunk from its last element (what `backward=true` does).
+ *   The product backwards are composed in Python from a reverse sum scan, as scan.cu:199-210 does. */
+int32_t nfa_scan_packed(int32_t n_rays, const int64_t* packed_info, const float* in, float* out,
+                        int32_t op_prod, int32_t inclusive, int32_t reverse, int32_t normalize,
+                        nfa_stream_t stream);
+
+/* replaces: {in,ex}clusive_sum_cub(indices, inputs, backward), {in,ex}clusive_prod_cub_forward
+ *   -- nerfacc.cpp:41-65, scan_cub.cu:59-287 (cub::DeviceScan::*ByKey).  A segment is a
+ *   maximal run of equal consecutive keys.  workspace: nfa_scan_by_key_workspace_bytes(n). */
+int64_t nfa_scan_by_key_workspace_bytes(int64_t n);
+int32_t nfa_scan_by_key(int64_t n, const int64_t* keys, const float* in, float* out,
+                        int32_t op_prod, int32_t inclusive, int32_t reverse, void* workspace,
+                        nfa_stream_t stream);
+
+/* replaces: pack_info (nerfacc/pack.py:38-46: zeros + index_add_ + cumsum + stack).
+ *   packed_info [n_rays, 2] = (chunk_start, chunk_cnt).  workspace:
+ *   nfa_pack_info_workspace_bytes(n_rays).  Indices outside [0, n_rays) are ignored. */
+int64_t nfa_pack_info_workspace_bytes(int32_t n_rays);
+int32_t nfa_pack_info(int64_t n, const int64_t* ray_indices, int32_t n_rays, int64_t* packed_info,
+                      void* workspace, nfa_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NERFACC_B200_H_ */

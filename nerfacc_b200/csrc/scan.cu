@@ -1,0 +1,493 @@
+// scan.cu -- segmented scans over the packed layout, pack_info.
+//
+// replaces (paths relative to /root/reference):
+//   nerfacc/cuda/csrc/scan.cu:9-304 + include/utils_scan.cuh:21-263
+//       (packed_info flavour: {in,ex}clusive_{sum,prod}, forward and the
+//        reverse-iterator backward launches)
+//   nerfacc/cuda/csrc/scan_cub.cu:59-287 (ray-index flavour, CUB DeviceScan::*ByKey)
+//   nerfacc/pack.py:38-46 (pack_info = index_add_ + cumsum)
+//
+// Packed flavour: one warp per ray, shuffle scan per 32-element tile with a
+// running carry; no shared memory and no block barriers (the reference's
+// Blelloch-in-smem kernel syncs under divergent control flow).
+// Key flavour: tile-local segmented scan + tiny carry pass + fix-up of each
+// tile's leading open segment (one pass over the data plus a few elements).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/nerfacc_b200.h"
+
+namespace nfa {
+
+constexpr unsigned kFullMask = 0xffffffffu;
+constexpr int kScanWarps = 8;
+
+template <bool kProd>
+__device__ __forceinline__ float op_apply(float a, float b) { return kProd ? a * b : a + b; }
+template <bool kProd>
+__device__ __forceinline__ float op_identity() { return kProd ? 1.0f : 0.0f; }
+
+// ---------------------------------------------------------------------------
+// packed_info flavour
+// ---------------------------------------------------------------------------
+template <bool kProd, bool kInclusive, bool kReverse>
+__global__ void __launch_bounds__(kScanWarps * 32) scan_packed_kernel(int32_t n_rays,
+                                                                      const int64_t* __restrict__ packed_info,
+                                                                      const float* __restrict__ in,
+                                                                      float* __restrict__ out, int32_t normalize)
+{
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * kScanWarps + (threadIdx.x >> 5);
+    if (r >= n_rays) return;
+    const longlong2 pi = *reinterpret_cast<const longlong2*>(packed_info + 2 * (int64_t)r);
+    const int64_t start = pi.x, n = pi.y;
+    float carry = op_identity<kProd>();
+    for (int64_t base = 0; base < n; base += 32) {
+        const int64_t j = base + lane;
+        const bool valid = j < n;
+        const int64_t k = kReverse ? start + n - 1 - j : start + j;
+        const float x = valid ? __ldg(in + k) : op_identity<kProd>();
+        float incl = x;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const float y = __shfl_up_sync(kFullMask, incl, s);
+            if (lane >= s) incl = op_apply<kProd>(y, incl);
+        }
+        float res;
+        if (kInclusive) {
+            res = op_apply<kProd>(carry, incl);
+        } else {
+            float excl = __shfl_up_sync(kFullMask, incl, 1);
+            if (lane == 0) excl = op_identity<kProd>();
+            res = op_apply<kProd>(carry, excl);
+        }
+        if (valid) out[k] = res;
+        carry = op_apply<kProd>(carry, __shfl_sync(kFullMask, incl, 31));
+    }
+    if (normalize) {  // reference utils_scan.cuh:102-109 (forward inclusive sum only)
+        const float tot = fmaxf(carry, 1e-10f);
+        __syncwarp();
+        for (int64_t j = lane; j < n; j += 32) out[start + j] = out[start + j] / tot;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// key (ray index) flavour: a segment is a maximal run of equal consecutive keys
+// ---------------------------------------------------------------------------
+constexpr int kKeyThreads = 256;
+constexpr int kKeyItems = 8;
+constexpr int kKeyTile = kKeyThreads * kKeyItems;
+
+struct KeyTileState {
+    float agg;        // scan value of the tile's trailing open segment
+    int32_t has_head; // tile contains a segment head
+    int32_t lead;     // number of leading elements that belong to the previous tile's segment
+    int32_t pad;
+};
+
+template <bool kProd>
+struct SegPair {
+    float v;
+    int f;
+};
+template <bool kProd>
+__device__ __forceinline__ SegPair<kProd> seg_combine(SegPair<kProd> a, SegPair<kProd> b)
+{
+    SegPair<kProd> r;
+    r.v = b.f ? b.v : op_apply<kProd>(a.v, b.v);
+    r.f = a.f | b.f;
+    return r;
+}
+
+// pass 1: tile-local segmented scan (logical order; physical index = n-1-j when reversed)
+template <bool kProd, bool kInclusive, bool kReverse>
+__global__ void __launch_bounds__(kKeyThreads) scan_bykey_tile_kernel(int64_t n, const int64_t* __restrict__ keys,
+                                                                      const float* __restrict__ in,
+                                                                      float* __restrict__ out,
+                                                                      KeyTileState* __restrict__ tiles)
+{
+    __shared__ float s_v[kKeyThreads / 32];
+    __shared__ int s_f[kKeyThreads / 32];
+    __shared__ int s_first_head;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t tile0 = (int64_t)blockIdx.x * kKeyTile;
+    const int64_t j0 = tile0 + (int64_t)tid * kKeyItems;
+    if (tid == 0) s_first_head = kKeyTile;
+    __syncthreads();
+
+    float x[kKeyItems];
+    int head[kKeyItems];
+    int64_t prev_key = 0;
+    bool have_prev = false;
+    if (j0 > 0 && j0 - 1 < n) {
+        prev_key = keys[kReverse ? n - 1 - (j0 - 1) : (j0 - 1)];
+        have_prev = true;
+    }
+    SegPair<kProd> acc;
+    acc.v = op_identity<kProd>();
+    acc.f = 0;
+    float res[kKeyItems];
+    int first_head_local = kKeyTile;
+#pragma unroll
+    for (int e = 0; e < kKeyItems; ++e) {
+        const int64_t j = j0 + e;
+        if (j < n) {
+            const int64_t k = kReverse ? n - 1 - j : j;
+            const int64_t key = keys[k];
+            x[e] = in[k];
+            head[e] = (!have_prev || key != prev_key) ? 1 : 0;
+            if (j == 0) head[e] = 1;
+            prev_key = key;
+            have_prev = true;
+        } else {
+            x[e] = op_identity<kProd>();
+            head[e] = 0;
+        }
+        if (head[e] && first_head_local == kKeyTile) first_head_local = tid * kKeyItems + e;
+        // thread-local segmented inclusive scan
+        if (head[e]) {
+            acc.v = x[e];
+            acc.f = 1;
+        } else {
+            acc.v = op_apply<kProd>(acc.v, x[e]);
+        }
+        res[e] = acc.v;
+    }
+    // block-level segmented inclusive scan of the per-thread aggregates
+    SegPair<kProd> incl = acc;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        SegPair<kProd> y;
+        y.v = __shfl_up_sync(kFullMask, incl.v, s);
+        y.f = __shfl_up_sync(kFullMask, incl.f, s);
+        if (lane >= s) incl = seg_combine<kProd>(y, incl);
+    }
+    if (lane == 31) {
+        s_v[warp] = incl.v;
+        s_f[warp] = incl.f;
+    }
+    if (first_head_local != kKeyTile) atomicMin(&s_first_head, first_head_local);
+    __syncthreads();
+    // exclusive prefix (over threads) = combine of previous warps, then previous lanes
+    SegPair<kProd> pre;
+    pre.v = op_identity<kProd>();
+    pre.f = 0;
+    for (int w = 0; w < warp; ++w) {
+        SegPair<kProd> y;
+        y.v = s_v[w];
+        y.f = s_f[w];
+        pre = seg_combine<kProd>(pre, y);
+    }
+    {
+        SegPair<kProd> y;
+        y.v = __shfl_up_sync(kFullMask, incl.v, 1);
+        y.f = __shfl_up_sync(kFullMask, incl.f, 1);
+        if (lane > 0) pre = seg_combine<kProd>(pre, y);
+    }
+    // write results: elements before the thread's first head continue `pre`
+    bool open = true;  // still in the segment carried in from the previous thread
+    float run_prev = pre.v;  // inclusive value just before the current element within its segment
+#pragma unroll
+    for (int e = 0; e < kKeyItems; ++e) {
+        const int64_t j = j0 + e;
+        if (j >= n) break;
+        const int64_t k = kReverse ? n - 1 - j : j;
+        if (head[e]) open = false;
+        float incl_v;
+        if (open) incl_v = op_apply<kProd>(pre.v, res[e]);
+        else incl_v = res[e];
+        float outv;
+        if (kInclusive) outv = incl_v;
+        else outv = head[e] ? op_identity<kProd>() : run_prev;
+        out[k] = outv;
+        run_prev = incl_v;
+    }
+    // tile state: aggregate of the trailing open segment
+    if (tid == kKeyThreads - 1) {
+        const SegPair<kProd> tot = seg_combine<kProd>(pre, acc);
+        KeyTileState st;
+        st.agg = tot.v;
+        st.has_head = tot.f;
+        st.lead = 0;
+        st.pad = 0;
+        tiles[blockIdx.x].agg = st.agg;
+        tiles[blockIdx.x].has_head = st.has_head;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int64_t remaining = n - tile0;
+        const int in_tile = remaining < kKeyTile ? (int)remaining : kKeyTile;
+        tiles[blockIdx.x].lead = s_first_head < in_tile ? s_first_head : in_tile;
+    }
+}
+
+// pass 2: carry into each tile (single CTA, serial over tiles in chunks; n_tiles = N/2048)
+template <bool kProd>
+__global__ void __launch_bounds__(1024) scan_bykey_carry_kernel(int32_t n_tiles, const KeyTileState* __restrict__ tiles,
+                                                                float* __restrict__ carry)
+{
+    __shared__ float s_v[32];
+    __shared__ int s_f[32];
+    __shared__ float s_run_v;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_run_v = op_identity<kProd>();
+    __syncthreads();
+    for (int base = 0; base < n_tiles; base += 1024) {
+        const int t = base + tid;
+        SegPair<kProd> me;
+        me.v = op_identity<kProd>();
+        me.f = 0;
+        if (t < n_tiles) {
+            me.v = tiles[t].agg;
+            me.f = tiles[t].has_head;
+        }
+        SegPair<kProd> incl = me;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            SegPair<kProd> y;
+            y.v = __shfl_up_sync(kFullMask, incl.v, s);
+            y.f = __shfl_up_sync(kFullMask, incl.f, s);
+            if (lane >= s) incl = seg_combine<kProd>(y, incl);
+        }
+        if (lane == 31) {
+            s_v[warp] = incl.v;
+            s_f[warp] = incl.f;
+        }
+        __syncthreads();
+        SegPair<kProd> pre;
+        pre.v = s_run_v;
+        pre.f = 0;
+        for (int w = 0; w < warp; ++w) {
+            SegPair<kProd> y;
+            y.v = s_v[w];
+            y.f = s_f[w];
+            pre = seg_combine<kProd>(pre, y);
+        }
+        SegPair<kProd> y;
+        y.v = __shfl_up_sync(kFullMask, incl.v, 1);
+        y.f = __shfl_up_sync(kFullMask, incl.f, 1);
+        if (lane > 0) pre = seg_combine<kProd>(pre, y);
+        if (t < n_tiles) carry[t] = pre.v;  // value carried INTO tile t
+        __syncthreads();
+        if (tid == 1023) s_run_v = seg_combine<kProd>(pre, me).v;
+        __syncthreads();
+    }
+}
+
+// pass 3: fold the carry into each tile's leading open segment
+template <bool kProd, bool kReverse>
+__global__ void __launch_bounds__(kKeyThreads) scan_bykey_fix_kernel(int64_t n, const KeyTileState* __restrict__ tiles,
+                                                                     const float* __restrict__ carry,
+                                                                     float* __restrict__ out)
+{
+    const int t = blockIdx.x;
+    if (t == 0) return;
+    const int lead = tiles[t].lead;
+    const float c = carry[t];
+    const int64_t tile0 = (int64_t)t * kKeyTile;
+    for (int e = threadIdx.x; e < lead; e += kKeyThreads) {
+        const int64_t j = tile0 + e;
+        const int64_t k = kReverse ? n - 1 - j : j;
+        out[k] = op_apply<kProd>(c, out[k]);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// pack_info
+// ---------------------------------------------------------------------------
+constexpr int kPackTile = 1024;
+
+__global__ void __launch_bounds__(256) pack_count_kernel(int64_t n, const int64_t* __restrict__ ray_indices,
+                                                         int32_t n_rays, unsigned long long* __restrict__ counts)
+{
+    // warp-aggregated histogram: one atomic per run of equal keys inside a warp
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n_up = (n + 31) & ~(int64_t)31;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_up; i += stride) {
+        const bool valid = i < n;
+        const long long key = valid ? ray_indices[i] : -1;
+        const long long prev = __shfl_up_sync(kFullMask, key, 1);
+        const bool head = valid && (lane == 0 || prev != key);
+        const unsigned heads = __ballot_sync(kFullMask, head);
+        const unsigned valids = __ballot_sync(kFullMask, valid);
+        if (head && key >= 0 && key < n_rays) {
+            const unsigned later = heads & ~((2u << lane) - 1u);  // heads strictly after this lane
+            const int end = later ? __ffs(later) - 1 : (32 - __clz(valids));
+            atomicAdd(counts + key, (unsigned long long)(end - lane));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kPackTile) pack_tilesum_kernel(int32_t n_rays,
+                                                                const unsigned long long* __restrict__ counts,
+                                                                unsigned long long* __restrict__ tile_sums)
+{
+    __shared__ unsigned long long s[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r = blockIdx.x * kPackTile + tid;
+    unsigned long long v = r < n_rays ? counts[r] : 0ull;
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_xor_sync(kFullMask, v, sft);
+    if (lane == 0) s[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        v = s[lane];
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_xor_sync(kFullMask, v, sft);
+        if (lane == 0) tile_sums[blockIdx.x] = v;
+    }
+}
+
+__global__ void __launch_bounds__(kPackTile) pack_scan_kernel(int32_t n_rays,
+                                                             const unsigned long long* __restrict__ counts,
+                                                             const unsigned long long* __restrict__ tile_sums,
+                                                             int64_t* __restrict__ packed_info)
+{
+    __shared__ unsigned long long s[32];
+    __shared__ unsigned long long s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned long long b = 0;
+    for (int i = tid; i < (int)blockIdx.x; i += kPackTile) b += tile_sums[i];
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) b += __shfl_xor_sync(kFullMask, b, sft);
+    if (lane == 0) s[warp] = b;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < 32; ++w) t += s[w];
+        s_base = t;
+    }
+    __syncthreads();
+    const int r = blockIdx.x * kPackTile + tid;
+    const unsigned long long c = r < n_rays ? counts[r] : 0ull;
+    unsigned long long x = c;
+#pragma unroll
+    for (int sft = 1; sft < 32; sft <<= 1) {
+        const unsigned long long y = __shfl_up_sync(kFullMask, x, sft);
+        if (lane >= sft) x += y;
+    }
+    __syncthreads();
+    if (lane == 31) s[warp] = x;
+    __syncthreads();
+    unsigned long long pre = s_base;
+    for (int w = 0; w < warp; ++w) pre += s[w];
+    if (r < n_rays) {
+        longlong2 v;
+        v.x = (long long)(pre + x - c);
+        v.y = (long long)c;
+        *reinterpret_cast<longlong2*>(packed_info + 2 * (int64_t)r) = v;
+    }
+}
+
+}  // namespace nfa
+
+using namespace nfa;
+
+static inline int32_t launch_status_s()
+{
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? NFA_OK : (int32_t)e;
+}
+
+template <bool kProd, bool kInclusive>
+static void launch_packed(bool reverse, int32_t n_rays, const int64_t* pi, const float* in, float* out,
+                          int32_t normalize, cudaStream_t s)
+{
+    const int blocks = (n_rays + kScanWarps - 1) / kScanWarps;
+    if (reverse) scan_packed_kernel<kProd, kInclusive, true><<<blocks, kScanWarps * 32, 0, s>>>(n_rays, pi, in, out, normalize);
+    else scan_packed_kernel<kProd, kInclusive, false><<<blocks, kScanWarps * 32, 0, s>>>(n_rays, pi, in, out, normalize);
+}
+
+template <bool kProd, bool kInclusive, bool kReverse>
+static void launch_bykey(int64_t n, const int64_t* keys, const float* in, float* out, void* workspace, cudaStream_t s)
+{
+    const int n_tiles = (int)((n + kKeyTile - 1) / kKeyTile);
+    KeyTileState* tiles = (KeyTileState*)workspace;
+    float* carry = (float*)((char*)workspace + (((int64_t)n_tiles * (int64_t)sizeof(KeyTileState) + 15) & ~(int64_t)15));
+    scan_bykey_tile_kernel<kProd, kInclusive, kReverse><<<n_tiles, kKeyThreads, 0, s>>>(n, keys, in, out, tiles);
+    if (n_tiles > 1) {
+        scan_bykey_carry_kernel<kProd><<<1, 1024, 0, s>>>(n_tiles, tiles, carry);
+        scan_bykey_fix_kernel<kProd, kReverse><<<n_tiles, kKeyThreads, 0, s>>>(n, tiles, carry, out);
+    }
+}
+
+extern "C" {
+
+int32_t nfa_scan_packed(int32_t n_rays, const int64_t* packed_info, const float* in, float* out, int32_t op_prod,
+                        int32_t inclusive, int32_t reverse, int32_t normalize, nfa_stream_t stream)
+{
+    if (n_rays < 0) return NFA_ERR_ARG;
+    if (n_rays == 0) return NFA_OK;
+    if (!packed_info || !in || !out) return NFA_ERR_ARG;
+    if ((((uintptr_t)packed_info) & 15u) != 0) return NFA_ERR_ARG;
+    if (normalize && (op_prod || !inclusive || reverse)) return NFA_ERR_UNSUPPORTED;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (op_prod) {
+        if (inclusive) launch_packed<true, true>(reverse, n_rays, packed_info, in, out, normalize, s);
+        else launch_packed<true, false>(reverse, n_rays, packed_info, in, out, normalize, s);
+    } else {
+        if (inclusive) launch_packed<false, true>(reverse, n_rays, packed_info, in, out, normalize, s);
+        else launch_packed<false, false>(reverse, n_rays, packed_info, in, out, normalize, s);
+    }
+    return launch_status_s();
+}
+
+int64_t nfa_scan_by_key_workspace_bytes(int64_t n)
+{
+    if (n <= 0) return 16;
+    const int64_t n_tiles = (n + kKeyTile - 1) / kKeyTile;
+    return ((n_tiles * (int64_t)sizeof(KeyTileState) + 15) & ~(int64_t)15) + ((n_tiles * 4 + 15) & ~(int64_t)15);
+}
+
+int32_t nfa_scan_by_key(int64_t n, const int64_t* keys, const float* in, float* out, int32_t op_prod,
+                        int32_t inclusive, int32_t reverse, void* workspace, nfa_stream_t stream)
+{
+    if (n < 0) return NFA_ERR_ARG;
+    if (n == 0) return NFA_OK;
+    if (!keys || !in || !out || !workspace) return NFA_ERR_ARG;
+    if (n > (int64_t)kKeyTile * INT32_MAX) return NFA_ERR_UNSUPPORTED;
+    cudaStream_t s = (cudaStream_t)stream;
+#define NFA_BYKEY(P, I, R) launch_bykey<P, I, R>(n, keys, in, out, workspace, s)
+    if (op_prod) {
+        if (inclusive) { if (reverse) NFA_BYKEY(true, true, true); else NFA_BYKEY(true, true, false); }
+        else { if (reverse) NFA_BYKEY(true, false, true); else NFA_BYKEY(true, false, false); }
+    } else {
+        if (inclusive) { if (reverse) NFA_BYKEY(false, true, true); else NFA_BYKEY(false, true, false); }
+        else { if (reverse) NFA_BYKEY(false, false, true); else NFA_BYKEY(false, false, false); }
+    }
+#undef NFA_BYKEY
+    return launch_status_s();
+}
+
+int64_t nfa_pack_info_workspace_bytes(int32_t n_rays)
+{
+    if (n_rays <= 0) return 16;
+    const int64_t tiles = (n_rays + kPackTile - 1) / kPackTile;
+    return (int64_t)n_rays * 8 + tiles * 8 + 16;
+}
+
+int32_t nfa_pack_info(int64_t n, const int64_t* ray_indices, int32_t n_rays, int64_t* packed_info, void* workspace,
+                      nfa_stream_t stream)
+{
+    if (n < 0 || n_rays < 0) return NFA_ERR_ARG;
+    if (n_rays == 0) return NFA_OK;
+    if (!packed_info || !workspace || (n > 0 && !ray_indices)) return NFA_ERR_ARG;
+    if ((((uintptr_t)packed_info) & 15u) != 0) return NFA_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned long long* counts = (unsigned long long*)workspace;
+    const int tiles = (n_rays + kPackTile - 1) / kPackTile;
+    unsigned long long* tile_sums = counts + n_rays;
+    cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)n_rays * 8, s);
+    if (e != cudaSuccess) return (int32_t)e;
+    if (n > 0) {
+        const int64_t warps = (n + 31) / 32;
+        const int blocks = (int)((warps + 7) / 8 < 148 * 16 ? (warps + 7) / 8 : 148 * 16);
+        pack_count_kernel<<<blocks, 256, 0, s>>>(n, ray_indices, n_rays, counts);
+    }
+    pack_tilesum_kernel<<<tiles, kPackTile, 0, s>>>(n_rays, counts, tile_sums);
+    pack_scan_kernel<<<tiles, kPackTile, 0, s>>>(n_rays, counts, tile_sums, packed_info);
+    return launch_status_s();
+}
+
+}  // extern "C"

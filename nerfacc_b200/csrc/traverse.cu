@@ -1,0 +1,899 @@
+// traverse.cu -- occupancy-grid traversal kernels for sm_100a and their C ABI.
+//
+// Pipeline for one OccGridEstimator.sampling() call (reference
+// nerfacc/estimators/occ_grid.py:154-177 -> nerfacc/grid.py:93-192 ->
+// nerfacc/cuda/csrc/grid.cu:320-474):
+//
+//   occ_pack_kernel   bool grid -> 4x4x4 brick words + 1-bit/brick mip   (cached per grid version)
+//   march_kernel      1 thread / ray, 128 rays / CTA.  Ray tile and brick mip staged
+//                     into shared memory with cp.async.bulk (TMA 1-D) + mbarrier;
+//                     pure DDA walk, no per-sample work (march.cuh); writes per-ray
+//                     counts + runs, per-tile sums, and (last CTA) the grand totals.
+//   expand_kernel     1 CTA / 128-ray tile: tile offset from the tile sums + block
+//                     scan -> packed_info; warps turn runs into samples with
+//                     coalesced stores (expand.cuh).
+//   march_fill_kernel only for rays with more runs than fit inline.
+//
+// No tensor cores: the path has no dense contraction; it is bound by dependent
+// f32 chains (march) and by HBM stores (expand).  See DESIGN.md.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/nerfacc_b200.h"
+#include "expand.cuh"
+#include "march.cuh"
+#include "occ_pack.cuh"
+
+namespace nfa {
+
+constexpr int kTileRays = 128;      // rays per CTA in march / expand
+constexpr int kRunSlots = NFA_RUN_SLOTS;
+constexpr int kExpandThreads = 256;
+
+struct RunRec {
+    float t_first;
+    uint32_t n;
+};
+
+struct TileSum {
+    unsigned long long samples;
+    uint32_t runs;
+    uint32_t flags;  // low 16: rays over the slot limit; high 16: stuck rays
+};
+
+// Workspace layout (all offsets 16-byte aligned):
+//   [0, 64)                      header: u32 done_counter
+//   tile_sums [n_tiles]          TileSum
+//   cnt_samples [R] u32, cnt_runs [R] u32
+//   runs [R * kRunSlots]         RunRec
+struct Workspace {
+    uint32_t* done;
+    TileSum* tiles;
+    uint32_t* cnt_samples;
+    uint32_t* cnt_runs;
+    RunRec* runs;
+    int n_tiles;
+};
+
+__host__ __device__ inline int64_t align16(int64_t x) { return (x + 15) & ~(int64_t)15; }
+
+__host__ __device__ inline int64_t ws_bytes(int32_t n_rays)
+{
+    const int64_t nt = (n_rays + kTileRays - 1) / kTileRays;
+    return 64 + align16(nt * (int64_t)sizeof(TileSum)) + align16((int64_t)n_rays * 4) * 2 +
+           align16((int64_t)n_rays * kRunSlots * (int64_t)sizeof(RunRec));
+}
+
+__host__ __device__ inline Workspace ws_view(void* base, int32_t n_rays)
+{
+    Workspace w;
+    char* p = (char*)base;
+    w.n_tiles = (n_rays + kTileRays - 1) / kTileRays;
+    w.done = (uint32_t*)p;
+    p += 64;
+    w.tiles = (TileSum*)p;
+    p += align16(w.n_tiles * (int64_t)sizeof(TileSum));
+    w.cnt_samples = (uint32_t*)p;
+    p += align16((int64_t)n_rays * 4);
+    w.cnt_runs = (uint32_t*)p;
+    p += align16((int64_t)n_rays * 4);
+    w.runs = (RunRec*)p;
+    return w;
+}
+
+// ---------------------------------------------------------------------------
+// small PTX wrappers: mbarrier + 1-D bulk async copy (TMA) global -> shared
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    // bounded: a lost completion must fault, not hang the GPU
+    for (int spin = 0; spin < (1 << 22); ++spin) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// occupancy packing
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) occ_pack_kernel(OccGeom g, const uint8_t* __restrict__ binaries,
+                                                       uint64_t* __restrict__ words, uint32_t* __restrict__ coarse,
+                                                       int64_t n_words, int64_t n_coarse)
+{
+    const int64_t cells = (int64_t)g.res[0] * g.res[1] * g.res[2];
+    // one thread per brick; a warp's 32 bricks share one coarse word
+    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_coarse * 32;
+         b += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t w = 0;
+        if (b < n_words) {
+            const int level = (int)(b / g.wpl);
+            int rem = (int)(b - (int64_t)level * g.wpl);
+            const int bz = rem % g.nb[2];
+            rem /= g.nb[2];
+            const int by = rem % g.nb[1];
+            const int bx = rem / g.nb[1];
+            w = occ_brick_word(binaries + level * cells, g, bx, by, bz);
+            words[b] = w;
+        }
+        const uint32_t any = __ballot_sync(0xffffffffu, w != 0);
+        if ((threadIdx.x & 31) == 0) coarse[b >> 5] = any;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// march
+// ---------------------------------------------------------------------------
+struct MarchParams {
+    int32_t n_rays;
+    const float* rays_o;
+    const float* rays_d;
+    const float* near_planes;
+    const float* far_planes;
+    OccGeom g;
+    const uint64_t* words;
+    const uint32_t* coarse;
+    int32_t coarse_words;  // padded count (multiple of 4)
+    const float* aabbs;
+    const float* t_sorted;
+    const int64_t* t_indices;
+    const uint8_t* hits;
+    float step_size;
+    Workspace ws;
+    int64_t* totals;
+    float* terminate;
+};
+
+struct SlotSink {
+    RunRec* slots;
+    __device__ __forceinline__ void push(uint32_t q, float t_first, uint32_t n)
+    {
+        if (q < (uint32_t)kRunSlots) {
+            RunRec r;
+            r.t_first = t_first;
+            r.n = n;
+            slots[q] = r;
+        }
+    }
+};
+
+template <bool kSmemCoarse>
+__global__ void __launch_bounds__(kTileRays) march_kernel(const MarchParams p)
+{
+    extern __shared__ __align__(16) uint32_t s_coarse[];
+    __shared__ __align__(16) float s_o[kTileRays * 3];
+    __shared__ __align__(16) float s_d[kTileRays * 3];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ unsigned long long s_red_samples[kTileRays / 32];
+    __shared__ uint32_t s_red_runs[kTileRays / 32], s_red_flags[kTileRays / 32];
+    __shared__ bool s_last;
+
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x;
+    const int r0 = tile * kTileRays;
+    const int nr = min(kTileRays, p.n_rays - r0);
+    const int r = r0 + tid;
+
+    // ---- stage the ray tile (and the brick mip) into shared memory -------
+    const float* g_o = p.rays_o + (int64_t)r0 * 3;
+    const float* g_d = p.rays_d + (int64_t)r0 * 3;
+    const uint32_t ray_bytes = (uint32_t)nr * 12u;
+    const bool bulk_rays = ((ray_bytes & 15u) == 0u) && ((((uintptr_t)g_o) | ((uintptr_t)g_d)) & 15u) == 0u;
+    const bool bulk_coarse = kSmemCoarse && ((((uintptr_t)p.coarse) & 15u) == 0u);
+    if (tid == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t bytes = 0;
+        if (bulk_rays) bytes += 2u * ray_bytes;
+        if (bulk_coarse) bytes += (uint32_t)p.coarse_words * 4u;
+        mbar_expect_tx(&s_bar, bytes);
+        if (bulk_rays) {
+            bulk_g2s(s_o, g_o, ray_bytes, &s_bar);
+            bulk_g2s(s_d, g_d, ray_bytes, &s_bar);
+        }
+        if (bulk_coarse) bulk_g2s(s_coarse, p.coarse, (uint32_t)p.coarse_words * 4u, &s_bar);
+    }
+    if (!bulk_rays) {
+        for (int i = tid; i < nr * 3; i += kTileRays) {
+            s_o[i] = g_o[i];
+            s_d[i] = g_d[i];
+        }
+    }
+    if (kSmemCoarse && !bulk_coarse) {
+        for (int i = tid; i < p.coarse_words; i += kTileRays) s_coarse[i] = p.coarse[i];
+    }
+    float near = 0.f, far = 0.f;
+    if (tid < nr) {
+        near = p.near_planes[r];
+        far = p.far_planes[r];
+    }
+    mbar_wait(&s_bar, 0);
+    __syncthreads();
+
+    // ---- per-ray march ----------------------------------------------------
+    uint32_t n_samples = 0, n_runs = 0, flags = 0;
+    if (tid < nr) {
+        OccView occ;
+        occ.words = p.words;
+        occ.coarse = kSmemCoarse ? s_coarse : p.coarse;
+        occ.g = p.g;
+        const float o[3] = {s_o[tid * 3 + 0], s_o[tid * 3 + 1], s_o[tid * 3 + 2]};
+        const float d[3] = {s_d[tid * 3 + 0], s_d[tid * 3 + 1], s_d[tid * 3 + 2]};
+        const Lattice L = lat_make(p.step_size);
+        SlotSink sink;
+        sink.slots = p.ws.runs + (int64_t)r * kRunSlots;
+        RayMarch m;
+        float term;
+        const bool want_term = p.terminate != nullptr;
+        if (p.t_sorted == nullptr) {
+            term = march_ray_single(m, sink, occ, o, d, near, far, p.aabbs, L, want_term);
+        } else {
+            const int G = p.g.n_grids;
+            term = march_ray_sorted(m, sink, occ, o, d, near, far, p.aabbs, G, p.t_sorted + (int64_t)r * 2 * G,
+                                    p.t_indices + (int64_t)r * 2 * G, p.hits + (int64_t)r * G, L, want_term);
+        }
+        n_samples = m.n_samples;
+        n_runs = m.n_runs;
+        flags = (n_runs > (uint32_t)kRunSlots ? 1u : 0u) | (m.ok ? 0u : 0x10000u);
+        p.ws.cnt_samples[r] = n_samples;
+        p.ws.cnt_runs[r] = n_runs;
+        if (want_term) p.terminate[r] = term;
+    }
+
+    // ---- tile sums, and grand totals by the last CTA to finish ------------
+    unsigned long long vs = n_samples;
+    uint32_t vr = n_runs, vf = flags;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        vs += __shfl_xor_sync(0xffffffffu, vs, s);
+        vr += __shfl_xor_sync(0xffffffffu, vr, s);
+        vf += __shfl_xor_sync(0xffffffffu, vf, s);
+    }
+    if ((tid & 31) == 0) {
+        s_red_samples[tid >> 5] = vs;
+        s_red_runs[tid >> 5] = vr;
+        s_red_flags[tid >> 5] = vf;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        TileSum ts;
+        ts.samples = 0;
+        ts.runs = 0;
+        ts.flags = 0;
+        for (int w = 0; w < kTileRays / 32; ++w) {
+            ts.samples += s_red_samples[w];
+            ts.runs += s_red_runs[w];
+            ts.flags += s_red_flags[w];
+        }
+        p.ws.tiles[tile] = ts;
+        __threadfence();
+        const uint32_t prev = atomicAdd(p.ws.done, 1u);
+        s_last = (prev == (uint32_t)(gridDim.x - 1));
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        unsigned long long a = 0, b = 0, c = 0, e = 0;
+        for (int i = tid; i < p.ws.n_tiles; i += kTileRays) {
+            const volatile unsigned long long* q = (const volatile unsigned long long*)&p.ws.tiles[i];
+            const unsigned long long w0 = q[0], w1 = q[1];  // {samples}, {runs | flags << 32}
+            a += w0;
+            b += (uint32_t)w1;
+            c += (w1 >> 32) & 0xffffu;
+            e += w1 >> 48;
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, s);
+            b += __shfl_xor_sync(0xffffffffu, b, s);
+            c += __shfl_xor_sync(0xffffffffu, c, s);
+            e += __shfl_xor_sync(0xffffffffu, e, s);
+        }
+        __shared__ unsigned long long s_tot[4][kTileRays / 32];
+        if ((tid & 31) == 0) {
+            s_tot[0][tid >> 5] = a;
+            s_tot[1][tid >> 5] = b;
+            s_tot[2][tid >> 5] = c;
+            s_tot[3][tid >> 5] = e;
+        }
+        __syncthreads();
+        if (tid < 4) {
+            unsigned long long v = 0;
+            for (int w = 0; w < kTileRays / 32; ++w) v += s_tot[tid][w];
+            p.totals[tid] = (int64_t)v;
+            __threadfence_system();
+        }
+        if (tid == 0) *p.ws.done = 0u;  // leave the workspace reusable
+    }
+}
+
+// ---------------------------------------------------------------------------
+// expand
+// ---------------------------------------------------------------------------
+struct ExpandParams {
+    int32_t n_rays;
+    Workspace ws;
+    float step_size;
+    // samples-only mode
+    int64_t sample_capacity;
+    int64_t* sm_packed_info;
+    int64_t* ray_indices;
+    float* t_starts;
+    float* t_ends;
+    // interval mode (kIntervals)
+    int64_t edge_capacity;
+    int64_t* iv_packed_info;
+    float* iv_vals;
+    int64_t* iv_ray_indices;
+    uint8_t* iv_is_left;
+    uint8_t* iv_is_right;
+    float* sm_vals;
+    uint8_t* sm_is_valid;
+};
+
+template <bool kIntervals>
+__global__ void __launch_bounds__(kExpandThreads) expand_kernel(const ExpandParams p)
+{
+    __shared__ unsigned long long s_red[2][kExpandThreads / 32];
+    __shared__ unsigned long long s_base[2];
+    __shared__ unsigned long long s_off[kTileRays];   // sample offset of each ray in the tile
+    __shared__ unsigned long long s_eoff[kTileRays];  // edge offset (interval mode)
+    __shared__ uint32_t s_wsum[2][kTileRays / 32];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x;
+    const int r0 = tile * kTileRays;
+    const int nr = min(kTileRays, p.n_rays - r0);
+
+    // tile base = sum of the sums of all earlier tiles
+    unsigned long long a = 0, b = 0;
+    for (int i = tid; i < tile; i += kExpandThreads) {
+        const TileSum ts = p.ws.tiles[i];
+        a += ts.samples;
+        b += ts.runs;
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, s);
+        b += __shfl_xor_sync(0xffffffffu, b, s);
+    }
+    if (lane == 0) {
+        s_red[0][warp] = a;
+        s_red[1][warp] = b;
+    }
+    // in-tile exclusive scan of the per-ray counts (first 4 warps)
+    uint32_t cs = 0, cr = 0, xs = 0, xr = 0;
+    if (tid < kTileRays) {
+        if (tid < nr) {
+            cs = p.ws.cnt_samples[r0 + tid];
+            cr = p.ws.cnt_runs[r0 + tid];
+        }
+        xs = cs;
+        xr = cr;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const uint32_t ys = __shfl_up_sync(0xffffffffu, xs, s);
+            const uint32_t yr = __shfl_up_sync(0xffffffffu, xr, s);
+            if (lane >= s) {
+                xs += ys;
+                xr += yr;
+            }
+        }
+        if (lane == 31) {
+            s_wsum[0][warp] = xs;
+            s_wsum[1][warp] = xr;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long ta = 0, tb = 0;
+        for (int w = 0; w < kExpandThreads / 32; ++w) {
+            ta += s_red[0][w];
+            tb += s_red[1][w];
+        }
+        s_base[0] = ta;
+        s_base[1] = tb;
+    }
+    __syncthreads();
+    if (tid < kTileRays) {
+        unsigned long long ws = 0, wr = 0;
+        for (int w = 0; w < warp; ++w) {
+            ws += s_wsum[0][w];
+            wr += s_wsum[1][w];
+        }
+        const unsigned long long off = s_base[0] + ws + (xs - cs);
+        const unsigned long long eoff = off + s_base[1] + wr + (xr - cr);
+        s_off[tid] = off;
+        s_eoff[tid] = eoff;
+        if (tid < nr) {
+            // packed_info = [chunk_start, chunk_cnt]  (reference data_specs.py:68-69)
+            longlong2 v;
+            v.x = (long long)off;
+            v.y = (long long)cs;
+            *reinterpret_cast<longlong2*>(p.sm_packed_info + 2 * (int64_t)(r0 + tid)) = v;
+            if (kIntervals) {
+                longlong2 e;
+                e.x = (long long)eoff;
+                e.y = (long long)cs + (long long)cr;
+                *reinterpret_cast<longlong2*>(p.iv_packed_info + 2 * (int64_t)(r0 + tid)) = e;
+            }
+        }
+    }
+    __syncthreads();
+
+    const Lattice L = lat_make(p.step_size);
+    for (int lr = warp; lr < nr; lr += kExpandThreads / 32) {
+        const int r = r0 + lr;
+        const uint32_t n_runs = p.ws.cnt_runs[r];
+        if (n_runs == 0 || n_runs > (uint32_t)kRunSlots) continue;  // the latter: nfa_march_fill
+        int64_t off = (int64_t)s_off[lr];
+        int64_t eoff = (int64_t)s_eoff[lr];
+        const RunRec* runs = p.ws.runs + (int64_t)r * kRunSlots;
+        for (uint32_t q = 0; q < n_runs; ++q) {
+            const RunRec run = runs[q];
+            RunIter it;
+            it.t = run.t_first;
+            it.left = run.n;
+            bool first_piece = true;
+            while (it.left > 0) {
+                LatPiece pc;
+                const uint32_t c = run_next_piece(L, it, pc);
+                for (uint32_t j = lane; j < c; j += 32) {
+                    const float ts = piece_start(pc, j);
+                    const float te = f_add(ts, L.dt);
+                    const int64_t k = off + j;
+                    if (!kIntervals) {
+                        if (k < p.sample_capacity) {
+                            p.ray_indices[k] = r;
+                            p.t_starts[k] = ts;
+                            p.t_ends[k] = te;
+                        }
+                    } else {
+                        if (k < p.sample_capacity) {
+                            p.ray_indices[k] = r;  // samples.ray_indices
+                            p.sm_vals[k] = f_mul(f_add(te, ts), 0.5f);  // reference grid.cu:251
+                            p.sm_is_valid[k] = 1;
+                        }
+                        const int64_t e = eoff + j;
+                        if (e < p.edge_capacity) {
+                            // left edge of sample j (reference grid.cu:219-245)
+                            p.iv_vals[e] = ts;
+                            p.iv_ray_indices[e] = r;
+                            p.iv_is_left[e] = 1;
+                            p.iv_is_right[e] = (first_piece && j == 0) ? 0 : 1;
+                        }
+                        if (it.left == 0 && j == c - 1 && e + 1 < p.edge_capacity) {
+                            // closing edge of the run
+                            p.iv_vals[e + 1] = te;
+                            p.iv_ray_indices[e + 1] = r;
+                            p.iv_is_left[e + 1] = 0;
+                            p.iv_is_right[e + 1] = 1;
+                        }
+                    }
+                }
+                off += c;
+                eoff += c;
+                first_piece = false;
+            }
+            eoff += 1;  // the closing edge
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// second pass for rays with more runs than inline slots
+// ---------------------------------------------------------------------------
+struct FillParams {
+    MarchParams m;
+    ExpandParams e;
+    bool want_samples;    // (ray_indices, t_starts, t_ends)
+    bool want_intervals;  // interval-mode arrays
+};
+
+struct FillSink {
+    const FillParams* fp;
+    Lattice L;
+    int64_t ray;
+    int64_t off;   // next sample slot
+    int64_t eoff;  // next edge slot
+    __device__ __forceinline__ void push(uint32_t, float t_first, uint32_t n)
+    {
+        const ExpandParams& p = fp->e;
+        float t = t_first;
+        for (uint32_t j = 0; j < n; ++j) {
+            const float te = f_add(t, L.dt);
+            if (fp->want_samples && off < p.sample_capacity) {
+                p.ray_indices[off] = ray;
+                p.t_starts[off] = t;
+                p.t_ends[off] = te;
+            }
+            if (fp->want_intervals) {
+                if (off < p.sample_capacity) {
+                    p.ray_indices[off] = ray;
+                    p.sm_vals[off] = f_mul(f_add(te, t), 0.5f);
+                    p.sm_is_valid[off] = 1;
+                }
+                if (eoff < p.edge_capacity) {
+                    p.iv_vals[eoff] = t;
+                    p.iv_ray_indices[eoff] = ray;
+                    p.iv_is_left[eoff] = 1;
+                    p.iv_is_right[eoff] = j == 0 ? 0 : 1;
+                }
+                if (j == n - 1 && eoff + 1 < p.edge_capacity) {
+                    p.iv_vals[eoff + 1] = te;
+                    p.iv_ray_indices[eoff + 1] = ray;
+                    p.iv_is_left[eoff + 1] = 0;
+                    p.iv_is_right[eoff + 1] = 1;
+                }
+            }
+            t = te;
+            ++off;
+            ++eoff;
+        }
+        ++eoff;
+    }
+};
+
+__global__ void __launch_bounds__(128) march_fill_kernel(const FillParams fp)
+{
+    const MarchParams& p = fp.m;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= p.n_rays) return;
+    if (p.ws.cnt_runs[r] <= (uint32_t)kRunSlots) return;
+    OccView occ;
+    occ.words = p.words;
+    occ.coarse = p.coarse;
+    occ.g = p.g;
+    const float o[3] = {p.rays_o[3 * (int64_t)r], p.rays_o[3 * (int64_t)r + 1], p.rays_o[3 * (int64_t)r + 2]};
+    const float d[3] = {p.rays_d[3 * (int64_t)r], p.rays_d[3 * (int64_t)r + 1], p.rays_d[3 * (int64_t)r + 2]};
+    FillSink sink;
+    sink.fp = &fp;
+    sink.L = lat_make(p.step_size);
+    sink.ray = r;
+    sink.off = fp.e.sm_packed_info[2 * (int64_t)r];
+    sink.eoff = fp.want_intervals ? fp.e.iv_packed_info[2 * (int64_t)r] : 0;
+    RayMarch m;
+    if (p.t_sorted == nullptr) {
+        march_ray_single(m, sink, occ, o, d, p.near_planes[r], p.far_planes[r], p.aabbs, sink.L, false);
+    } else {
+        const int G = p.g.n_grids;
+        march_ray_sorted(m, sink, occ, o, d, p.near_planes[r], p.far_planes[r], p.aabbs, G,
+                         p.t_sorted + (int64_t)r * 2 * G, p.t_indices + (int64_t)r * 2 * G, p.hits + (int64_t)r * G,
+                         sink.L, false);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// ray / box kernels (reference grid.cu:284-313; grid.py:156-162)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ray_aabb_kernel(int32_t n_rays, const float* __restrict__ rays_o,
+                                                       const float* __restrict__ rays_d, int32_t n_aabbs,
+                                                       const float* __restrict__ aabbs, float near, float far,
+                                                       float miss, float* __restrict__ t_mins,
+                                                       float* __restrict__ t_maxs, uint8_t* __restrict__ hits)
+{
+    const int64_t total = (int64_t)n_rays * n_aabbs;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / n_aabbs;
+        const int g = (int)(i - r * n_aabbs);
+        const float o[3] = {rays_o[3 * r], rays_o[3 * r + 1], rays_o[3 * r + 2]};
+        const float inv[3] = {f_rcp(rays_d[3 * r]), f_rcp(rays_d[3 * r + 1]), f_rcp(rays_d[3 * r + 2])};
+        float a = miss, b = miss;
+        const bool hit = slab_test(o, inv, aabbs + 6 * g, near, far, a, b);
+        t_mins[i] = hit ? a : miss;
+        t_maxs[i] = hit ? b : miss;
+        hits[i] = hit ? 1 : 0;
+    }
+}
+
+constexpr int kMaxSortBoxes = 32;
+
+__global__ void __launch_bounds__(128) intersect_sorted_kernel(int32_t n_rays, const float* __restrict__ rays_o,
+                                                               const float* __restrict__ rays_d, int32_t n_aabbs,
+                                                               const float* __restrict__ aabbs,
+                                                               float* __restrict__ t_sorted,
+                                                               int64_t* __restrict__ t_indices,
+                                                               uint8_t* __restrict__ hits)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rays) return;
+    const float o[3] = {rays_o[3 * (int64_t)r], rays_o[3 * (int64_t)r + 1], rays_o[3 * (int64_t)r + 2]};
+    const float inv[3] = {f_rcp(rays_d[3 * (int64_t)r]), f_rcp(rays_d[3 * (int64_t)r + 1]),
+                          f_rcp(rays_d[3 * (int64_t)r + 2])};
+    float v[2 * kMaxSortBoxes];
+    int ix[2 * kMaxSortBoxes];
+    const int m = 2 * n_aabbs;
+    for (int g = 0; g < n_aabbs; ++g) {
+        float a = INFINITY, b = INFINITY;
+        const bool hit = slab_test(o, inv, aabbs + 6 * g, -INFINITY, INFINITY, a, b);
+        v[g] = hit ? a : INFINITY;
+        v[n_aabbs + g] = hit ? b : INFINITY;
+        hits[(int64_t)r * n_aabbs + g] = hit ? 1 : 0;
+    }
+    // stable insertion sort of (value, position in cat([t_mins, t_maxs]))
+    for (int j = 0; j < m; ++j) {
+        const float x = v[j];
+        int k = j;
+        while (k > 0 && v[k - 1] > x) {
+            v[k] = v[k - 1];
+            ix[k] = ix[k - 1];
+            --k;
+        }
+        v[k] = x;
+        ix[k] = j;
+    }
+    for (int j = 0; j < m; ++j) {
+        t_sorted[(int64_t)r * m + j] = v[j];
+        t_indices[(int64_t)r * m + j] = ix[j];
+    }
+}
+
+}  // namespace nfa
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+using namespace nfa;
+
+static inline int32_t launch_status()
+{
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? NFA_OK : (int32_t)e;
+}
+
+extern "C" {
+
+int32_t nfa_version(void) { return NFA_ABI_VERSION; }
+
+const char* nfa_error_string(int32_t code)
+{
+    if (code == NFA_OK) return "ok";
+    if (code == NFA_ERR_ARG) return "invalid argument";
+    if (code == NFA_ERR_UNSUPPORTED) return "unsupported configuration";
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "unknown error";
+}
+
+int32_t nfa_ray_aabb_intersect(int32_t n_rays, const float* rays_o, const float* rays_d, int32_t n_aabbs,
+                               const float* aabbs, float near_plane, float far_plane, float miss_value,
+                               float* t_mins, float* t_maxs, uint8_t* hits, nfa_stream_t stream)
+{
+    if (n_rays < 0 || n_aabbs < 0) return NFA_ERR_ARG;
+    const int64_t total = (int64_t)n_rays * n_aabbs;
+    if (total == 0) return NFA_OK;
+    if (!rays_o || !rays_d || !aabbs || !t_mins || !t_maxs || !hits) return NFA_ERR_ARG;
+    const int blocks = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+    ray_aabb_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(n_rays, rays_o, rays_d, n_aabbs, aabbs, near_plane,
+                                                               far_plane, miss_value, t_mins, t_maxs, hits);
+    return launch_status();
+}
+
+int32_t nfa_intersect_sorted(int32_t n_rays, const float* rays_o, const float* rays_d, int32_t n_aabbs,
+                             const float* aabbs, float* t_sorted, int64_t* t_indices, uint8_t* hits,
+                             nfa_stream_t stream)
+{
+    if (n_rays < 0 || n_aabbs <= 0) return NFA_ERR_ARG;
+    if (n_aabbs > kMaxSortBoxes) return NFA_ERR_UNSUPPORTED;
+    if (n_rays == 0) return NFA_OK;
+    if (!rays_o || !rays_d || !aabbs || !t_sorted || !t_indices || !hits) return NFA_ERR_ARG;
+    intersect_sorted_kernel<<<(n_rays + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n_rays, rays_o, rays_d, n_aabbs,
+                                                                                    aabbs, t_sorted, t_indices, hits);
+    return launch_status();
+}
+
+int64_t nfa_occ_words(int32_t n_grids, int32_t rx, int32_t ry, int32_t rz)
+{
+    if (n_grids <= 0 || rx <= 0 || ry <= 0 || rz <= 0) return 0;
+    return (int64_t)n_grids * occ_geom(n_grids, rx, ry, rz).wpl;
+}
+
+int64_t nfa_occ_coarse_words(int32_t n_grids, int32_t rx, int32_t ry, int32_t rz)
+{
+    if (n_grids <= 0 || rx <= 0 || ry <= 0 || rz <= 0) return 0;
+    return occ_coarse_words(occ_geom(n_grids, rx, ry, rz));
+}
+
+int32_t nfa_occ_pack(int32_t n_grids, int32_t rx, int32_t ry, int32_t rz, const uint8_t* binaries, uint64_t* words,
+                     uint32_t* coarse, nfa_stream_t stream)
+{
+    if (n_grids <= 0 || rx <= 0 || ry <= 0 || rz <= 0 || !binaries || !words || !coarse) return NFA_ERR_ARG;
+    const OccGeom g = occ_geom(n_grids, rx, ry, rz);
+    const int64_t n_words = (int64_t)n_grids * g.wpl;
+    if (n_words > (int64_t)INT32_MAX) return NFA_ERR_UNSUPPORTED;
+    const int64_t n_coarse = occ_coarse_words(g);
+    const int64_t threads = n_coarse * 32;
+    const int blocks = (int)((threads + 255) / 256 < 148 * 16 ? (threads + 255) / 256 : 148 * 16);
+    occ_pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(g, binaries, words, coarse, n_words, n_coarse);
+    return launch_status();
+}
+
+int64_t nfa_march_workspace_bytes(int32_t n_rays) { return n_rays < 0 ? 0 : ws_bytes(n_rays); }
+
+static int32_t fill_march_params(MarchParams& p, int32_t n_rays, const float* rays_o, const float* rays_d,
+                                 const float* near_planes, const float* far_planes, int32_t n_grids, int32_t rx,
+                                 int32_t ry, int32_t rz, const uint64_t* words, const uint32_t* coarse,
+                                 const float* aabbs, const float* t_sorted, const int64_t* t_indices,
+                                 const uint8_t* hits, float step_size, void* workspace)
+{
+    if (n_rays < 0 || n_grids <= 0 || rx <= 0 || ry <= 0 || rz <= 0) return NFA_ERR_ARG;
+    if (!(step_size > 0.0f)) return NFA_ERR_UNSUPPORTED;
+    if (n_rays > 0 && (!rays_o || !rays_d || !near_planes || !far_planes || !words || !coarse || !aabbs || !workspace))
+        return NFA_ERR_ARG;
+    const bool have_sorted = t_sorted && t_indices && hits;
+    if (!have_sorted && n_grids != 1) return NFA_ERR_ARG;
+    p.n_rays = n_rays;
+    p.rays_o = rays_o;
+    p.rays_d = rays_d;
+    p.near_planes = near_planes;
+    p.far_planes = far_planes;
+    p.g = occ_geom(n_grids, rx, ry, rz);
+    p.words = words;
+    p.coarse = coarse;
+    p.coarse_words = (int32_t)occ_coarse_words(p.g);
+    p.aabbs = aabbs;
+    p.t_sorted = have_sorted ? t_sorted : nullptr;
+    p.t_indices = have_sorted ? t_indices : nullptr;
+    p.hits = have_sorted ? hits : nullptr;
+    p.step_size = step_size;
+    p.ws = ws_view(workspace, n_rays);
+    p.totals = nullptr;
+    p.terminate = nullptr;
+    return NFA_OK;
+}
+
+int32_t nfa_march(int32_t n_rays, const float* rays_o, const float* rays_d, const float* near_planes,
+                  const float* far_planes, int32_t n_grids, int32_t rx, int32_t ry, int32_t rz,
+                  const uint64_t* words, const uint32_t* coarse, const float* aabbs, const float* t_sorted,
+                  const int64_t* t_indices, const uint8_t* hits, float step_size, void* workspace, int64_t* totals,
+                  float* terminate_planes, nfa_stream_t stream)
+{
+    MarchParams p;
+    const int32_t rc = fill_march_params(p, n_rays, rays_o, rays_d, near_planes, far_planes, n_grids, rx, ry, rz,
+                                         words, coarse, aabbs, t_sorted, t_indices, hits, step_size, workspace);
+    if (rc != NFA_OK) return rc;
+    if (!totals) return NFA_ERR_ARG;
+    p.totals = totals;
+    p.terminate = terminate_planes;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n_rays == 0) {
+        return (int32_t)cudaMemsetAsync(totals, 0, 4 * sizeof(int64_t), s);
+    }
+    const int tiles = p.ws.n_tiles;
+    const size_t coarse_bytes = (size_t)p.coarse_words * 4;
+    // keep the brick mip in shared memory while it leaves room for >= 2 CTAs / SM
+    if (coarse_bytes <= 96 * 1024) {
+        if (coarse_bytes > 40 * 1024)
+            cudaFuncSetAttribute(march_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        march_kernel<true><<<tiles, kTileRays, coarse_bytes, s>>>(p);
+    } else {
+        march_kernel<false><<<tiles, kTileRays, 0, s>>>(p);
+    }
+    return launch_status();
+}
+
+int32_t nfa_expand_samples(int32_t n_rays, const void* workspace, float step_size, int64_t capacity,
+                           int64_t* packed_info, int64_t* ray_indices, float* t_starts, float* t_ends,
+                           nfa_stream_t stream)
+{
+    if (n_rays < 0 || capacity < 0) return NFA_ERR_ARG;
+    if (n_rays == 0) return NFA_OK;
+    if (!workspace || !packed_info) return NFA_ERR_ARG;
+    if (capacity > 0 && (!ray_indices || !t_starts || !t_ends)) return NFA_ERR_ARG;
+    if ((((uintptr_t)packed_info) & 15u) != 0) return NFA_ERR_ARG;
+    ExpandParams p = {};
+    p.n_rays = n_rays;
+    p.ws = ws_view(const_cast<void*>(workspace), n_rays);
+    p.step_size = step_size;
+    p.sample_capacity = capacity;
+    p.sm_packed_info = packed_info;
+    p.ray_indices = ray_indices;
+    p.t_starts = t_starts;
+    p.t_ends = t_ends;
+    expand_kernel<false><<<p.ws.n_tiles, kExpandThreads, 0, (cudaStream_t)stream>>>(p);
+    return launch_status();
+}
+
+int32_t nfa_expand_intervals(int32_t n_rays, const void* workspace, float step_size, int64_t edge_capacity,
+                             int64_t sample_capacity, int64_t* iv_packed_info, float* iv_vals,
+                             int64_t* iv_ray_indices, uint8_t* iv_is_left, uint8_t* iv_is_right,
+                             int64_t* sm_packed_info, float* sm_vals, int64_t* sm_ray_indices, uint8_t* sm_is_valid,
+                             nfa_stream_t stream)
+{
+    if (n_rays < 0 || edge_capacity < 0 || sample_capacity < 0) return NFA_ERR_ARG;
+    if (n_rays == 0) return NFA_OK;
+    if (!workspace || !iv_packed_info || !sm_packed_info) return NFA_ERR_ARG;
+    if (edge_capacity > 0 && (!iv_vals || !iv_ray_indices || !iv_is_left || !iv_is_right)) return NFA_ERR_ARG;
+    if (sample_capacity > 0 && (!sm_vals || !sm_ray_indices || !sm_is_valid)) return NFA_ERR_ARG;
+    if (((((uintptr_t)iv_packed_info) | ((uintptr_t)sm_packed_info)) & 15u) != 0) return NFA_ERR_ARG;
+    ExpandParams p = {};
+    p.n_rays = n_rays;
+    p.ws = ws_view(const_cast<void*>(workspace), n_rays);
+    p.step_size = step_size;
+    p.sample_capacity = sample_capacity;
+    p.sm_packed_info = sm_packed_info;
+    p.ray_indices = sm_ray_indices;
+    p.edge_capacity = edge_capacity;
+    p.iv_packed_info = iv_packed_info;
+    p.iv_vals = iv_vals;
+    p.iv_ray_indices = iv_ray_indices;
+    p.iv_is_left = iv_is_left;
+    p.iv_is_right = iv_is_right;
+    p.sm_vals = sm_vals;
+    p.sm_is_valid = sm_is_valid;
+    expand_kernel<true><<<p.ws.n_tiles, kExpandThreads, 0, (cudaStream_t)stream>>>(p);
+    return launch_status();
+}
+
+int32_t nfa_march_fill(int32_t n_rays, const float* rays_o, const float* rays_d, const float* near_planes,
+                       const float* far_planes, int32_t n_grids, int32_t rx, int32_t ry, int32_t rz,
+                       const uint64_t* words, const uint32_t* coarse, const float* aabbs, const float* t_sorted,
+                       const int64_t* t_indices, const uint8_t* hits, float step_size, const void* workspace,
+                       int64_t sample_capacity, const int64_t* sm_packed_info, int64_t* ray_indices, float* t_starts,
+                       float* t_ends, int64_t edge_capacity, const int64_t* iv_packed_info, float* iv_vals,
+                       int64_t* iv_ray_indices, uint8_t* iv_is_left, uint8_t* iv_is_right, float* sm_vals,
+                       int64_t* sm_ray_indices, uint8_t* sm_is_valid, nfa_stream_t stream)
+{
+    FillParams fp = {};
+    const int32_t rc =
+        fill_march_params(fp.m, n_rays, rays_o, rays_d, near_planes, far_planes, n_grids, rx, ry, rz, words, coarse,
+                          aabbs, t_sorted, t_indices, hits, step_size, const_cast<void*>(workspace));
+    if (rc != NFA_OK) return rc;
+    if (n_rays == 0) return NFA_OK;
+    if (!sm_packed_info) return NFA_ERR_ARG;
+    fp.want_samples = t_starts != nullptr;
+    fp.want_intervals = iv_vals != nullptr;
+    if (fp.want_samples == fp.want_intervals) return NFA_ERR_ARG;  // exactly one output group
+    fp.e.n_rays = n_rays;
+    fp.e.sample_capacity = sample_capacity;
+    fp.e.sm_packed_info = const_cast<int64_t*>(sm_packed_info);
+    if (fp.want_samples) {
+        if (!ray_indices || !t_ends) return NFA_ERR_ARG;
+        fp.e.ray_indices = ray_indices;
+        fp.e.t_starts = t_starts;
+        fp.e.t_ends = t_ends;
+    } else {
+        if (!iv_packed_info || !iv_ray_indices || !iv_is_left || !iv_is_right || !sm_vals || !sm_ray_indices ||
+            !sm_is_valid)
+            return NFA_ERR_ARG;
+        fp.e.ray_indices = sm_ray_indices;
+        fp.e.edge_capacity = edge_capacity;
+        fp.e.iv_packed_info = const_cast<int64_t*>(iv_packed_info);
+        fp.e.iv_vals = iv_vals;
+        fp.e.iv_ray_indices = iv_ray_indices;
+        fp.e.iv_is_left = iv_is_left;
+        fp.e.iv_is_right = iv_is_right;
+        fp.e.sm_vals = sm_vals;
+        fp.e.sm_is_valid = sm_is_valid;
+    }
+    march_fill_kernel<<<(n_rays + 127) / 128, 128, 0, (cudaStream_t)stream>>>(fp);
+    return launch_status();
+}
+
+}  // extern "C"

@@ -1,0 +1,303 @@
+"""Ray/box intersection and occupancy-grid traversal.
+
+Public names, arguments and return types mirror /root/reference/nerfacc/grid.py
+(ray_aabb_intersect :13-51, traverse_grids :93-192, helpers :54-90,195-237).
+
+`traverse_grids` drives the native pipeline of csrc/traverse.cu:
+pack the bool grid to brick words (cached) -> march (one DDA pass, runs) ->
+expand (coalesced per-sample arrays).  One host synchronisation per call, to
+learn the output size -- the reference needs two (data_spec.hpp:90-91) plus
+those of the boolean-mask selects in its callers.
+"""
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from .data_specs import RayIntervals, RaySamples
+from .pack import _stash_packed_info
+
+
+@torch.no_grad()
+def ray_aabb_intersect(
+    rays_o: Tensor,
+    rays_d: Tensor,
+    aabbs: Tensor,
+    near_plane: float = -float("inf"),
+    far_plane: float = float("inf"),
+    miss_value: float = float("inf"),
+) -> Tuple[Tensor, Tensor, Tensor]:
+    """Slab test of every ray against every box.
+
+    Returns (t_mins, t_maxs, hits), each (n_rays, m); misses hold `miss_value`
+    (reference grid.py:13-51 -> csrc/grid.cu:284-313).
+    """
+    assert rays_o.ndim == 2 and rays_o.shape[-1] == 3
+    assert rays_d.ndim == 2 and rays_d.shape[-1] == 3
+    assert aabbs.ndim == 2 and aabbs.shape[-1] == 6
+    _lib.require_cuda(rays_o, "ray_aabb_intersect")
+    rays_o, rays_d, aabbs = rays_o.contiguous().float(), rays_d.contiguous().float(), aabbs.contiguous().float()
+    n_rays, m = rays_o.shape[0], aabbs.shape[0]
+    device = rays_o.device
+    t_mins = torch.empty((n_rays, m), dtype=torch.float32, device=device)
+    t_maxs = torch.empty((n_rays, m), dtype=torch.float32, device=device)
+    hits = torch.empty((n_rays, m), dtype=torch.bool, device=device)
+    if n_rays * m > 0:
+        _lib.call("nfa_ray_aabb_intersect", device, n_rays, _lib.ptr(rays_o), _lib.ptr(rays_d), m, _lib.ptr(aabbs),
+                  float(near_plane), float(far_plane), float(miss_value), _lib.ptr(t_mins), _lib.ptr(t_maxs),
+                  _lib.ptr(hits))
+    return t_mins, t_maxs, hits
+
+
+def _ray_aabb_intersect(
+    rays_o: Tensor,
+    rays_d: Tensor,
+    aabbs: Tensor,
+    near_plane: float = -float("inf"),
+    far_plane: float = float("inf"),
+    miss_value: float = float("inf"),
+) -> Tuple[Tensor, Tensor, Tensor]:
+    """Plain-torch slab test with the same outputs as :func:`ray_aabb_intersect` (test helper)."""
+    lo, hi = aabbs[None, :, :3], aabbs[None, :, 3:]
+    o, d = rays_o[:, None, :], rays_d[:, None, :]
+    ta, tb = (lo - o) / d, (hi - o) / d
+    t_mins = torch.minimum(ta, tb).amax(dim=-1)
+    t_maxs = torch.maximum(ta, tb).amin(dim=-1)
+    hits = (t_maxs > t_mins) & (t_maxs > 0)
+    t_mins = torch.where(hits, t_mins.clamp(near_plane, far_plane), torch.full_like(t_mins, miss_value))
+    t_maxs = torch.where(hits, t_maxs.clamp(near_plane, far_plane), torch.full_like(t_maxs, miss_value))
+    return t_mins, t_maxs, hits
+
+
+# --------------------------------------------------------------------------
+# native traversal plumbing
+# --------------------------------------------------------------------------
+
+class _OccPack:
+    """Brick-packed copy of a bool grid; derived, never persisted."""
+
+    __slots__ = ("key", "words", "coarse", "shape")
+
+    def __init__(self, binaries: Tensor):
+        lib = _lib.load()
+        g, rx, ry, rz = (int(s) for s in binaries.shape)
+        device = binaries.device
+        b = binaries.contiguous()
+        if b.dtype != torch.bool:
+            b = b != 0
+        self.shape = (g, rx, ry, rz)
+        self.words = torch.empty(lib.nfa_occ_words(g, rx, ry, rz), dtype=torch.int64, device=device)
+        self.coarse = torch.empty(lib.nfa_occ_coarse_words(g, rx, ry, rz), dtype=torch.int32, device=device)
+        _lib.call("nfa_occ_pack", device, g, rx, ry, rz, _lib.ptr(b), _lib.ptr(self.words), _lib.ptr(self.coarse))
+
+
+_occ_cache: Dict[tuple, _OccPack] = {}
+
+
+def _packed_grid(binaries: Tensor) -> _OccPack:
+    key = (binaries.data_ptr(), binaries._version, tuple(binaries.shape), binaries.device, binaries.dtype)
+    hit = _occ_cache.get(key)
+    if hit is None:
+        if len(_occ_cache) >= 8:
+            _occ_cache.clear()
+        hit = _OccPack(binaries)
+        hit.key = key
+        _occ_cache[key] = hit
+    return hit
+
+
+class _MarchScratch:
+    """Per-(device, n_rays) reusable workspace + pinned read-back slot."""
+
+    def __init__(self, device, n_rays: int):
+        lib = _lib.load()
+        self.workspace = torch.zeros(lib.nfa_march_workspace_bytes(n_rays), dtype=torch.uint8, device=device)
+        self.totals_dev = torch.zeros(4, dtype=torch.int64, device=device)
+        self.totals_host = torch.zeros(4, dtype=torch.int64).pin_memory()
+
+
+_scratch_cache: Dict[tuple, _MarchScratch] = {}
+
+
+def _scratch(device, n_rays: int) -> _MarchScratch:
+    key = (device, n_rays)
+    s = _scratch_cache.get(key)
+    if s is None:
+        if len(_scratch_cache) >= 8:
+            _scratch_cache.clear()
+        s = _MarchScratch(device, n_rays)
+        _scratch_cache[key] = s
+    return s
+
+
+class _MarchResult:
+    __slots__ = ("n_samples", "n_runs", "ray_indices", "t_starts", "t_ends", "packed_info",
+                 "intervals", "samples", "terminate_planes")
+
+
+def _march(rays_o: Tensor, rays_d: Tensor, binaries: Tensor, aabbs: Tensor, near_planes: Tensor,
+           far_planes: Tensor, step_size: float, t_sorted: Optional[Tensor], t_indices: Optional[Tensor],
+           hits: Optional[Tensor], want_intervals: bool, want_terminate: bool,
+           capacity_hint: int = 0) -> _MarchResult:
+    """Constant-step traversal: march -> (sync) -> expand."""
+    device = rays_o.device
+    n_rays = rays_o.shape[0]
+    n_grids, rx, ry, rz = (int(s) for s in binaries.shape)
+    occ = _packed_grid(binaries)
+    if n_grids > 1 and t_sorted is None:
+        t_sorted = torch.empty((n_rays, 2 * n_grids), dtype=torch.float32, device=device)
+        t_indices = torch.empty((n_rays, 2 * n_grids), dtype=torch.int64, device=device)
+        hits = torch.empty((n_rays, n_grids), dtype=torch.bool, device=device)
+        if n_rays > 0:
+            _lib.call("nfa_intersect_sorted", device, n_rays, _lib.ptr(rays_o), _lib.ptr(rays_d), n_grids,
+                      _lib.ptr(aabbs), _lib.ptr(t_sorted), _lib.ptr(t_indices), _lib.ptr(hits))
+    sc = _scratch(device, n_rays)
+    term = torch.empty(n_rays, dtype=torch.float32, device=device) if want_terminate else None
+    geom = (n_grids, rx, ry, rz)
+    march_args = (n_rays, _lib.ptr(rays_o), _lib.ptr(rays_d), _lib.ptr(near_planes), _lib.ptr(far_planes), *geom,
+                  _lib.ptr(occ.words), _lib.ptr(occ.coarse), _lib.ptr(aabbs), _lib.ptr(t_sorted),
+                  _lib.ptr(t_indices), _lib.ptr(hits), float(step_size), _lib.ptr(sc.workspace))
+    _lib.call("nfa_march", device, *march_args, _lib.ptr(sc.totals_dev), _lib.ptr(term))
+    sc.totals_host.copy_(sc.totals_dev, non_blocking=True)
+
+    res = _MarchResult()
+    res.terminate_planes = term
+    res.intervals = res.samples = None
+    stream = torch.cuda.current_stream(device)
+
+    def read_totals():
+        stream.synchronize()
+        n, runs, over, stuck = (int(v) for v in sc.totals_host.tolist())
+        if stuck:
+            raise RuntimeError(
+                f"traverse_grids: step_size={step_size} is below the float32 resolution of the marching "
+                f"distance on {stuck} ray(s); the march cannot advance (the reference would not terminate).")
+        return n, runs, over
+
+    packed_info = torch.empty((n_rays, 2), dtype=torch.int64, device=device)
+    if not want_intervals:
+        def expand(cap):
+            ri = torch.empty(cap, dtype=torch.int64, device=device)
+            ts = torch.empty(cap, dtype=torch.float32, device=device)
+            te = torch.empty(cap, dtype=torch.float32, device=device)
+            _lib.call("nfa_expand_samples", device, n_rays, _lib.ptr(sc.workspace), float(step_size), cap,
+                      _lib.ptr(packed_info), _lib.ptr(ri), _lib.ptr(ts), _lib.ptr(te))
+            return ri, ts, te
+
+        bufs = None
+        if capacity_hint > 0:
+            bufs = expand(capacity_hint)
+        n, runs, over = read_totals()
+        if bufs is None or n > capacity_hint:
+            bufs = expand(n)
+            cap = n
+        else:
+            cap = capacity_hint
+        ri, ts, te = bufs
+        if over:
+            _lib.call("nfa_march_fill", device, *march_args, cap, _lib.ptr(packed_info), _lib.ptr(ri), _lib.ptr(ts),
+                      _lib.ptr(te), 0, None, None, None, None, None, None, None, None)
+        res.ray_indices, res.t_starts, res.t_ends = ri[:n], ts[:n], te[:n]
+    else:
+        n, runs, over = read_totals()
+        e = n + runs
+        iv_pi = torch.empty((n_rays, 2), dtype=torch.int64, device=device)
+        iv_vals = torch.empty(e, dtype=torch.float32, device=device)
+        iv_ray = torch.empty(e, dtype=torch.int64, device=device)
+        iv_left = torch.empty(e, dtype=torch.bool, device=device)
+        iv_right = torch.empty(e, dtype=torch.bool, device=device)
+        sm_vals = torch.empty(n, dtype=torch.float32, device=device)
+        sm_ray = torch.empty(n, dtype=torch.int64, device=device)
+        sm_valid = torch.empty(n, dtype=torch.bool, device=device)
+        _lib.call("nfa_expand_intervals", device, n_rays, _lib.ptr(sc.workspace), float(step_size), e, n,
+                  _lib.ptr(iv_pi), _lib.ptr(iv_vals), _lib.ptr(iv_ray), _lib.ptr(iv_left), _lib.ptr(iv_right),
+                  _lib.ptr(packed_info), _lib.ptr(sm_vals), _lib.ptr(sm_ray), _lib.ptr(sm_valid))
+        if over:
+            _lib.call("nfa_march_fill", device, *march_args, n, _lib.ptr(packed_info), None, None, None,
+                      e, _lib.ptr(iv_pi), _lib.ptr(iv_vals), _lib.ptr(iv_ray), _lib.ptr(iv_left),
+                      _lib.ptr(iv_right), _lib.ptr(sm_vals), _lib.ptr(sm_ray), _lib.ptr(sm_valid))
+        res.intervals = RayIntervals(vals=iv_vals, packed_info=iv_pi, ray_indices=iv_ray, is_left=iv_left,
+                                     is_right=iv_right)
+        res.samples = RaySamples(vals=sm_vals, packed_info=packed_info, ray_indices=sm_ray, is_valid=sm_valid)
+        res.ray_indices = sm_ray
+    res.n_samples, res.n_runs, res.packed_info = n, runs, packed_info
+    _stash_packed_info(res.ray_indices, packed_info, n_rays)
+    return res
+
+
+@torch.no_grad()
+def traverse_grids(
+    rays_o: Tensor,  # [n_rays, 3]
+    rays_d: Tensor,  # [n_rays, 3]
+    binaries: Tensor,  # [m, resx, resy, resz]
+    aabbs: Tensor,  # [m, 6]
+    near_planes: Optional[Tensor] = None,  # [n_rays]
+    far_planes: Optional[Tensor] = None,  # [n_rays]
+    step_size: Optional[float] = 1e-3,
+    cone_angle: Optional[float] = 0.0,
+    traverse_steps_limit: Optional[int] = None,
+    over_allocate: Optional[bool] = False,
+    rays_mask: Optional[Tensor] = None,  # [n_rays]
+    t_sorted: Optional[Tensor] = None,  # [n_rays, m * 2]
+    t_indices: Optional[Tensor] = None,  # [n_rays, m * 2]
+    hits: Optional[Tensor] = None,  # [n_rays, m]
+) -> Tuple[RayIntervals, RaySamples, Tensor]:
+    """March rays through one or more nested binary grids.
+
+    Same arguments, defaults and return triple (RayIntervals, RaySamples,
+    termination planes) as the reference (grid.py:93-192).  Not differentiable.
+    """
+    _lib.require_cuda(rays_o, "traverse_grids")
+    device = rays_o.device
+    rays_o, rays_d = rays_o.contiguous().float(), rays_d.contiguous().float()
+    aabbs = aabbs.contiguous().float()
+    if near_planes is None:
+        near_planes = torch.zeros_like(rays_o[:, 0])
+    if far_planes is None:
+        far_planes = torch.full_like(rays_o[:, 0], float("inf"))
+    near_planes, far_planes = near_planes.contiguous().float(), far_planes.contiguous().float()
+    if traverse_steps_limit is None:
+        traverse_steps_limit = -1
+    if over_allocate:
+        assert traverse_steps_limit > 0, "traverse_steps_limit must be set if over_allocate is True."
+    have_sorted = t_sorted is not None and t_indices is not None and hits is not None
+    if have_sorted:
+        t_sorted, t_indices, hits = t_sorted.contiguous().float(), t_indices.contiguous(), hits.contiguous()
+    else:
+        t_sorted = t_indices = hits = None
+
+    fast = (cone_angle == 0.0 and step_size is not None and step_size > 0.0 and traverse_steps_limit <= 0
+            and not over_allocate)
+    if not fast:
+        raise NotImplementedError(
+            "nerfacc_b200.traverse_grids: cone_angle > 0, step_size <= 0 and traverse_steps_limit / "
+            "over_allocate are not built yet in this round (constant-step exact-allocation mode only).")
+    # rays_mask is ignored in exact-allocation mode by the reference too (grid.cu:418,450)
+    res = _march(rays_o, rays_d, binaries, aabbs, near_planes, far_planes, float(step_size), t_sorted, t_indices,
+                 hits, want_intervals=True, want_terminate=True)
+    return res.intervals, res.samples, res.terminate_planes
+
+
+def _enlarge_aabb(aabb, factor: float) -> Tensor:
+    """Scale a box about its centre (reference grid.py:195-198)."""
+    lo, hi = aabb[:3], aabb[3:]
+    mid, half = (lo + hi) * 0.5, (hi - lo) * 0.5
+    return torch.cat([mid - half * factor, mid + half * factor])
+
+
+def _query(x: Tensor, data: Tensor, base_aabb: Tensor) -> Tensor:
+    """Look up `data` (m, rx, ry, rz) at points `x`, picking the mip level of nested 2x boxes.
+
+    Test helper with the reference's semantics (grid.py:201-237): returns (values * selector, selector).
+    """
+    lo, hi = base_aabb[:3], base_aabb[3:]
+    u = (x - lo) / (hi - lo) - 0.5  # base box -> [-0.5, 0.5]^3
+    reach = u.abs().amax(dim=-1).clamp(min=0.1)  # keep frexp away from 0
+    level = (torch.frexp(reach)[1].long() + 1).clamp(min=0)
+    inside = level < data.shape[0]
+    u = u / (2.0 ** level)[:, None] + 0.5
+    res = torch.tensor(data.shape[1:], device=x.device)
+    cell = torch.minimum((u * res).long(), res - 1)
+    level = level.clamp(max=data.shape[0] - 1)
+    return data[level, cell[:, 0], cell[:, 1], cell[:, 2]] * inside, inside
