@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- ray-samples/s through the sampling + compositing hot path.
+
+Metric (BASELINE.json): samples/s through `OccGridEstimator.sampling` (grid traversal)
++ `rendering` (render_weight_from_density + 3x accumulate_along_rays) forward AND
+backward, 65 536 rays on a 128^3 occupancy grid, ~128 samples/ray, per GPU.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5            # this implementation
+    python bench.py --impl reference ...                        # CPU arm (see below)
+    torchrun --nproc-per-node N bench.py --gpus N ...           # weak scaling, rays sharded
+
+One step = one pass of the hot path over one batch of synthetic rays:
+sampling -> rendering -> MSE loss on colours -> backward (d/dsigmas, d/drgbs).  sigmas /
+rgbs stand in for the user's radiance field (seeded leaf tensors).
+
+`value`   samples/s with the ray batch already resident in HBM.
+`e2e`     same step through the public API with HOST inputs: rays copied from pinned
+          memory every step and the scalar loss read back, inside the timed region.
+`--impl reference`  the reference has no CPU implementation of the packed path
+          (nerfacc/pack.py:47-48); the arm therefore times the CPU oracle port
+          (oracle/oracle.c, OpenMP over rays) of exactly this path on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "ray-samples/sec (traverse+composite fwd+bwd)"
+RAYS_PER_GPU = 65536
+GRID_RES = 128
+
+# algorithmic bytes (SURVEY.md 8d / DESIGN.md "Roofline")
+B_TRAVERSE, B_FWD, B_BWD, B_RAY = 16, 44, 48, 88
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index: int):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def start(self):
+        def run():
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            while not self._stop.is_set():
+                try:
+                    out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([c.strip() for c in out.split(",")])
+                except Exception:
+                    pass
+                self._stop.wait(0.1)
+        self._t = threading.Thread(target=run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_oracle_step(orc, ro, rd, bins, aabbs, step_size, sig_seed=43):
+    """One pass of the hot path on the host cores with the oracle port. Returns (n_samples, seconds)."""
+    t0 = time.perf_counter()
+    ri, ts, te, pi = orc.occgrid_sampling(ro, rd, bins, aabbs, render_step_size=step_size)
+    n = len(ri)
+    rng = np.random.default_rng(sig_seed)
+    t_gen = time.perf_counter()
+    sig = (5 * rng.random(n)).astype(np.float32)
+    rgb = rng.random((n, 3)).astype(np.float32)
+    t_gen = time.perf_counter() - t_gen  # synthetic field values are not part of the path
+    o = orc.composite(ts, te, sig, rgb, packed_info=pi)
+    gC = (2.0 / o["colors"].size) * (o["colors"] - 0.5)
+    orc.composite_backward(ts, te, sig, rgb, pi, gC=gC.astype(np.float32))
+    return n, time.perf_counter() - t0 - t_gen
+
+
+def run_cpu_arm(args, rank, world):
+    """`--impl reference`: CPU arm.  Rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    from nerfacc_b200 import scenes
+    orc.build()
+    n_rays = 4096  # bounded sample of the same workload (same geometry, 1/16 of the rays)
+    ro, rd = scenes.ball_rays(n_rays)
+    bins, aabbs = scenes.ball_grid(GRID_RES), scenes.nested_aabbs(1)
+    for _ in range(max(1, min(args.warmup, 3))):
+        cpu_oracle_step(orc, ro, rd, bins, aabbs, scenes.BALL_STEP)
+    tot_n, tot_t = 0, 0.0
+    for _ in range(args.steps):
+        n, t = cpu_oracle_step(orc, ro, rd, bins, aabbs, scenes.BALL_STEP)
+        tot_n += n
+        tot_t += t
+    v = tot_n / tot_t
+    sample = f"{n_rays} of the {RAYS_PER_GPU} rays of the same scene per step (oracle port, OpenMP)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{GRID_RES}^3 occ-grid ball scene, {RAYS_PER_GPU} rays/GPU, ~128 samples/ray, traverse + "
+                               "composite fwd+bwd; CPU arm runs a bounded sample", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": orc.num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_cpu_arm(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    import nerfacc_b200 as nfa
+    from nerfacc_b200 import _lib, parallel, scenes
+
+    assert torch.cuda.is_available(), "bench.py (ours) needs a GPU; there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    # ---- synthetic workload: every rank owns a 65 536-ray shard of a world*65 536 batch (weak scaling)
+    n_total = RAYS_PER_GPU * world
+    ro_all, rd_all = scenes.ball_rays(n_total, seed=42)
+    b, e = parallel.shard_bounds(n_total, rank, world)
+    ro_h = torch.from_numpy(ro_all[b:e]).pin_memory()
+    rd_h = torch.from_numpy(rd_all[b:e]).pin_memory()
+    ro_d, rd_d = ro_h.to(dev), rd_h.to(dev)
+    R = e - b
+    est = nfa.OccGridEstimator(torch.from_numpy(scenes.ROI_AABB), resolution=GRID_RES, levels=1).to(dev)
+    est.binaries = torch.from_numpy(scenes.ball_grid(GRID_RES)).to(dev)
+    step_size = scenes.BALL_STEP
+
+    ri, ts, te = est.sampling(ro_d, rd_d, render_step_size=step_size)
+    N = ri.numel()
+    g = torch.Generator(device="cpu").manual_seed(43 + rank)
+    sigmas = (5 * torch.rand(N, generator=g)).to(dev).requires_grad_(True)
+    rgbs = torch.rand(N, 3, generator=g).to(dev).requires_grad_(True)
+    target = torch.rand(R, 3, generator=g).to(dev)
+    loss_host = torch.zeros(1).pin_memory()
+
+    def field(t_starts, t_ends, ray_indices):  # stands in for the user's radiance field
+        return rgbs, sigmas
+
+    def step(host_inputs: bool):
+        if host_inputs:
+            o, d = ro_h.to(dev, non_blocking=True), rd_h.to(dev, non_blocking=True)
+        else:
+            o, d = ro_d, rd_d
+        ri_, ts_, te_ = est.sampling(o, d, render_step_size=step_size)
+        colors, opac, depth, _ = nfa.rendering(ts_, te_, ri_, n_rays=R, rgb_sigma_fn=field)
+        loss = torch.nn.functional.mse_loss(colors, target)
+        sigmas.grad = None
+        rgbs.grad = None
+        loss.backward()
+        tot = parallel.all_reduce_loss(loss)  # the only collective of the path
+        if host_inputs:
+            loss_host.copy_(tot, non_blocking=True)
+        return ri_.numel()
+
+    def timed(host_inputs: bool, steps: int, warmup: int, clocks=None):
+        for _ in range(warmup):
+            step(host_inputs)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if clocks:
+            clocks.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.launches
+        e0.record()
+        n = 0
+        for _ in range(steps):
+            n += step(host_inputs)
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ck = clocks.stop() if clocks else None
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms, float(n)], device=dev, dtype=torch.float64)
+        if world > 1:
+            tm = t.clone()
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            ms, n = float(tm[0]), float(t[1])
+        return ms, float(n), _lib.launches - l0, ck
+
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    ms, n_samples, launches, ck = timed(False, args.steps, args.warmup, clocks)
+    value = n_samples / (ms * 1e-3)
+    ms_e2e, n_e2e, _, _ = timed(True, args.steps, 2)
+    e2e_value = n_e2e / (ms_e2e * 1e-3)
+
+    # ---- per-kernel roofline: CUDA events on the launching stream, L2 flushed before each launch
+    roof = None
+    cpu_base = None
+    if rank == 0:
+        peak, peak_kind = load_peaks()
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        pi = nfa.pack_info(ri, R)
+        col, op, dep, ex = nfa.rendering(ts, te, ri, n_rays=R, rgb_sigma_fn=field)
+        gcol = torch.rand_like(col)
+
+        def time_call(fn, reps=10):
+            tot = 0.0
+            for _ in range(reps):
+                flush.fill_(1)
+                a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                c.record()
+                torch.cuda.synchronize()
+                tot += a.elapsed_time(c)
+            return tot / reps * 1e-3
+
+        def k_fwd():
+            with torch.no_grad():
+                nfa.rendering(ts, te, ri, n_rays=R, rgb_sigma_fn=lambda a, b_, c: (rgbs.detach(), sigmas.detach()))
+
+        def k_bwd():
+            torch.autograd.grad(col, [sigmas, rgbs], gcol, retain_graph=True)
+
+        def k_trav():
+            est.sampling(ro_d, rd_d, render_step_size=step_size)
+
+        t_fwd, t_bwd, t_trav = time_call(k_fwd), time_call(k_bwd), time_call(k_trav)
+        stages = {
+            "composite_bwd": (B_BWD * N + 40 * R, t_bwd),
+            "composite_fwd": (B_FWD * N + 36 * R, t_fwd),
+            "traverse(march+expand+sync)": (B_TRAVERSE * N + 48 * R, t_trav),
+        }
+        dom = max(["composite_bwd", "composite_fwd"], key=lambda k: stages[k][1])
+        by, tt = stages[dom]
+        roof = {"bound": "hbm", "kernel": dom, "achieved": by / tt / 1e9, "peak": peak, "peak_kind": peak_kind,
+                "unit": "GB/s", "frac": by / tt / 1e9 / peak, "traffic": None,
+                "stages_us": {k: round(v[1] * 1e6, 1) for k, v in stages.items()},
+                "stages_gbs": {k: round(v[0] / v[1] / 1e9, 1) for k, v in stages.items()},
+                "step_frac_of_roofline": ((B_TRAVERSE + B_FWD + B_BWD) * N + B_RAY * R) / (ms / args.steps * 1e-3) / 1e9 / peak}
+        if not args.no_cpu_baseline:
+            from oracle import oracle as orc
+            orc.build()
+            n_cpu = 4096
+            bins, aabbs = scenes.ball_grid(GRID_RES), scenes.nested_aabbs(1)
+            cpu_oracle_step(orc, ro_all[:n_cpu], rd_all[:n_cpu], bins, aabbs, step_size)
+            tn, tsec = 0, 0.0
+            t_begin = time.perf_counter()
+            while tsec < 3.0 and time.perf_counter() - t_begin < 30.0:
+                n_, t_ = cpu_oracle_step(orc, ro_all[:n_cpu], rd_all[:n_cpu], bins, aabbs, step_size)
+                tn += n_
+                tsec += t_
+            cpu_base = {"value": tn / tsec, "unit": "samples/s", "cores": orc.num_threads(), "kind": "port",
+                        "sample": f"{n_cpu} rays of the same scene, repeated for ~3 s (oracle port, OpenMP over rays)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{GRID_RES}^3 occ-grid (ball, 6.5% occupied), {RAYS_PER_GPU} rays/GPU, "
+                                   f"{N / R:.1f} samples/ray, traverse + composite fwd+bwd",
+                       "n_samples_per_gpu": N, "render_step_size": step_size, "parallelism": f"ray-shard dp{world}",
+                       "l2": "per-step working set ~0.9 GB > 126 MB L2 (inputs larger than L2); per-kernel "
+                             "roofline timings flush L2 before each launch"},
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(R * 24),
+                    "d2h_bytes_per_step": 4 + 32, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": ck,
+            "roofline": roof,
+            "cpu_baseline": cpu_base,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -77,7 +77,7 @@ def _ray_aabb_intersect(
 class _OccPack:
     """Brick-packed copy of a bool grid; derived, never persisted."""
 
-    __slots__ = ("key", "words", "coarse", "shape")
+    __slots__ = ("words", "coarse", "shape")
 
     def __init__(self, binaries: Tensor):
         lib = _lib.load()
@@ -92,19 +92,19 @@ class _OccPack:
         _lib.call("nfa_occ_pack", device, g, rx, ry, rz, _lib.ptr(b), _lib.ptr(self.words), _lib.ptr(self.coarse))
 
 
-_occ_cache: Dict[tuple, _OccPack] = {}
-
-
 def _packed_grid(binaries: Tensor) -> _OccPack:
-    key = (binaries.data_ptr(), binaries._version, tuple(binaries.shape), binaries.device, binaries.dtype)
-    hit = _occ_cache.get(key)
-    if hit is None:
-        if len(_occ_cache) >= 8:
-            _occ_cache.clear()
-        hit = _OccPack(binaries)
-        hit.key = key
-        _occ_cache[key] = hit
-    return hit
+    """Brick-pack `binaries`, cached ON the tensor object and keyed by its version counter.
+
+    The cache dies with the tensor and is invalidated by any in-place write, so
+    `estimator.binaries = new` / `estimator.binaries[...] = x` are both picked up
+    (a pointer-keyed cache is not safe: the allocator recycles addresses).
+    """
+    hit = getattr(binaries, "_nfa_occ", None)
+    if hit is not None and hit[0] == binaries._version and hit[1].shape == tuple(int(s) for s in binaries.shape):
+        return hit[1]
+    pack = _OccPack(binaries)
+    binaries._nfa_occ = (binaries._version, pack)
+    return pack
 
 
 class _MarchScratch:

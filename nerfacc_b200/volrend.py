@@ -139,6 +139,15 @@ def _composite_packed(dens: Tensor, rgbs: Optional[Tensor], t_starts: Optional[T
     _lib.require_cuda(dens, "rendering")
     assert dens.dim() == 1, "flattened inputs must be 1-D"
     pi = _segments(packed_info, ray_indices, n_rays)
+    if dens.numel() == 0:
+        # nothing to launch; per-ray outputs of empty rays are zero (+ background)
+        if not want_rays:
+            return dens, dens, dens, None, None, None
+        zeros = torch.zeros((pi.shape[0], 1), dtype=torch.float32, device=dens.device)
+        colors = zeros.expand(-1, 3).clone() if rgbs is not None else None
+        if colors is not None and bkgd is not None:
+            colors = colors + bkgd
+        return dens, dens, dens, colors, zeros, zeros.clone() if t_starts is not None else None
     return _Composite.apply(_f32c(dens), _f32c(rgbs), pi, _f32c(t_starts), _f32c(t_ends), _f32c(prefix_trans),
                             _f32c(bkgd), from_alpha, expected_depths, want_rays)
 

@@ -117,7 +117,7 @@ tm, tM, h = ref.ray_aabb_intersect(T(ro3), T(rd3), T(boxes))
 save("ref_ray_aabb", rays_o=ro3, rays_d=rd3, aabbs=boxes, t_mins=N(tm), t_maxs=N(tM), hits=N(h))
 
 # (f) rendering forward + backward on the ball samples
-R = 512
+R = 96
 est = estimator(ball, scenes.nested_aabbs(1))
 ri, ts, te = est.sampling(T(ro[:R]), T(rd[:R]), render_step_size=scenes.BALL_STEP)
 n = ri.numel()
@@ -150,11 +150,11 @@ save("ref_render_extras", alphas_in=N(al), gW=gW, gT=gT, gA=gA, weights_a=N(w), 
      g_sigmas=N(sig.grad))
 
 # (g) scans
-cnts = rng.integers(0, 200, 500)
+cnts = rng.integers(0, 100, 120)
 starts = np.cumsum(cnts) - cnts
 pinfo = np.stack([starts, cnts], -1).astype(np.int64)
 m = int(cnts.sum())
-idx = np.repeat(np.arange(500), cnts).astype(np.int64)
+idx = np.repeat(np.arange(120), cnts).astype(np.int64)
 x_np = (rng.random(m) * 0.2 + 0.9).astype(np.float32)
 out = {}
 for nm in ["inclusive_sum", "exclusive_sum", "inclusive_prod", "exclusive_prod"]:

@@ -1,0 +1,71 @@
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on a B200)")
+
+
+def pytest_collection_modifyitems(config, items):
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:  # pragma: no cover
+        has_gpu = False
+    if has_gpu:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def orc():
+    """The CPU oracle (test infrastructure)."""
+    from oracle import oracle
+    oracle.build()
+    return oracle
+
+
+@pytest.fixture(scope="session")
+def host_sim():
+    """CPU build of the product's host+device traversal headers (tests/host_sim)."""
+    import ctypes as C
+    d = os.path.join(ROOT, "tests", "host_sim")
+    so = os.path.join(d, "libhost_sim.so")
+    src = os.path.join(d, "host_sim.cpp")
+    hdrs = [os.path.join(ROOT, "nerfacc_b200", "csrc", h) for h in ("lattice.cuh", "march.cuh", "expand.cuh", "occ_pack.cuh", "nfa_math.cuh")]
+    newest = max(os.path.getmtime(p) for p in [src] + hdrs)
+    if not os.path.exists(so) or os.path.getmtime(so) < newest:
+        subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
+                               "-Wno-unknown-pragmas", "-o", so, src])
+    lib = C.CDLL(so)
+    lib.sim_chain.restype = C.c_float
+    lib.sim_chain.argtypes = [C.c_float, C.c_float, C.c_uint32]
+    lib.sim_seek.argtypes = [C.c_float, C.c_float, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]
+    lib.sim_expand_run.argtypes = [C.c_float, C.c_float, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.sim_occ_words.restype = C.c_int64
+    lib.sim_occ_coarse_words.restype = C.c_int64
+    lib.sim_march.restype = C.c_int64
+    return lib
+
+
+def load_golden(name):
+    import numpy as np
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def golden_bins(z):
+    import numpy as np
+    shp = tuple(int(v) for v in z["binaries_shape"])
+    return np.unpackbits(z["binaries_bits"])[: int(np.prod(shp))].reshape(shp).astype(bool)

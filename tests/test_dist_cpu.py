@@ -1,0 +1,56 @@
+"""world_size-2 gloo check of the ray-sharding helpers (host logic of the N>1 path)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from nerfacc_b200 import parallel
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_rays, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rays = torch.arange(n_rays * 3, dtype=torch.float32).reshape(n_rays, 3)
+    o, d = parallel.shard_rays(rays, -rays, rank, world)
+    local = o.sum()  # stands in for the per-rank loss
+    tot = parallel.all_reduce_loss(local, average=False)
+    q.put((rank, o.shape[0], float(o[0, 0]) if o.shape[0] else -1.0, float(local), float(tot)))
+    dist.destroy_process_group()
+
+
+def test_shard_bounds_partition():
+    for n in [0, 1, 7, 65536, 524288 + 3]:
+        for w in [1, 2, 3, 8]:
+            spans = [parallel.shard_bounds(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [e - b for b, e in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_two_rank_gloo_allreduce():
+    world, n_rays = 2, 1001
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_rays, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    total = float(torch.arange(n_rays * 3, dtype=torch.float32).sum())
+    assert res[0][1] + res[1][1] == n_rays and res[0][2] == 0.0 and res[1][2] == 501 * 3.0
+    assert abs(res[0][3] + res[1][3] - total) / total < 1e-6
+    assert res[0][4] == res[1][4] and abs(res[0][4] - total) / total < 1e-6

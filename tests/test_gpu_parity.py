@@ -1,0 +1,489 @@
+"""GPU parity tests: the native sm_100a path (through the C ABI) vs the CPU oracle,
+vs golden vectors of the reference CUDA build, and the reference's own test cases
+(/root/reference/tests/test_{grid,rendering,pack,scan}.py) restated.
+
+Bars (BASELINE.json north_star): bit-exact ray_indices / packed_info / t_starts / t_ends;
+1e-5 abs on weights / colours (tolerances are written next to each assert)."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+import nerfacc_b200 as nfa
+from nerfacc_b200 import _lib, scenes
+from conftest import golden_bins, load_golden
+
+pytestmark = pytest.mark.gpu
+dev = "cuda:0"
+
+
+def T(a, **kw):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev, **kw)
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _estimator(bins, aabbs):
+    est = nfa.OccGridEstimator(torch.from_numpy(aabbs[0]), resolution=list(bins.shape[1:]), levels=bins.shape[0]).to(dev)
+    est.binaries = T(bins)
+    return est
+
+
+def test_native_library_is_loaded():
+    lib = _lib.load()
+    assert lib.nfa_version() == 1
+    before = _lib.launches
+    nfa.pack_info(torch.tensor([0, 0, 1], device=dev), 2)
+    assert _lib.launches > before  # the call went through the C ABI, not a torch fallback
+
+
+# ---------------------------------------------------------------- sampling vs oracle
+
+def _check_sampling(orc, ro, rd, bins, aabbs, **kw):
+    est = _estimator(bins, aabbs)
+    tk = {k: (T(v) if isinstance(v, np.ndarray) else v) for k, v in kw.items()}
+    out = []
+    for _ in range(2):  # second call takes the capacity-hint (expand-before-sync) path
+        ri, ts, te = est.sampling(T(ro), T(rd), **tk)
+        out.append((ri, ts, te))
+    o_ri, o_ts, o_te, o_pi = orc.occgrid_sampling(ro, rd, bins, aabbs, **kw)
+    for ri, ts, te in out:
+        assert ri.dtype == torch.int64 and ts.dtype == torch.float32
+        np.testing.assert_array_equal(N(ri), o_ri)   # bit-exact
+        np.testing.assert_array_equal(N(ts), o_ts)   # bit-exact
+        np.testing.assert_array_equal(N(te), o_te)   # bit-exact
+        np.testing.assert_array_equal(N(nfa.pack_info(ri, ro.shape[0])), o_pi)
+    return len(o_ri)
+
+
+def test_sampling_ball_scene(orc):
+    ro, rd = scenes.ball_rays(4096)
+    n = _check_sampling(orc, ro, rd, scenes.ball_grid(128), scenes.nested_aabbs(1), render_step_size=scenes.BALL_STEP)
+    assert 122 <= n / 4096 <= 134
+
+
+def test_sampling_many_runs_per_ray(orc):
+    """More runs than inline slots: exercises nfa_march_fill."""
+    ro, rd = scenes.ball_rays(1024)
+    rng = np.random.default_rng(7)
+    frag = scenes.ball_grid(128) & (rng.random((1, 128, 128, 128)) > 0.5)
+    _check_sampling(orc, ro, rd, frag, scenes.nested_aabbs(1), render_step_size=scenes.BALL_STEP)
+
+
+def test_sampling_nested_levels_and_planes(orc):
+    rng = np.random.default_rng(11)
+    R = 300
+    ro = rng.standard_normal((R, 3)).astype(np.float32)
+    rd = rng.standard_normal((R, 3)).astype(np.float32)
+    rd /= np.linalg.norm(rd, axis=1, keepdims=True)
+    bins4 = rng.random((4, 32, 32, 32)) > 0.5
+    a4 = scenes.nested_aabbs(4)
+    _check_sampling(orc, ro, rd, bins4, a4, render_step_size=1e-2)
+    _check_sampling(orc, ro, rd, bins4, a4, render_step_size=1e-2, near_plane=0.15, far_plane=3.4,
+                    t_min=rng.random(R).astype(np.float32), t_max=(1 + 3 * rng.random(R)).astype(np.float32))
+    _check_sampling(orc, ro, rd, rng.random((2, 30, 17, 5)) > 0.3, a4[:2], render_step_size=4e-3)
+    # stratified jitter stand-in: per-ray near planes inside one step
+    _check_sampling(orc, ro, rd, bins4[:1], a4[:1], render_step_size=5e-3, t_min=(rng.random(R) * 5e-3).astype(np.float32))
+
+
+def test_sampling_edge_cases(orc):
+    a1 = scenes.nested_aabbs(1)
+    est = _estimator(np.zeros((1, 8, 8, 8), bool), a1)
+    ro, rd = scenes.ball_rays(100)
+    ri, ts, te = est.sampling(T(ro), T(rd), render_step_size=1e-2)  # empty grid
+    assert ri.numel() == ts.numel() == te.numel() == 0 and ri.dtype == torch.int64
+    ri, ts, te = est.sampling(T(ro[:0]), T(rd[:0]), render_step_size=1e-2)  # empty ray batch
+    assert ri.numel() == 0
+    full = _estimator(np.ones((1, 4, 4, 4), bool), a1)
+    away = T(ro) * 0 + torch.tensor([5.0, 5.0, 5.0], device=dev)
+    ri, _, _ = full.sampling(away, T(np.tile(np.array([[1, 0, 0]], np.float32), (100, 1))), render_step_size=1e-2)
+    assert ri.numel() == 0  # all rays miss
+    # axis-aligned directions (zero components)
+    ro2 = np.array([[-2, 0.1, 0.2], [0.3, -3, 0.1], [0.01, 0.02, 5], [0, 0, 0]], np.float32)
+    rd2 = np.array([[1, 0, 0], [0, 1, 0], [0, 0, -1], [0, 0, 1]], np.float32)
+    rng = np.random.default_rng(3)
+    _check_sampling(orc, ro2, rd2, rng.random((4, 32, 32, 32)) > 0.5, scenes.nested_aabbs(4), render_step_size=1e-2)
+    # step far below the float32 resolution of t: the reference would never terminate, we raise
+    huge = nfa.OccGridEstimator([-1e6, -1e6, -1e6, 1e6, 1e6, 1e6], resolution=4).to(dev)
+    huge.binaries = torch.ones_like(huge.binaries)
+    with pytest.raises(RuntimeError, match="cannot advance"):
+        huge.sampling(T(ro2[:1] * 0), T(rd2[:1]), near_plane=3.0e5, far_plane=1e10, render_step_size=1e-3)
+
+
+def test_grid_mutation_invalidates_pack(orc):
+    ro, rd = scenes.ball_rays(256)
+    a1 = scenes.nested_aabbs(1)
+    est = _estimator(scenes.ball_grid(32), a1)
+    n0 = est.sampling(T(ro), T(rd), render_step_size=1e-2)[0].numel()
+    est.binaries[0, :16] = False  # in-place edit
+    o = orc.occgrid_sampling(ro, rd, N(est.binaries), a1, render_step_size=1e-2)
+    assert est.sampling(T(ro), T(rd), render_step_size=1e-2)[0].numel() == len(o[0]) < n0
+    est.binaries = T(scenes.ball_grid(32, radius=0.3))  # reassignment (reference occ_grid.py:404)
+    o = orc.occgrid_sampling(ro, rd, scenes.ball_grid(32, radius=0.3), a1, render_step_size=1e-2)
+    np.testing.assert_array_equal(N(est.sampling(T(ro), T(rd), render_step_size=1e-2)[1]), o[1])
+
+
+# ---------------------------------------------------------------- vs reference-CUDA goldens
+
+@pytest.mark.parametrize("name", ["ref_sampling_ball", "ref_sampling_frag", "ref_sampling_lvl4",
+                                  "ref_sampling_lvl4_tminmax"])
+def test_sampling_matches_reference_cuda(name):
+    z = load_golden(name)
+    kw = dict(zip([str(s) for s in z["kw_names"]], [float(v) for v in z["kw_vals"]]))
+    if "in_t_min" in z:
+        kw["t_min"], kw["t_max"] = T(z["in_t_min"]), T(z["in_t_max"])
+    est = _estimator(golden_bins(z), z["aabbs"])
+    ri, ts, te = est.sampling(T(z["rays_o"]), T(z["rays_d"]), **kw)
+    assert ri.numel() == int(z["n_samples"])
+    assert _sha(N(ri)) == str(z["ray_indices_sha"])                                   # bit-exact
+    np.testing.assert_array_equal(N(nfa.pack_info(ri, z["rays_o"].shape[0])), z["packed_info"])  # bit-exact
+    np.testing.assert_array_equal(N(ts), z["t_starts"])
+    np.testing.assert_array_equal(N(te), z["t_ends"])
+
+
+def test_traverse_grids_matches_reference_cuda(orc):
+    z = load_golden("ref_traverse_lvl4")
+    iv, sm, term = nfa.traverse_grids(T(z["rays_o"]), T(z["rays_d"]), T(golden_bins(z)), T(z["aabbs"]),
+                                      step_size=float(z["step_size"]))
+    np.testing.assert_array_equal(N(iv.vals), z["iv_vals"])
+    np.testing.assert_array_equal(np.packbits(N(iv.is_left)), z["iv_left"])
+    np.testing.assert_array_equal(np.packbits(N(iv.is_right)), z["iv_right"])
+    np.testing.assert_array_equal(N(iv.packed_info), z["iv_packed_info"])
+    assert _sha(N(iv.ray_indices)) == str(z["iv_ray_sha"])
+    np.testing.assert_array_equal(N(sm.vals), z["sm_vals"])
+    np.testing.assert_array_equal(N(sm.packed_info), z["sm_packed_info"])
+    assert _sha(N(sm.ray_indices)) == str(z["sm_ray_sha"]) and bool(sm.is_valid.all())
+    _, _, o_term = orc.traverse_grids(z["rays_o"], z["rays_d"], golden_bins(z), z["aabbs"], step_size=float(z["step_size"]))
+    d = ~np.isnan(o_term)
+    np.testing.assert_array_equal(N(term)[d], z["terminate"][d])
+    # pre-computed crossings (reference examples/utils.py:332-342) give the same result
+    tm, tM, hits = nfa.ray_aabb_intersect(T(z["rays_o"]), T(z["rays_d"]), T(z["aabbs"]))
+    tsrt, tidx = torch.sort(torch.cat([tm, tM], -1), -1)
+    iv2, _, _ = nfa.traverse_grids(T(z["rays_o"]), T(z["rays_d"]), T(golden_bins(z)), T(z["aabbs"]),
+                                   step_size=float(z["step_size"]), t_sorted=tsrt, t_indices=tidx, hits=hits)
+    np.testing.assert_array_equal(N(iv2.vals), z["iv_vals"])
+
+
+def test_ray_aabb_matches_reference_cuda():
+    z = load_golden("ref_ray_aabb")
+    tm, tM, h = nfa.ray_aabb_intersect(T(z["rays_o"]), T(z["rays_d"]), T(z["aabbs"]))
+    np.testing.assert_array_equal(N(tm), z["t_mins"])
+    np.testing.assert_array_equal(N(tM), z["t_maxs"])
+    np.testing.assert_array_equal(N(h), z["hits"])
+    # reference tests/test_grid.py:8-35: agrees with the plain-torch version
+    _tm, _tM, _h = nfa.grid._ray_aabb_intersect(T(z["rays_o"]), T(z["rays_d"]), T(z["aabbs"]))
+    assert torch.allclose(tm, _tm) and torch.allclose(tM, _tM) and (h == _h).all()
+
+
+def test_rendering_matches_reference_cuda():
+    z = load_golden("ref_render_ball")
+    R = int(z["n_rays"])
+    ri = T(np.repeat(np.arange(R), z["packed_info"][:, 1]))
+    sig, rgb = T(z["sigmas"]).requires_grad_(True), T(z["rgbs"]).requires_grad_(True)
+    col, op, dep, ex = nfa.rendering(T(z["t_starts"]), T(z["t_ends"]), ri, n_rays=R,
+                                     rgb_sigma_fn=lambda a, b, c: (rgb, sig), render_bkgd=T(z["bkgd"]))
+    for got, key in [(ex["weights"], "weights"), (ex["trans"], "trans"), (ex["alphas"], "alphas"), (col, "colors"),
+                     (op, "opacities"), (dep, "depths")]:
+        np.testing.assert_allclose(N(got), z[key], atol=1e-5, rtol=0, err_msg=key)   # north_star tolerance
+    ((col * T(z["gC"])).sum() + (op * T(z["gO"])).sum() + (dep * T(z["gD"])).sum()).backward()
+    np.testing.assert_allclose(N(sig.grad), z["g_sigmas"], atol=1e-5, rtol=1e-4)
+    np.testing.assert_allclose(N(rgb.grad), z["g_rgbs"], atol=1e-5, rtol=1e-4)
+    x = load_golden("ref_render_extras")
+    al = T(x["alphas_in"]).requires_grad_(True)
+    w, tr = nfa.render_weight_from_alpha(al, ray_indices=ri, n_rays=R)
+    np.testing.assert_allclose(N(w), x["weights_a"], atol=1e-5, rtol=0)
+    np.testing.assert_allclose(N(tr), x["trans_a"], atol=1e-5, rtol=0)
+    ((w * T(x["gW"])).sum() + (tr * T(x["gT"])).sum()).backward()
+    np.testing.assert_allclose(N(al.grad), x["g_alphas"], atol=2e-5, rtol=1e-4)
+    sig.grad = None
+    w2, t2, a2 = nfa.render_weight_from_density(T(z["t_starts"]), T(z["t_ends"]), sig, ray_indices=ri, n_rays=R)
+    ((w2 * T(x["gW"])).sum() + (t2 * T(x["gT"])).sum() + (a2 * T(x["gA"])).sum()).backward()
+    np.testing.assert_allclose(N(sig.grad), x["g_sigmas"], atol=1e-5, rtol=1e-4)
+
+
+def test_scans_match_reference_cuda():
+    s = load_golden("ref_scans")
+    pi = T(s["packed_info"])
+    idx = T(np.repeat(np.arange(len(s["packed_info"])), s["packed_info"][:, 1]))
+    gy = T((np.arange(len(s["x"])) % 7 + 1).astype(np.float32))
+    for nm in ["inclusive_sum", "exclusive_sum", "inclusive_prod", "exclusive_prod"]:
+        for mode in ["packed", "key"]:
+            x = T(s["x"]).requires_grad_(True)
+            y = getattr(nfa, nm)(x, packed_info=pi) if mode == "packed" else getattr(nfa, nm)(x, indices=idx)
+            np.testing.assert_allclose(N(y), s[f"{nm}_{mode}"], rtol=2e-5, atol=1e-6, err_msg=f"{nm}/{mode}")
+            (y * gy).sum().backward()
+            np.testing.assert_allclose(N(x.grad), s[f"{nm}_{mode}_grad"], rtol=5e-5, atol=1e-5, err_msg=f"{nm}/{mode}/grad")
+
+
+# ---------------------------------------------------------------- fused compositing vs the f64 oracle
+
+def _ball_samples(R=2048):
+    ro, rd = scenes.ball_rays(R)
+    est = _estimator(scenes.ball_grid(128), scenes.nested_aabbs(1))
+    ri, ts, te = est.sampling(T(ro), T(rd), render_step_size=scenes.BALL_STEP)
+    return ri, ts, te, N(nfa.pack_info(ri, R))
+
+
+@pytest.mark.parametrize("expected_depths,bkgd", [(True, True), (False, False)])
+def test_fused_rendering_vs_oracle(orc, expected_depths, bkgd):
+    R = 2048
+    ri, ts, te, pi = _ball_samples(R)
+    n = ri.numel()
+    g = torch.Generator().manual_seed(43)
+    sig = (5 * torch.rand(n, generator=g)).to(dev).requires_grad_(True)
+    rgb = torch.rand(n, 3, generator=g).to(dev).requires_grad_(True)
+    bk = torch.tensor([0.2, 0.5, 0.9], device=dev) if bkgd else None
+    col, op, dep, ex = nfa.rendering(ts, te, ri, n_rays=R, rgb_sigma_fn=lambda a, b, c: (rgb, sig), render_bkgd=bk,
+                                     expected_depths=expected_depths)
+    assert col.shape == (R, 3) and op.shape == (R, 1) and dep.shape == (R, 1)
+    o = orc.composite(N(ts), N(te), N(sig), N(rgb), packed_info=pi, render_bkgd=None if bk is None else N(bk),
+                      expected_depths=expected_depths)
+    for got, key in [(ex["weights"], "weights"), (ex["trans"], "trans"), (ex["alphas"], "alphas"), (col, "colors"),
+                     (op, "opacities"), (dep, "depths")]:
+        np.testing.assert_allclose(N(got), o[key], atol=1e-5, rtol=0, err_msg=key)
+    gC, gO, gD = (torch.rand(s, generator=g).to(dev) for s in [(R, 3), (R, 1), (R, 1)])
+    ((col * gC).sum() + (op * gO).sum() + (dep * gD).sum()).backward()
+    gs, gr = orc.composite_backward(N(ts), N(te), N(sig), N(rgb), pi, gC=N(gC), gO=N(gO).ravel(), gD=N(gD).ravel(),
+                                    render_bkgd=None if bk is None else N(bk), expected_depths=expected_depths)
+    np.testing.assert_allclose(N(sig.grad), gs, atol=1e-5, rtol=1e-4)
+    np.testing.assert_allclose(N(rgb.grad), gr, atol=1e-5, rtol=1e-4)
+    # weights sum to the opacity; colours are linear in rgbs
+    np.testing.assert_allclose(N(nfa.accumulate_along_rays(ex["weights"], None, ri, R)), N(op), atol=1e-5)
+    col2, _, _, _ = nfa.rendering(ts, te, ri, n_rays=R, rgb_sigma_fn=lambda a, b, c: (2 * rgb.detach(), sig.detach()))
+    col1, _, _, _ = nfa.rendering(ts, te, ri, n_rays=R, rgb_sigma_fn=lambda a, b, c: (rgb.detach(), sig.detach()))
+    np.testing.assert_allclose(N(col2), 2 * N(col1), atol=1e-5)
+
+
+def test_general_gradients_prefix_trans_and_alpha_route(orc):
+    R = 512
+    ri, ts, te, pi = _ball_samples(R)
+    n = ri.numel()
+    g = torch.Generator().manual_seed(5)
+    sig = (5 * torch.rand(n, generator=g)).to(dev).requires_grad_(True)
+    pt = (0.5 + 0.5 * torch.rand(n, generator=g)).to(dev)
+    gW, gT, gA = (torch.rand(n, generator=g).to(dev) for _ in range(3))
+    for kwargs in [dict(ray_indices=ri, n_rays=R), dict(packed_info=T(pi))]:
+        sig.grad = None
+        w, tr, a = nfa.render_weight_from_density(ts, te, sig, prefix_trans=pt, **kwargs)
+        o = orc.composite(N(ts), N(te), N(sig), None, packed_info=pi, prefix_trans=N(pt))
+        np.testing.assert_allclose(N(w), o["weights"], atol=1e-5)
+        np.testing.assert_allclose(N(tr), o["trans"], atol=1e-5)
+        ((w * gW).sum() + (tr * gT).sum() + (a * gA).sum()).backward()
+        gs, _ = orc.composite_backward(N(ts), N(te), N(sig), None, pi, gW=N(gW), gT=N(gT), gA=N(gA), prefix_trans=N(pt))
+        np.testing.assert_allclose(N(sig.grad), gs, atol=1e-5, rtol=1e-4)
+    # background colour that requires grad goes through autograd
+    bk = torch.tensor([0.2, 0.5, 0.9], device=dev, requires_grad=True)
+    rgb = torch.rand(n, 3, generator=g).to(dev)
+    col, op, _, _ = nfa.rendering(ts, te, ri, n_rays=R, rgb_sigma_fn=lambda a, b, c: (rgb, sig.detach()), render_bkgd=bk)
+    col.sum().backward()
+    np.testing.assert_allclose(N(bk.grad), np.full(3, float((1 - op).sum())), rtol=1e-5)
+    # transmittance / visibility entry points
+    tr2, a2 = nfa.render_transmittance_from_density(ts, te, sig.detach(), ray_indices=ri, n_rays=R)
+    o = orc.composite(N(ts), N(te), N(sig), None, packed_info=pi)
+    np.testing.assert_allclose(N(tr2), o["trans"], atol=1e-5)
+    vis = nfa.render_visibility_from_density(ts, te, sig.detach(), ray_indices=ri, n_rays=R, early_stop_eps=0.3, alpha_thre=0.01)
+    exp = (o["trans"] >= 0.3) & (o["alphas"] >= 0.01)
+    assert (N(vis) != exp).mean() < 1e-4  # thresholds on values that differ by ~1e-7
+
+
+# ---------------------------------------------------------------- the reference's own test cases
+
+def test_reference_rendering_cases():
+    ri = torch.tensor([0, 2, 2, 2, 2], dtype=torch.int64, device=dev)
+    al = torch.tensor([0.4, 0.3, 0.8, 0.8, 0.5], device=dev)
+    # tests/test_rendering.py:8-34
+    vis = nfa.render_visibility_from_alpha(al, ray_indices=ri, early_stop_eps=0.03, alpha_thre=0.0)
+    assert vis.tolist() == [True, True, True, True, False]
+    vis = nfa.render_visibility_from_alpha(al, ray_indices=ri, early_stop_eps=0.05, alpha_thre=0.35)
+    assert vis.tolist() == [True, False, True, True, False]
+    # :38-57
+    w, _ = nfa.render_weight_from_alpha(al, ray_indices=ri, n_rays=3)
+    assert torch.allclose(w, torch.tensor([0.4, 0.3, 0.7 * 0.8, 0.14 * 0.8, 0.028 * 0.5], device=dev))
+    # :61-83 density == alpha
+    sig = torch.rand(5, device=dev)
+    ts = torch.rand_like(sig)
+    te = torch.rand_like(sig) + 1.0
+    w1, _, _ = nfa.render_weight_from_density(ts, te, sig, ray_indices=ri, n_rays=3)
+    w2, _ = nfa.render_weight_from_alpha(1.0 - torch.exp(-sig * (te - ts)), ray_indices=ri, n_rays=3)
+    assert torch.allclose(w1, w2)
+    # :87-106 accumulate, ray 1 empty
+    vals = torch.rand(5, 2, device=dev)
+    acc = nfa.accumulate_along_rays(al, values=vals, ray_indices=ri, n_rays=3)
+    assert acc.shape == (3, 2) and torch.allclose(acc[0], al[0] * vals[0]) and (acc[1] == 0).all()
+    assert torch.allclose(acc[2], (al[1:, None] * vals[1:]).sum(0))
+    out = torch.ones(3, 2, device=dev)
+    nfa.accumulate_along_rays_(al, values=vals, ray_indices=ri, outputs=out)
+    assert torch.allclose(out, acc + 1)
+    # :197-218 smoke
+    nfa.rendering(ts, te, ray_indices=ri, n_rays=3, rgb_sigma_fn=lambda a, b, c: (torch.stack([a] * 3, -1), a))
+    c, o, d, _ = nfa.rendering(ts[:0], te[:0], ray_indices=ri[:0], n_rays=3, rgb_sigma_fn=lambda a, b, c: (torch.stack([a] * 3, -1), a))
+    assert c.shape == (3, 3) and (c == 0).all() and (o == 0).all()
+
+
+def test_reference_grad_goldens_all_routes():
+    # tests/test_rendering.py:110-193
+    ri = torch.tensor([0, 2, 2, 2, 2], dtype=torch.int64, device=dev)
+    pi = torch.tensor([[0, 1], [1, 0], [1, 4]], dtype=torch.long, device=dev)
+    sig = torch.tensor([0.4, 0.8, 0.1, 0.8, 0.1], device=dev, requires_grad=True)
+    ts = torch.rand_like(sig)
+    te = ts + 1.0
+    w_ref = torch.tensor([0.3297, 0.5507, 0.0428, 0.2239, 0.0174], device=dev)
+    g_ref = torch.tensor([0.6703, 0.1653, 0.1653, 0.1653, 0.1653], device=dev)
+
+    def routes():
+        tr, _ = nfa.render_transmittance_from_density(ts, te, sig, ray_indices=ri, n_rays=3)
+        yield tr * (1.0 - torch.exp(-sig * (te - ts)))
+        tr, _ = nfa.render_transmittance_from_density(ts, te, sig, packed_info=pi, n_rays=3)
+        yield tr * (1.0 - torch.exp(-sig * (te - ts)))
+        yield nfa.render_weight_from_density(ts, te, sig, ray_indices=ri, n_rays=3)[0]
+        yield nfa.render_weight_from_density(ts, te, sig, packed_info=pi, n_rays=3)[0]
+        yield nfa.render_weight_from_alpha(1.0 - torch.exp(-sig * (te - ts)), ray_indices=ri, n_rays=3)[0]
+        yield nfa.render_weight_from_alpha(1.0 - torch.exp(-sig * (te - ts)), packed_info=pi, n_rays=3)[0]
+
+    for w in routes():
+        sig.grad = None
+        w.sum().backward()
+        assert torch.allclose(w_ref, w, atol=1e-4) and torch.allclose(g_ref, sig.grad, atol=1e-4)
+
+
+def test_reference_pack_and_scan_cases():
+    # tests/test_pack.py:8-18 (int64 result compared with an int32 golden)
+    ri = torch.tensor([0, 2, 2, 2, 2], dtype=torch.int64, device=dev)
+    gold = torch.tensor([[0, 1], [1, 0], [1, 4]], dtype=torch.int32, device=dev)
+    assert (nfa.pack_info(ri, n_rays=3) == gold).all()
+    assert nfa.pack_info(ri).shape == (3, 2) and nfa.pack_info(ri.int(), 3).dtype == torch.int32
+    # tests/test_scan.py:8-172: batched vs packed vs by-key, values and gradients
+    torch.manual_seed(42)
+    for fn, tol in [(nfa.inclusive_sum, 1e-5), (nfa.exclusive_sum, 3e-4), (nfa.inclusive_prod, 1e-5), (nfa.exclusive_prod, 1e-5)]:
+        data = torch.rand((5, 1000), device=dev, requires_grad=True)
+        o1 = fn(data).flatten()
+        o1.sum().backward()
+        g1 = data.grad.clone()
+        data.grad = None
+        starts = torch.arange(0, data.numel(), data.shape[1], device=dev, dtype=torch.long)
+        pi = torch.stack([starts, torch.full((5,), 1000, dtype=torch.long, device=dev)], -1)
+        o2 = fn(data.flatten(), packed_info=pi)
+        o2.sum().backward()
+        g2 = data.grad.clone()
+        data.grad = None
+        idx = torch.arange(5, device=dev, dtype=torch.long).repeat_interleave(1000)
+        o3 = fn(data.flatten(), indices=idx)
+        o3.sum().backward()
+        g3 = data.grad.clone()
+        assert torch.allclose(o1, o2, atol=tol) and torch.allclose(o1, o3, atol=tol)
+        assert torch.allclose(g1, g2, rtol=1e-3, atol=1e-4) and torch.allclose(g1, g3, rtol=1e-3, atol=1e-4)
+
+
+def test_reference_grid_cases():
+    from nerfacc_b200.grid import _enlarge_aabb, _query
+    torch.manual_seed(42)
+    # tests/test_grid.py:39-68
+    ro = torch.randn((10, 3), device=dev)
+    rd = torch.randn((10, 3), device=dev)
+    rd = rd / rd.norm(dim=-1, keepdim=True)
+    base = torch.tensor([-1.0, -1.0, -1.0, 1.0, 1.0, 1.0], device=dev)
+    aabbs = torch.stack([_enlarge_aabb(base, 2 ** i) for i in range(4)])
+    binaries = torch.rand((4, 32, 32, 32), device=dev) > 0.5
+    iv, sm, _ = nfa.traverse_grids(ro, rd, binaries, aabbs)
+    ts, te = iv.vals[iv.is_left], iv.vals[iv.is_right]
+    pos = ro[sm.ray_indices] + rd[sm.ray_indices] * (ts + te)[:, None] / 2.0
+    occs, sel = _query(pos, binaries, base)
+    assert occs.all() and sel.all() and ts.numel() > 0
+    # :135-159
+    d = torch.tensor([[1.0, 0.01, 0.01]], device=dev)
+    iv, _, _ = nfa.traverse_grids(torch.tensor([[-1.0, 0.0, 0.0]], device=dev), d / d.norm(),
+                                  torch.ones((1, 1, 1, 1), dtype=torch.bool, device=dev),
+                                  torch.tensor([[0.0, 0.0, 0.0, 1.0, 1.0, 1.0]], device=dev), step_size=0.05,
+                                  near_planes=torch.tensor([1.2], device=dev), far_planes=torch.tensor([1.5], device=dev))
+    assert iv.vals.numel() > 0 and (iv.vals >= 1.2 - 0.025).all() and (iv.vals <= 1.5 + 0.025).all()
+    # :163-203
+    n_rays = 64
+    ro = torch.rand((n_rays, 3), device=dev) * 2 - 1.0
+    rd = torch.rand((n_rays, 3), device=dev)
+    rd = rd / rd.norm(dim=-1, keepdim=True)
+    t_min = torch.rand((n_rays,), device=dev)
+    t_max = t_min + torch.rand((n_rays,), device=dev)
+    est = nfa.OccGridEstimator(roi_aabb=base, resolution=32, levels=4)
+    est.binaries = binaries
+    ri, ts, te = est.sampling(rays_o=ro, rays_d=rd, near_plane=0.15, far_plane=0.85, t_min=t_min, t_max=t_max,
+                              render_step_size=0.01)
+    assert (ts >= (t_min[ri] - 0.005)).all() and (te <= (t_max[ri] + 0.005)).all()
+    # :207-233
+    est = nfa.OccGridEstimator(roi_aabb=base, resolution=32, levels=4).to(dev)
+    K = torch.tensor([[[100.0, 0, 50.0], [0, 100.0, 50.0], [0, 0, 1]]], device=dev)
+    pose = torch.tensor([[[-1.0, 0.0, 0.0, 0.0], [0.0, 1.0, 0.0, 0.0], [0.0, 0.0, -1.0, 2.5]]], device=dev)
+    est.mark_invisible_cells(K, pose, 100, 100)
+    assert (est.occs == -1).sum() == 77660 and (est.occs == 0).sum() == 53412
+
+
+def test_sampling_with_sigma_fn_filters_like_reference_semantics(orc):
+    R = 512
+    ro, rd = scenes.ball_rays(R)
+    est = _estimator(scenes.ball_grid(64), scenes.nested_aabbs(1))
+    est.occs.fill_(1.0)
+    sigma_fn = lambda ts, te, ri: 40.0 * torch.ones_like(ts)
+    ri, ts, te = est.sampling(T(ro), T(rd), sigma_fn=sigma_fn, render_step_size=1e-2, early_stop_eps=1e-2, alpha_thre=0.0)
+    o_ri, o_ts, o_te, o_pi = orc.occgrid_sampling(ro, rd, scenes.ball_grid(64), scenes.nested_aabbs(1), render_step_size=1e-2)
+    o = orc.composite(o_ts, o_te, np.full(len(o_ts), 40.0, np.float32), None, packed_info=o_pi)
+    keep = o["trans"] >= 1e-2
+    assert abs(int(keep.sum()) - ri.numel()) <= 2 and 0 < ri.numel() < len(o_ri)
+
+
+# ---------------------------------------------------------------- full-size properties (config 2 of BASELINE.json)
+
+def test_full_size_properties():
+    R = 65536
+    ro, rd = scenes.ball_rays(R)
+    bins = scenes.ball_grid(128)
+    est = _estimator(bins, scenes.nested_aabbs(1))
+    tro, trd = T(ro), T(rd)
+    ri, ts, te = est.sampling(tro, trd, render_step_size=scenes.BALL_STEP)
+    ri2, ts2, te2 = est.sampling(tro, trd, render_step_size=scenes.BALL_STEP)  # hinted path, deterministic
+    assert torch.equal(ri, ri2) and torch.equal(ts, ts2) and torch.equal(te, te2)
+    n = ri.numel()
+    assert 122 <= n / R <= 134
+    assert (ri[1:] >= ri[:-1]).all()                       # sorted / grouped
+    pi = nfa.pack_info(ri, R)
+    assert int(pi[:, 1].sum()) == n and (pi[:, 0] == torch.cumsum(pi[:, 1], 0) - pi[:, 1]).all()
+    cnt = torch.bincount(ri, minlength=R)
+    assert torch.equal(cnt, pi[:, 1])
+    assert (te > ts).all()
+    same_ray = ri[1:] == ri[:-1]
+    contiguous = te[:-1] == ts[1:]
+    gap = ts[1:] - te[:-1]
+    assert (gap[same_ray] >= 0).all() and contiguous[same_ray].float().mean() > 0.95  # runs share edges bit-exactly
+    # every midpoint sits in an occupied cell (reference tests/test_grid.py:59-68)
+    pos = tro[ri] + trd[ri] * ((ts + te) / 2.0)[:, None]
+    occ, sel = nfa.grid._query(pos, T(bins), torch.from_numpy(scenes.ROI_AABB).to(dev))
+    assert occ.all() and sel.all()
+    # compositing at full size: weights sum to opacity, checksum of the per-ray reduction
+    sig = 5 * torch.rand(n, device=dev)
+    rgb = torch.rand(n, 3, device=dev)
+    col, op, dep, ex = nfa.rendering(ts, te, ri, n_rays=R, rgb_sigma_fn=lambda a, b, c: (rgb, sig))
+    w64 = torch.zeros(R, dtype=torch.float64, device=dev).index_add_(0, ri, ex["weights"].double())
+    assert (w64 - op[:, 0].double()).abs().max() < 1e-5
+    c64 = torch.zeros(R, 3, dtype=torch.float64, device=dev).index_add_(0, ri, (ex["weights"][:, None] * rgb).double())
+    assert (c64 - col.double()).abs().max() < 1e-5
+    assert (ex["trans"] <= 1).all() and (ex["trans"] >= 0).all() and (op <= 1 + 1e-5).all()
+    first = pi[pi[:, 1] > 0, 0]
+    assert (ex["trans"][first] == 1).all()
+
+
+def test_abi_direct_call_with_raw_pointers():
+    """Call the library the way a foreign host would: plain pointers and sizes."""
+    lib = _lib.load()
+    ri = torch.tensor([0, 0, 0, 2, 2, 5], dtype=torch.int64, device=dev)
+    out = torch.empty((6, 2), dtype=torch.int64, device=dev)
+    ws = torch.empty(lib.nfa_pack_info_workspace_bytes(6), dtype=torch.uint8, device=dev)
+    rc = lib.nfa_pack_info(6, ri.data_ptr(), 6, out.data_ptr(), ws.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert out.tolist() == [[0, 3], [3, 0], [3, 2], [5, 0], [5, 0], [5, 1]]
+    assert lib.nfa_pack_info(6, ri.data_ptr(), 6, out.data_ptr() + 8, ws.data_ptr(), None) == -1  # misaligned output

@@ -1,0 +1,184 @@
+"""CPU checks of the product's host+device traversal headers (lattice.cuh / march.cuh /
+expand.cuh / occ_pack.cuh, compiled for the host by tests/host_sim) against
+(a) serial float chains and (b) the oracle's restatement of the reference kernel."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from nerfacc_b200 import scenes
+
+F = C.POINTER(C.c_float)
+U32 = C.POINTER(C.c_uint32)
+I64 = C.POINTER(C.c_int64)
+U8 = C.POINTER(C.c_uint8)
+U64 = C.POINTER(C.c_uint64)
+I32 = C.POINTER(C.c_int32)
+
+STEPS = [1e-3, 5e-3, 5.2e-3, 0.01, 2 ** -8, 3 * 2 ** -10, 1.5 * 2 ** -7, 0.0123456, 1e-2 / 3, 0.25, 0.7]
+
+
+def _p(a, t):
+    return None if a is None else a.ctypes.data_as(t)
+
+
+def _seek_serial(t0, dt, target):
+    t, dt, target = np.float32(t0), np.float32(dt), np.float32(target)
+    h = np.float32(dt * np.float32(0.5))
+    k = 0
+    while not (np.float32(t + h) >= target):
+        t = np.float32(t + dt)
+        k += 1
+    return float(t), k
+
+
+@pytest.mark.parametrize("dt", STEPS)
+def test_lattice_seek_matches_serial_chain(host_sim, dt):
+    rng = np.random.default_rng(int(dt * 1e7))
+    for _ in range(200):
+        t0 = float(np.float32(rng.choice([0.0, rng.random() * dt * 4, rng.random() * 0.1, rng.random() * 5,
+                                          rng.random() * 40, -rng.random() * 0.05])))
+        target = float(np.float32(t0 + rng.random() * rng.choice([0.01, 0.1, 1, 6])))
+        t, k = C.c_float(), C.c_uint32()
+        ok = host_sim.sim_seek(t0, dt, target, C.byref(t), C.byref(k))
+        ts, ks = _seek_serial(t0, dt, target)
+        assert ok == 1 and np.float32(t.value) == np.float32(ts) and k.value == ks, (dt, t0, target)
+
+
+@pytest.mark.parametrize("dt", STEPS)
+def test_run_expansion_matches_serial_chain(host_sim, dt):
+    rng = np.random.default_rng(int(dt * 1e7) + 1)
+    for _ in range(40):
+        t0 = float(np.float32(rng.choice([0.0, rng.random() * dt * 4, rng.random() * 5, rng.random() * 40,
+                                          1.99, 3.999, 7.9995])))
+        n = int(rng.integers(1, 700))
+        s, e = np.empty(n, np.float32), np.empty(n, np.float32)
+        host_sim.sim_expand_run(t0, dt, n, _p(s, F), _p(e, F))
+        t, d = np.float32(t0), np.float32(dt)
+        ref = np.empty(n, np.float32)
+        for i in range(n):
+            ref[i] = t
+            t = np.float32(t + d)
+        np.testing.assert_array_equal(s, ref)
+        np.testing.assert_array_equal(e[:-1], s[1:])
+        assert e[-1] == t
+
+
+def test_stuck_lattice_is_reported(host_sim):
+    # dt far below ulp(t)/2: the reference would spin forever; we report it
+    t, k = C.c_float(), C.c_uint32()
+    assert host_sim.sim_seek(1.0e6, 1e-3, 2.0e6, C.byref(t), C.byref(k)) == 0
+
+
+def _sim_sampling(sim, ro, rd, bins, aabbs, near, far, step, multi=None):
+    G, rx, ry, rz = bins.shape
+    R = ro.shape[0]
+    words = np.zeros(sim.sim_occ_words(G, rx, ry, rz), np.uint64)
+    coarse = np.zeros(sim.sim_occ_coarse_words(G, rx, ry, rz), np.uint32)
+    b8 = np.ascontiguousarray(bins.astype(np.uint8))
+    sim.sim_occ_pack(G, rx, ry, rz, _p(b8, U8), _p(words, U64), _p(coarse, U32))
+    ns, nr = np.zeros(R, np.int64), np.zeros(R, np.int64)
+    term, ok = np.zeros(R, np.float32), np.zeros(R, np.int32)
+    cap = 2_000_000
+    rt, rn = np.zeros(cap, np.float32), np.zeros(cap, np.uint32)
+    ts_, ti_, hits_ = (None, None, None) if multi is None else multi
+    tot = sim.sim_march(R, _p(ro, F), _p(rd, F), _p(near, F), _p(far, F), G, rx, ry, rz, _p(words, U64), _p(coarse, U32),
+                        _p(aabbs, F), _p(ts_, F), _p(ti_, I64), _p(hits_, U8), C.c_float(step), _p(ns, I64), _p(nr, I64),
+                        _p(term, F), _p(ok, I32), _p(rt, F), _p(rn, U32), C.c_int64(cap))
+    assert tot >= 0
+    N = int(ns.sum())
+    s, e, ri = np.empty(N, np.float32), np.empty(N, np.float32), np.empty(N, np.int64)
+    w = q = 0
+    for r in range(R):
+        for _ in range(nr[r]):
+            n = int(rn[q])
+            sim.sim_expand_run(float(rt[q]), step, n, s[w:].ctypes.data_as(F), e[w:].ctypes.data_as(F))
+            ri[w:w + n] = r
+            w += n
+            q += 1
+    assert w == N
+    return ri, s, e, ns, nr, term, ok
+
+
+def _compare(sim, orc, ro, rd, bins, aabbs, near, far, step, multi=False):
+    iv, sm, term_o = orc.traverse_grids(ro, rd, bins, aabbs, near_planes=near, far_planes=far, step_size=step)
+    m = None
+    if multi:
+        tm, tM, h = orc.ray_aabb_intersect(ro, rd, aabbs)
+        tsrt, tidx = orc.sort_intersections(tm, tM)
+        m = (tsrt, tidx, np.ascontiguousarray(h.astype(np.uint8)))
+    ri, s, e, ns, nr, term, ok = _sim_sampling(sim, ro, rd, bins, aabbs, near, far, step, m)
+    assert ok.all()
+    np.testing.assert_array_equal(ns, sm["packed_info"][:, 1])
+    np.testing.assert_array_equal(nr, iv["packed_info"][:, 1] - sm["packed_info"][:, 1])  # runs = edges - samples
+    np.testing.assert_array_equal(ri, sm["ray_indices"])
+    np.testing.assert_array_equal(s, iv["vals"][iv["is_left"]])
+    np.testing.assert_array_equal(e, iv["vals"][iv["is_right"]])
+    d = ~np.isnan(term_o)
+    np.testing.assert_array_equal(term[d], term_o[d])
+    return len(ri)
+
+
+def test_march_ball_scene(host_sim, orc):
+    R = 2048
+    ro, rd = scenes.ball_rays(R)
+    bins, aabbs = scenes.ball_grid(128), scenes.nested_aabbs(1)
+    near, far = np.zeros(R, np.float32), np.full(R, 1e10, np.float32)
+    n = _compare(host_sim, orc, ro, rd, bins, aabbs, near, far, scenes.BALL_STEP)
+    assert 122 <= n / R <= 134  # SURVEY 8d calibration window
+    rng = np.random.default_rng(7)
+    _compare(host_sim, orc, ro, rd, bins, aabbs, (rng.random(R) * scenes.BALL_STEP).astype(np.float32), far, scenes.BALL_STEP)
+    _compare(host_sim, orc, ro[:256], rd[:256], bins, aabbs, near[:256], far[:256], 1e-3)
+    frag = bins & (rng.random(bins.shape) > 0.5)
+    _compare(host_sim, orc, ro[:512], rd[:512], frag, aabbs, near[:512], far[:512], scenes.BALL_STEP)
+
+
+def test_march_nested_random_grids(host_sim, orc):
+    rng = np.random.default_rng(11)
+    R = 200
+    ro = rng.standard_normal((R, 3)).astype(np.float32)
+    rd = rng.standard_normal((R, 3)).astype(np.float32)
+    rd /= np.linalg.norm(rd, axis=1, keepdims=True)
+    bins4 = rng.random((4, 32, 32, 32)) > 0.5
+    a4 = scenes.nested_aabbs(4)
+    zero, inf = np.zeros(R, np.float32), np.full(R, np.inf, np.float32)
+    _compare(host_sim, orc, ro, rd, bins4, a4, zero, inf, 2e-3, multi=True)
+    _compare(host_sim, orc, ro, rd, bins4, a4, rng.random(R).astype(np.float32), (1 + rng.random(R) * 3).astype(np.float32),
+             1e-2, multi=True)
+    # single level: crossings computed inline vs supplied sorted arrays
+    _compare(host_sim, orc, ro, rd, bins4[:1], a4[:1], zero, inf, 3e-3)
+    _compare(host_sim, orc, ro, rd, bins4[:1], a4[:1], zero, inf, 3e-3, multi=True)
+    # resolution not a multiple of the brick size, non-cubic
+    odd = rng.random((2, 30, 17, 5)) > 0.3
+    _compare(host_sim, orc, ro, rd, odd, a4[:2], zero, inf, 4e-3, multi=True)
+
+
+def test_march_degenerate_rays(host_sim, orc):
+    rng = np.random.default_rng(3)
+    bins4 = rng.random((4, 32, 32, 32)) > 0.5
+    a4 = scenes.nested_aabbs(4)
+    ro = np.array([[-2, 0.1, 0.2], [0.3, -3, 0.1], [0.01, 0.02, 5], [0, 0, 0], [9, 9, 9], [0.5, 0.5, 0.5]], np.float32)
+    rd = np.array([[1, 0, 0], [0, 1, 0], [0, 0, -1], [0, 0, 1], [1, 0, 0], [-0.6, 0.8, 0]], np.float32)
+    R = len(ro)
+    _compare(host_sim, orc, ro, rd, bins4, a4, np.zeros(R, np.float32), np.full(R, np.inf, np.float32), 1e-2, multi=True)
+    # 1x1x1 grid, near/far inside the box (reference tests/test_grid.py:135-159)
+    d = np.array([[1.0, 0.01, 0.01]])
+    d = (d / np.linalg.norm(d)).astype(np.float32)
+    _compare(host_sim, orc, np.array([[-1.0, 0, 0]], np.float32), d, np.ones((1, 1, 1, 1), bool),
+             np.array([[0, 0, 0, 1, 1, 1]], np.float32), np.array([1.2], np.float32), np.array([1.5], np.float32), 0.05)
+    # empty grid and empty ray batch
+    e = np.zeros((1, 8, 8, 8), bool)
+    assert _compare(host_sim, orc, ro, rd, e, a4[:1], np.zeros(R, np.float32), np.full(R, np.inf, np.float32), 1e-2) == 0
+
+
+def test_march_matches_reference_cuda_goldens(host_sim):
+    from conftest import golden_bins, load_golden
+    for name in ["ref_sampling_ball", "ref_sampling_frag"]:
+        z = load_golden(name)
+        R = z["rays_o"].shape[0]
+        step = float(z["kw_vals"][0])
+        ri, s, e, ns, nr, term, ok = _sim_sampling(host_sim, z["rays_o"], z["rays_d"], golden_bins(z), z["aabbs"],
+                                                   np.zeros(R, np.float32), np.full(R, 1e10, np.float32), step)
+        np.testing.assert_array_equal(ns, z["packed_info"][:, 1])
+        np.testing.assert_array_equal(s, z["t_starts"])
+        np.testing.assert_array_equal(e, z["t_ends"])
