@@ -242,32 +242,37 @@ def main():
         peak, peak_kind = load_peaks()
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
         pi = nfa.pack_info(ri, R)
-        col, op, dep, ex = nfa.rendering(ts, te, ri, n_rays=R, rgb_sigma_fn=field)
-        gcol = torch.rand_like(col)
+        gcol = torch.rand(R, 3, device=dev)
 
-        def time_call(fn, reps=10):
+        def time_call(fn, setup=None, reps=10):
             tot = 0.0
             for _ in range(reps):
+                arg = setup() if setup else None
                 flush.fill_(1)
                 a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
-                fn()
+                fn(arg)
                 c.record()
                 torch.cuda.synchronize()
                 tot += a.elapsed_time(c)
             return tot / reps * 1e-3
 
-        def k_fwd():
+        def k_fwd(_):
             with torch.no_grad():
                 nfa.rendering(ts, te, ri, n_rays=R, rgb_sigma_fn=lambda a, b_, c: (rgbs.detach(), sigmas.detach()))
 
-        def k_bwd():
-            torch.autograd.grad(col, [sigmas, rgbs], gcol, retain_graph=True)
+        def bwd_setup():
+            sigmas.grad = None
+            rgbs.grad = None
+            return nfa.rendering(ts, te, ri, n_rays=R, rgb_sigma_fn=field)[0]
 
-        def k_trav():
+        def k_bwd(colors):
+            colors.backward(gcol)
+
+        def k_trav(_):
             est.sampling(ro_d, rd_d, render_step_size=step_size)
 
-        t_fwd, t_bwd, t_trav = time_call(k_fwd), time_call(k_bwd), time_call(k_trav)
+        t_fwd, t_bwd, t_trav = time_call(k_fwd), time_call(k_bwd, bwd_setup), time_call(k_trav)
         stages = {
             "composite_bwd": (B_BWD * N + 40 * R, t_bwd),
             "composite_fwd": (B_FWD * N + 36 * R, t_fwd),

@@ -28,9 +28,7 @@ extern "C" {
 #define NFA_ERR_ARG (-1)         /* null pointer / negative size / inconsistent sizes */
 #define NFA_ERR_UNSUPPORTED (-2) /* valid request outside what this build implements */
 
-#define NFA_ABI_VERSION 1
-/* runs kept inline per ray by nfa_march(); rays with more are finished by nfa_march_fill() */
-#define NFA_RUN_SLOTS 8
+#define NFA_ABI_VERSION 2
 
 typedef void* nfa_stream_t; /* cudaStream_t */
 
@@ -76,29 +74,33 @@ int32_t nfa_occ_pack(int32_t n_grids, int32_t rx, int32_t ry, int32_t rz, const 
 /* replaces: traverse_grids(...) nerfacc/cuda/csrc/nerfacc.cpp:75-96, grid.cu:320-474
  *   (kernel :68-282) for the two-pass (exact allocation) mode.
  *
- * nfa_march: one DDA pass per ray.  Writes per-ray sample counts and the runs
- *   (t_first, n) of consecutive samples into `workspace`, and the totals
- *   totals[0] = n_samples, [1] = n_runs, [2] = rays with > NFA_RUN_SLOTS runs,
- *   [3] = rays whose marching variable stopped advancing (reference would hang)
- *   into `totals` (4 x int64; device memory or host-visible pinned memory).
- *   t_sorted / t_indices / hits may be NULL when n_grids == 1 (crossings are
- *   then computed in the kernel).  terminate_planes [n_rays] may be NULL.
- *   workspace: nfa_march_workspace_bytes(n_rays) bytes, zero-filled once when
- *   allocated (the kernels leave it reusable). */
-int64_t nfa_march_workspace_bytes(int32_t n_rays);
+ * nfa_march: one DDA pass per ray.  Appends every run (t_first, n) of consecutive
+ *   samples to a pool inside `workspace` (capacity `run_capacity` runs) and writes per-ray
+ *   sample / run counts there; the totals
+ *     totals[0] = n_samples, [1] = n_runs, [2] = run_capacity used, [3] = rays whose
+ *     marching variable stopped advancing (the reference would not terminate)
+ *   go to `totals` (4 x int64, device memory).  If totals[1] > run_capacity the pool
+ *   overflowed: call again with a larger pool (counts and totals are still exact).
+ *   t_sorted / t_indices / hits may be NULL when n_grids == 1 (crossings are then
+ *   computed in the kernel).  terminate_planes [n_rays] may be NULL.
+ *   workspace: nfa_march_workspace_bytes(n_rays, run_capacity) bytes whose first 64
+ *   bytes are zero on first use (the kernels leave it reusable). */
+int64_t nfa_march_workspace_bytes(int32_t n_rays, int64_t run_capacity);
 int32_t nfa_march(int32_t n_rays, const float* rays_o, const float* rays_d,
                   const float* near_planes, const float* far_planes,
                   int32_t n_grids, int32_t rx, int32_t ry, int32_t rz,
                   const uint64_t* words, const uint32_t* coarse, const float* aabbs,
                   const float* t_sorted, const int64_t* t_indices, const uint8_t* hits,
-                  float step_size, void* workspace, int64_t* totals, float* terminate_planes,
-                  nfa_stream_t stream);
+                  float step_size, int64_t run_capacity, void* workspace, int64_t* totals,
+                  float* terminate_planes, nfa_stream_t stream);
 
 /* nfa_expand_samples: runs -> packed (ray_indices, t_starts, t_ends) + packed_info.
  *   replaces the fill pass plus `vals[is_left]`, `vals[is_right]` of
- *   nerfacc/estimators/occ_grid.py:174-177.  Elements at index >= capacity are
- *   not written (the caller re-runs with a larger buffer). packed_info: [n_rays, 2]. */
-int32_t nfa_expand_samples(int32_t n_rays, const void* workspace, float step_size, int64_t capacity,
+ *   nerfacc/estimators/occ_grid.py:174-177.  `totals` is the device array nfa_march
+ *   filled.  Elements at index >= capacity are not written (the caller re-runs with a
+ *   larger buffer).  packed_info: [n_rays, 2] = (chunk_start, chunk_cnt). */
+int32_t nfa_expand_samples(int32_t n_rays, int64_t run_capacity, const void* workspace,
+                           const int64_t* totals, float step_size, int64_t capacity,
                            int64_t* packed_info, int64_t* ray_indices, float* t_starts, float* t_ends,
                            nfa_stream_t stream);
 
@@ -106,28 +108,13 @@ int32_t nfa_expand_samples(int32_t n_rays, const void* workspace, float step_siz
  *   (nerfacc/cuda/csrc/include/data_spec.hpp:6-16, nerfacc/data_specs.py:12-180):
  *   intervals {vals, ray_indices, is_left, is_right, packed_info} with n_samples + n_runs
  *   edges, samples {vals = midpoints, ray_indices, is_valid, packed_info}. */
-int32_t nfa_expand_intervals(int32_t n_rays, const void* workspace, float step_size,
+int32_t nfa_expand_intervals(int32_t n_rays, int64_t run_capacity, const void* workspace,
+                             const int64_t* totals, float step_size,
                              int64_t edge_capacity, int64_t sample_capacity,
                              int64_t* iv_packed_info, float* iv_vals, int64_t* iv_ray_indices,
                              uint8_t* iv_is_left, uint8_t* iv_is_right,
                              int64_t* sm_packed_info, float* sm_vals, int64_t* sm_ray_indices,
                              uint8_t* sm_is_valid, nfa_stream_t stream);
-
-/* nfa_march_fill: second DDA pass for the rays nfa_march flagged (more than
- *   NFA_RUN_SLOTS runs); writes their samples / edges at the offsets the expand
- *   call stored in packed_info.  Pass NULL for the output group not wanted. */
-int32_t nfa_march_fill(int32_t n_rays, const float* rays_o, const float* rays_d,
-                       const float* near_planes, const float* far_planes,
-                       int32_t n_grids, int32_t rx, int32_t ry, int32_t rz,
-                       const uint64_t* words, const uint32_t* coarse, const float* aabbs,
-                       const float* t_sorted, const int64_t* t_indices, const uint8_t* hits,
-                       float step_size, const void* workspace,
-                       int64_t sample_capacity, const int64_t* sm_packed_info,
-                       int64_t* ray_indices, float* t_starts, float* t_ends,
-                       int64_t edge_capacity, const int64_t* iv_packed_info,
-                       float* iv_vals, int64_t* iv_ray_indices, uint8_t* iv_is_left, uint8_t* iv_is_right,
-                       float* sm_vals, int64_t* sm_ray_indices, uint8_t* sm_is_valid,
-                       nfa_stream_t stream);
 
 /* ----------------------------------------------------------------------- */
 /* Volume rendering over the packed layout                                  */

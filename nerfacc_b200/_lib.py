@@ -29,15 +29,13 @@ SIGNATURES = {
     "nfa_occ_words": (_c_i64, [_c_i32] * 4),
     "nfa_occ_coarse_words": (_c_i64, [_c_i32] * 4),
     "nfa_occ_pack": (_c_i32, [_c_i32] * 4 + [_c_ptr] * 4),
-    "nfa_march_workspace_bytes": (_c_i64, [_c_i32]),
+    "nfa_march_workspace_bytes": (_c_i64, [_c_i32, _c_i64]),
     "nfa_march": (_c_i32, [_c_i32, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32, _c_i32,
-                           _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_f32, _c_ptr, _c_ptr, _c_ptr, _c_ptr]),
-    "nfa_expand_samples": (_c_i32, [_c_i32, _c_ptr, _c_f32, _c_i64, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr]),
-    "nfa_expand_intervals": (_c_i32, [_c_i32, _c_ptr, _c_f32, _c_i64, _c_i64] + [_c_ptr] * 10),
-    "nfa_march_fill": (_c_i32, [_c_i32, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32, _c_i32,
-                                _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_f32, _c_ptr,
-                                _c_i64, _c_ptr, _c_ptr, _c_ptr, _c_ptr,
-                                _c_i64, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr]),
+                           _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_f32, _c_i64, _c_ptr, _c_ptr, _c_ptr,
+                           _c_ptr]),
+    "nfa_expand_samples": (_c_i32, [_c_i32, _c_i64, _c_ptr, _c_ptr, _c_f32, _c_i64, _c_ptr, _c_ptr, _c_ptr, _c_ptr,
+                                    _c_ptr]),
+    "nfa_expand_intervals": (_c_i32, [_c_i32, _c_i64, _c_ptr, _c_ptr, _c_f32, _c_i64, _c_i64] + [_c_ptr] * 10),
     "nfa_composite_fwd": (_c_i32, [_c_i32, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_ptr, _c_ptr, _c_ptr, _c_i32]
                           + [_c_ptr] * 8),
     "nfa_composite_bwd": (_c_i32, [_c_i32, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_ptr, _c_ptr, _c_ptr, _c_i32]
@@ -52,8 +50,7 @@ SIGNATURES = {
     "nfa_pack_info": (_c_i32, [_c_i64, _c_ptr, _c_i32, _c_ptr, _c_ptr, _c_ptr]),
 }
 
-ABI_VERSION = 1
-RUN_SLOTS = 8
+ABI_VERSION = 2
 
 _lib = None
 launches = 0  # number of native kernel-launching calls made through this module (bench.py reports it)

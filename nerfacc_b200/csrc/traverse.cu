@@ -6,13 +6,16 @@
 //
 //   occ_pack_kernel   bool grid -> 4x4x4 brick words + 1-bit/brick mip   (cached per grid version)
 //   march_kernel      1 thread / ray, 128 rays / CTA.  Ray tile and brick mip staged
-//                     into shared memory with cp.async.bulk (TMA 1-D) + mbarrier;
-//                     pure DDA walk, no per-sample work (march.cuh); writes per-ray
-//                     counts + runs, per-tile sums, and (last CTA) the grand totals.
-//   expand_kernel     1 CTA / 128-ray tile: tile offset from the tile sums + block
-//                     scan -> packed_info; warps turn runs into samples with
-//                     coalesced stores (expand.cuh).
-//   march_fill_kernel only for rays with more runs than fit inline.
+//                     into shared memory with cp.async.bulk (TMA 1-D) + mbarrier.
+//                     Phase 1: pure DDA walk recording occupied stretches (divergent
+//                     but cheap); phase 2: closed-form lattice seeks, all lanes in
+//                     step (march.cuh).  Runs go to a pool through a warp-aggregated
+//                     atomic cursor; per-ray counts, per-tile sums and (last CTA) the
+//                     grand totals are written for the offsets pass.
+//   offsets_kernel    1 CTA / 128-ray tile: tile base from the tile sums + block scan
+//                     -> packed_info (ray-ordered offsets, so ray_indices stay sorted).
+//   expand_runs_kernel one warp per run: lanes compute their sample from the lattice
+//                     closed form and store coalesced (expand.cuh).
 //
 // No tensor cores: the path has no dense contraction; it is bound by dependent
 // f32 chains (march) and by HBM stores (expand).  See DESIGN.md.
@@ -26,50 +29,59 @@
 
 namespace nfa {
 
-constexpr int kTileRays = 128;      // rays per CTA in march / expand
-constexpr int kRunSlots = NFA_RUN_SLOTS;
+constexpr int kTileRays = 128;      // rays per CTA in the march / offsets kernels
+constexpr int kDescSlots = 8;       // stretch descriptors buffered per ray between the two march phases
 constexpr int kExpandThreads = 256;
 
+// One run of consecutive lattice samples, as written by the march kernel (32 bytes, two 16-byte stores).
 struct RunRec {
-    float t_first;
-    uint32_t n;
+    uint32_t ray;         // ray id (tile-global)
+    uint32_t sample_off;  // samples of the ray before this run
+    uint32_t n;           // samples in the run
+    uint32_t t_first;     // bit pattern of the first sample's start
+    uint32_t run_idx;     // runs of the ray before this run (interval edges: +1 edge per run)
+    uint32_t pad[3];
 };
 
 struct TileSum {
     unsigned long long samples;
     uint32_t runs;
-    uint32_t flags;  // low 16: rays over the slot limit; high 16: stuck rays
+    uint32_t stuck;  // rays whose lattice stopped advancing
 };
 
 // Workspace layout (all offsets 16-byte aligned):
-//   [0, 64)                      header: u32 done_counter
-//   tile_sums [n_tiles]          TileSum
+//   [0, 64)                 header: u32 done_counter, u32 pool_cursor
+//   tile_sums [n_tiles]     TileSum
 //   cnt_samples [R] u32, cnt_runs [R] u32
-//   runs [R * kRunSlots]         RunRec
+//   pool [run_capacity]     RunRec
 struct Workspace {
     uint32_t* done;
+    uint32_t* cursor;
     TileSum* tiles;
     uint32_t* cnt_samples;
     uint32_t* cnt_runs;
-    RunRec* runs;
+    RunRec* pool;
     int n_tiles;
+    int64_t run_capacity;
 };
 
 __host__ __device__ inline int64_t align16(int64_t x) { return (x + 15) & ~(int64_t)15; }
 
-__host__ __device__ inline int64_t ws_bytes(int32_t n_rays)
+__host__ __device__ inline int64_t ws_bytes(int32_t n_rays, int64_t run_capacity)
 {
     const int64_t nt = (n_rays + kTileRays - 1) / kTileRays;
     return 64 + align16(nt * (int64_t)sizeof(TileSum)) + align16((int64_t)n_rays * 4) * 2 +
-           align16((int64_t)n_rays * kRunSlots * (int64_t)sizeof(RunRec));
+           run_capacity * (int64_t)sizeof(RunRec);
 }
 
-__host__ __device__ inline Workspace ws_view(void* base, int32_t n_rays)
+__host__ __device__ inline Workspace ws_view(void* base, int32_t n_rays, int64_t run_capacity)
 {
     Workspace w;
     char* p = (char*)base;
     w.n_tiles = (n_rays + kTileRays - 1) / kTileRays;
+    w.run_capacity = run_capacity;
     w.done = (uint32_t*)p;
+    w.cursor = (uint32_t*)(p + 4);
     p += 64;
     w.tiles = (TileSum*)p;
     p += align16(w.n_tiles * (int64_t)sizeof(TileSum));
@@ -77,7 +89,7 @@ __host__ __device__ inline Workspace ws_view(void* base, int32_t n_rays)
     p += align16((int64_t)n_rays * 4);
     w.cnt_runs = (uint32_t*)p;
     p += align16((int64_t)n_rays * 4);
-    w.runs = (RunRec*)p;
+    w.pool = (RunRec*)p;
     return w;
 }
 
@@ -171,37 +183,59 @@ struct MarchParams {
     float* terminate;
 };
 
-struct SlotSink {
-    RunRec* slots;
-    __device__ __forceinline__ void push(uint32_t q, float t_first, uint32_t n)
+// descriptor buffer: one shared-memory column per thread, joined flags in a register
+struct SmemBuf {
+    float* pend;   // [kDescSlots][kTileRays]
+    float* open;
+    uint32_t joined_mask;
+    int tid;
+    __device__ __forceinline__ void put(int j, float p, float o, bool jn)
     {
-        if (q < (uint32_t)kRunSlots) {
-            RunRec r;
-            r.t_first = t_first;
-            r.n = n;
-            slots[q] = r;
-        }
+        pend[j * kTileRays + tid] = p;
+        open[j * kTileRays + tid] = o;
+        joined_mask |= (jn ? 1u : 0u) << j;
     }
 };
 
-template <bool kSmemCoarse>
+// append the runs the lanes of a warp closed in this step: one atomic per warp
+__device__ __forceinline__ void emit_runs(const RunOut& out, uint32_t ray, const Workspace& ws, int lane)
+{
+    const unsigned mask = __ballot_sync(0xffffffffu, out.valid);
+    if (mask == 0u) return;
+    const int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(ws.cursor, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (out.valid) {
+        const uint32_t slot = base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+        if ((int64_t)slot < ws.run_capacity) {
+            uint4* dst = reinterpret_cast<uint4*>(ws.pool + slot);
+            dst[0] = make_uint4(ray, out.sample_off, out.n, __float_as_uint(out.t_first));
+            dst[1] = make_uint4(out.run_idx, 0u, 0u, 0u);
+        }
+    }
+}
+
+template <bool kSingle, bool kSmemCoarse>
 __global__ void __launch_bounds__(kTileRays) march_kernel(const MarchParams p)
 {
     extern __shared__ __align__(16) uint32_t s_coarse[];
     __shared__ __align__(16) float s_o[kTileRays * 3];
     __shared__ __align__(16) float s_d[kTileRays * 3];
+    __shared__ float s_pend[kDescSlots * kTileRays];
+    __shared__ float s_open[kDescSlots * kTileRays];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ unsigned long long s_red_samples[kTileRays / 32];
     __shared__ uint32_t s_red_runs[kTileRays / 32], s_red_flags[kTileRays / 32];
     __shared__ bool s_last;
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int tile = blockIdx.x;
     const int r0 = tile * kTileRays;
     const int nr = min(kTileRays, p.n_rays - r0);
     const int r = r0 + tid;
 
-    // ---- stage the ray tile (and the brick mip) into shared memory -------
+    // ---- stage the ray tile (and the brick mip) into shared memory: TMA bulk copies + mbarrier
     const float* g_o = p.rays_o + (int64_t)r0 * 3;
     const float* g_d = p.rays_d + (int64_t)r0 * 3;
     const uint32_t ray_bytes = (uint32_t)nr * 12u;
@@ -229,54 +263,82 @@ __global__ void __launch_bounds__(kTileRays) march_kernel(const MarchParams p)
     if (kSmemCoarse && !bulk_coarse) {
         for (int i = tid; i < p.coarse_words; i += kTileRays) s_coarse[i] = p.coarse[i];
     }
+    const bool active = tid < nr;
     float near = 0.f, far = 0.f;
-    if (tid < nr) {
+    if (active) {
         near = p.near_planes[r];
         far = p.far_planes[r];
     }
     mbar_wait(&s_bar, 0);
     __syncthreads();
 
-    // ---- per-ray march ----------------------------------------------------
-    uint32_t n_samples = 0, n_runs = 0, flags = 0;
-    if (tid < nr) {
-        OccView occ;
-        occ.words = p.words;
-        occ.coarse = kSmemCoarse ? s_coarse : p.coarse;
-        occ.g = p.g;
-        const float o[3] = {s_o[tid * 3 + 0], s_o[tid * 3 + 1], s_o[tid * 3 + 2]};
-        const float d[3] = {s_d[tid * 3 + 0], s_d[tid * 3 + 1], s_d[tid * 3 + 2]};
-        const Lattice L = lat_make(p.step_size);
-        SlotSink sink;
-        sink.slots = p.ws.runs + (int64_t)r * kRunSlots;
-        RayMarch m;
-        float term;
-        const bool want_term = p.terminate != nullptr;
-        if (p.t_sorted == nullptr) {
-            term = march_ray_single(m, sink, occ, o, d, near, far, p.aabbs, L, want_term);
+    // ---- two-phase march (march.cuh) ---------------------------------------
+    OccView occ;
+    occ.words = p.words;
+    occ.coarse = kSmemCoarse ? s_coarse : p.coarse;
+    occ.g = p.g;
+    const Lattice L = lat_make(p.step_size);
+    const float o[3] = {active ? s_o[tid * 3 + 0] : 0.f, active ? s_o[tid * 3 + 1] : 0.f, active ? s_o[tid * 3 + 2] : 0.f};
+    const float d[3] = {active ? s_d[tid * 3 + 0] : 1.f, active ? s_d[tid * 3 + 1] : 1.f, active ? s_d[tid * 3 + 2] : 1.f};
+    Walk w;
+    LatState m;
+    walk_init(w, o, d, near, far);
+    lat_init(m, L, near);
+    w.done = !active;
+    SmemBuf buf;
+    buf.pend = s_pend;
+    buf.open = s_open;
+    buf.joined_mask = 0u;
+    buf.tid = tid;
+    int n_desc = 0;
+    const int G = p.g.n_grids;
+    const int64_t rr = active ? r : 0;
+    const SingleBox single{p.aabbs};
+    const SortedBoxes sorted{p.aabbs, G, kSingle ? nullptr : p.t_sorted + rr * 2 * G,
+                             kSingle ? nullptr : p.t_indices + rr * 2 * G, kSingle ? nullptr : p.hits + rr * G};
+    for (;;) {
+        // phase 1: DDA only (divergent, cheap)
+        if (kSingle) {
+            while (!w.done && n_desc < kDescSlots) walk_step(w, single, occ, buf, n_desc);
         } else {
-            const int G = p.g.n_grids;
-            term = march_ray_sorted(m, sink, occ, o, d, near, far, p.aabbs, G, p.t_sorted + (int64_t)r * 2 * G,
-                                    p.t_indices + (int64_t)r * 2 * G, p.hits + (int64_t)r * G, L, want_term);
+            while (!w.done && n_desc < kDescSlots) walk_step(w, sorted, occ, buf, n_desc);
         }
-        n_samples = m.n_samples;
-        n_runs = m.n_runs;
-        flags = (n_runs > (uint32_t)kRunSlots ? 1u : 0u) | (m.ok ? 0u : 0x10000u);
-        p.ws.cnt_samples[r] = n_samples;
-        p.ws.cnt_runs[r] = n_runs;
-        if (want_term) p.terminate[r] = term;
+        // phase 2: lattice seeks, all lanes in step
+        const int maxd = __reduce_max_sync(0xffffffffu, n_desc);
+        for (int j = 0; j < maxd; ++j) {
+            RunOut out;
+            out.valid = false;
+            if (j < n_desc)
+                lat_consume(m, s_pend[j * kTileRays + tid], s_open[j * kTileRays + tid], (buf.joined_mask >> j) & 1u, out);
+            emit_runs(out, (uint32_t)r, p.ws, lane);
+        }
+        n_desc = 0;
+        buf.joined_mask = 0u;
+        if (__all_sync(0xffffffffu, w.done)) break;
+    }
+    {
+        RunOut out;
+        out.valid = false;
+        float term = 0.f;
+        if (active) term = lat_finish(m, walk_tail_pend(w), p.terminate != nullptr, out);
+        emit_runs(out, (uint32_t)r, p.ws, lane);
+        if (active) {
+            p.ws.cnt_samples[r] = m.n_samples;
+            p.ws.cnt_runs[r] = m.n_runs;
+            if (p.terminate) p.terminate[r] = term;
+        }
     }
 
     // ---- tile sums, and grand totals by the last CTA to finish ------------
-    unsigned long long vs = n_samples;
-    uint32_t vr = n_runs, vf = flags;
+    unsigned long long vs = active ? m.n_samples : 0u;
+    uint32_t vr = active ? m.n_runs : 0u, vf = (active && !m.ok) ? 1u : 0u;
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) {
         vs += __shfl_xor_sync(0xffffffffu, vs, s);
         vr += __shfl_xor_sync(0xffffffffu, vr, s);
         vf += __shfl_xor_sync(0xffffffffu, vf, s);
     }
-    if ((tid & 31) == 0) {
+    if (lane == 0) {
         s_red_samples[tid >> 5] = vs;
         s_red_runs[tid >> 5] = vr;
         s_red_flags[tid >> 5] = vf;
@@ -286,11 +348,11 @@ __global__ void __launch_bounds__(kTileRays) march_kernel(const MarchParams p)
         TileSum ts;
         ts.samples = 0;
         ts.runs = 0;
-        ts.flags = 0;
-        for (int w = 0; w < kTileRays / 32; ++w) {
-            ts.samples += s_red_samples[w];
-            ts.runs += s_red_runs[w];
-            ts.flags += s_red_flags[w];
+        ts.stuck = 0;
+        for (int k = 0; k < kTileRays / 32; ++k) {
+            ts.samples += s_red_samples[k];
+            ts.runs += s_red_runs[k];
+            ts.stuck += s_red_flags[k];
         }
         p.ws.tiles[tile] = ts;
         __threadfence();
@@ -300,82 +362,59 @@ __global__ void __launch_bounds__(kTileRays) march_kernel(const MarchParams p)
     __syncthreads();
     if (s_last) {
         __threadfence();
-        unsigned long long a = 0, b = 0, c = 0, e = 0;
+        unsigned long long a = 0, b = 0, c = 0;
         for (int i = tid; i < p.ws.n_tiles; i += kTileRays) {
             const volatile unsigned long long* q = (const volatile unsigned long long*)&p.ws.tiles[i];
-            const unsigned long long w0 = q[0], w1 = q[1];  // {samples}, {runs | flags << 32}
+            const unsigned long long w0 = q[0], w1 = q[1];  // {samples}, {runs | stuck << 32}
             a += w0;
             b += (uint32_t)w1;
-            c += (w1 >> 32) & 0xffffu;
-            e += w1 >> 48;
+            c += w1 >> 32;
         }
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) {
             a += __shfl_xor_sync(0xffffffffu, a, s);
             b += __shfl_xor_sync(0xffffffffu, b, s);
             c += __shfl_xor_sync(0xffffffffu, c, s);
-            e += __shfl_xor_sync(0xffffffffu, e, s);
         }
-        __shared__ unsigned long long s_tot[4][kTileRays / 32];
-        if ((tid & 31) == 0) {
+        __shared__ unsigned long long s_tot[3][kTileRays / 32];
+        if (lane == 0) {
             s_tot[0][tid >> 5] = a;
             s_tot[1][tid >> 5] = b;
             s_tot[2][tid >> 5] = c;
-            s_tot[3][tid >> 5] = e;
         }
         __syncthreads();
-        if (tid < 4) {
+        if (tid < 3) {
             unsigned long long v = 0;
-            for (int w = 0; w < kTileRays / 32; ++w) v += s_tot[tid][w];
-            p.totals[tid] = (int64_t)v;
-            __threadfence_system();
+            for (int k = 0; k < kTileRays / 32; ++k) v += s_tot[tid][k];
+            // totals: [0] samples, [1] runs, [2] run-pool capacity used for this call, [3] stuck rays
+            p.totals[tid == 2 ? 3 : tid] = (int64_t)v;
         }
-        if (tid == 0) *p.ws.done = 0u;  // leave the workspace reusable
+        if (tid == 3) p.totals[2] = p.ws.run_capacity;
+        if (tid == 0) {  // leave the workspace reusable
+            *p.ws.done = 0u;
+            *p.ws.cursor = 0u;
+        }
     }
 }
 
 // ---------------------------------------------------------------------------
-// expand
+// offsets: per-ray packed_info from the counts (tile base from the tile sums + block scan)
 // ---------------------------------------------------------------------------
-struct ExpandParams {
-    int32_t n_rays;
-    Workspace ws;
-    float step_size;
-    // samples-only mode
-    int64_t sample_capacity;
-    int64_t* sm_packed_info;
-    int64_t* ray_indices;
-    float* t_starts;
-    float* t_ends;
-    // interval mode (kIntervals)
-    int64_t edge_capacity;
-    int64_t* iv_packed_info;
-    float* iv_vals;
-    int64_t* iv_ray_indices;
-    uint8_t* iv_is_left;
-    uint8_t* iv_is_right;
-    float* sm_vals;
-    uint8_t* sm_is_valid;
-};
-
 template <bool kIntervals>
-__global__ void __launch_bounds__(kExpandThreads) expand_kernel(const ExpandParams p)
+__global__ void __launch_bounds__(kTileRays) offsets_kernel(int32_t n_rays, Workspace ws, int64_t* sm_packed_info,
+                                                           int64_t* iv_packed_info)
 {
-    __shared__ unsigned long long s_red[2][kExpandThreads / 32];
+    __shared__ unsigned long long s_red[2][kTileRays / 32];
     __shared__ unsigned long long s_base[2];
-    __shared__ unsigned long long s_off[kTileRays];   // sample offset of each ray in the tile
-    __shared__ unsigned long long s_eoff[kTileRays];  // edge offset (interval mode)
     __shared__ uint32_t s_wsum[2][kTileRays / 32];
-
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x;
     const int r0 = tile * kTileRays;
-    const int nr = min(kTileRays, p.n_rays - r0);
+    const int nr = min(kTileRays, n_rays - r0);
 
-    // tile base = sum of the sums of all earlier tiles
     unsigned long long a = 0, b = 0;
-    for (int i = tid; i < tile; i += kExpandThreads) {
-        const TileSum ts = p.ws.tiles[i];
+    for (int i = tid; i < tile; i += kTileRays) {
+        const TileSum ts = ws.tiles[i];
         a += ts.samples;
         b += ts.runs;
     }
@@ -388,205 +427,140 @@ __global__ void __launch_bounds__(kExpandThreads) expand_kernel(const ExpandPara
         s_red[0][warp] = a;
         s_red[1][warp] = b;
     }
-    // in-tile exclusive scan of the per-ray counts (first 4 warps)
-    uint32_t cs = 0, cr = 0, xs = 0, xr = 0;
-    if (tid < kTileRays) {
-        if (tid < nr) {
-            cs = p.ws.cnt_samples[r0 + tid];
-            cr = p.ws.cnt_runs[r0 + tid];
-        }
-        xs = cs;
-        xr = cr;
+    uint32_t cs = 0, cr = 0;
+    if (tid < nr) {
+        cs = ws.cnt_samples[r0 + tid];
+        cr = ws.cnt_runs[r0 + tid];
+    }
+    uint32_t xs = cs, xr = cr;
 #pragma unroll
-        for (int s = 1; s < 32; s <<= 1) {
-            const uint32_t ys = __shfl_up_sync(0xffffffffu, xs, s);
-            const uint32_t yr = __shfl_up_sync(0xffffffffu, xr, s);
-            if (lane >= s) {
-                xs += ys;
-                xr += yr;
-            }
+    for (int s = 1; s < 32; s <<= 1) {
+        const uint32_t ys = __shfl_up_sync(0xffffffffu, xs, s);
+        const uint32_t yr = __shfl_up_sync(0xffffffffu, xr, s);
+        if (lane >= s) {
+            xs += ys;
+            xr += yr;
         }
-        if (lane == 31) {
-            s_wsum[0][warp] = xs;
-            s_wsum[1][warp] = xr;
-        }
+    }
+    if (lane == 31) {
+        s_wsum[0][warp] = xs;
+        s_wsum[1][warp] = xr;
     }
     __syncthreads();
     if (tid == 0) {
         unsigned long long ta = 0, tb = 0;
-        for (int w = 0; w < kExpandThreads / 32; ++w) {
-            ta += s_red[0][w];
-            tb += s_red[1][w];
+        for (int k = 0; k < kTileRays / 32; ++k) {
+            ta += s_red[0][k];
+            tb += s_red[1][k];
         }
         s_base[0] = ta;
         s_base[1] = tb;
     }
     __syncthreads();
-    if (tid < kTileRays) {
-        unsigned long long ws = 0, wr = 0;
-        for (int w = 0; w < warp; ++w) {
-            ws += s_wsum[0][w];
-            wr += s_wsum[1][w];
-        }
-        const unsigned long long off = s_base[0] + ws + (xs - cs);
-        const unsigned long long eoff = off + s_base[1] + wr + (xr - cr);
-        s_off[tid] = off;
-        s_eoff[tid] = eoff;
-        if (tid < nr) {
-            // packed_info = [chunk_start, chunk_cnt]  (reference data_specs.py:68-69)
-            longlong2 v;
-            v.x = (long long)off;
-            v.y = (long long)cs;
-            *reinterpret_cast<longlong2*>(p.sm_packed_info + 2 * (int64_t)(r0 + tid)) = v;
-            if (kIntervals) {
-                longlong2 e;
-                e.x = (long long)eoff;
-                e.y = (long long)cs + (long long)cr;
-                *reinterpret_cast<longlong2*>(p.iv_packed_info + 2 * (int64_t)(r0 + tid)) = e;
-            }
-        }
+    unsigned long long wsum = 0, wrun = 0;
+    for (int k = 0; k < warp; ++k) {
+        wsum += s_wsum[0][k];
+        wrun += s_wsum[1][k];
     }
-    __syncthreads();
-
-    const Lattice L = lat_make(p.step_size);
-    for (int lr = warp; lr < nr; lr += kExpandThreads / 32) {
-        const int r = r0 + lr;
-        const uint32_t n_runs = p.ws.cnt_runs[r];
-        if (n_runs == 0 || n_runs > (uint32_t)kRunSlots) continue;  // the latter: nfa_march_fill
-        int64_t off = (int64_t)s_off[lr];
-        int64_t eoff = (int64_t)s_eoff[lr];
-        const RunRec* runs = p.ws.runs + (int64_t)r * kRunSlots;
-        for (uint32_t q = 0; q < n_runs; ++q) {
-            const RunRec run = runs[q];
-            RunIter it;
-            it.t = run.t_first;
-            it.left = run.n;
-            bool first_piece = true;
-            while (it.left > 0) {
-                LatPiece pc;
-                const uint32_t c = run_next_piece(L, it, pc);
-                for (uint32_t j = lane; j < c; j += 32) {
-                    const float ts = piece_start(pc, j);
-                    const float te = f_add(ts, L.dt);
-                    const int64_t k = off + j;
-                    if (!kIntervals) {
-                        if (k < p.sample_capacity) {
-                            p.ray_indices[k] = r;
-                            p.t_starts[k] = ts;
-                            p.t_ends[k] = te;
-                        }
-                    } else {
-                        if (k < p.sample_capacity) {
-                            p.ray_indices[k] = r;  // samples.ray_indices
-                            p.sm_vals[k] = f_mul(f_add(te, ts), 0.5f);  // reference grid.cu:251
-                            p.sm_is_valid[k] = 1;
-                        }
-                        const int64_t e = eoff + j;
-                        if (e < p.edge_capacity) {
-                            // left edge of sample j (reference grid.cu:219-245)
-                            p.iv_vals[e] = ts;
-                            p.iv_ray_indices[e] = r;
-                            p.iv_is_left[e] = 1;
-                            p.iv_is_right[e] = (first_piece && j == 0) ? 0 : 1;
-                        }
-                        if (it.left == 0 && j == c - 1 && e + 1 < p.edge_capacity) {
-                            // closing edge of the run
-                            p.iv_vals[e + 1] = te;
-                            p.iv_ray_indices[e + 1] = r;
-                            p.iv_is_left[e + 1] = 0;
-                            p.iv_is_right[e + 1] = 1;
-                        }
-                    }
-                }
-                off += c;
-                eoff += c;
-                first_piece = false;
-            }
-            eoff += 1;  // the closing edge
+    if (tid < nr) {
+        const unsigned long long off = s_base[0] + wsum + (xs - cs);
+        // packed_info = [chunk_start, chunk_cnt]  (reference data_specs.py:68-69)
+        longlong2 v;
+        v.x = (long long)off;
+        v.y = (long long)cs;
+        *reinterpret_cast<longlong2*>(sm_packed_info + 2 * (int64_t)(r0 + tid)) = v;
+        if (kIntervals) {
+            longlong2 e;  // a run of n samples has n + 1 edges
+            e.x = (long long)(off + s_base[1] + wrun + (xr - cr));
+            e.y = (long long)cs + (long long)cr;
+            *reinterpret_cast<longlong2*>(iv_packed_info + 2 * (int64_t)(r0 + tid)) = e;
         }
     }
 }
 
 // ---------------------------------------------------------------------------
-// second pass for rays with more runs than inline slots
+// expand: runs -> per-sample arrays, one warp per run, coalesced stores
 // ---------------------------------------------------------------------------
-struct FillParams {
-    MarchParams m;
-    ExpandParams e;
-    bool want_samples;    // (ray_indices, t_starts, t_ends)
-    bool want_intervals;  // interval-mode arrays
+struct ExpandParams {
+    Workspace ws;
+    const int64_t* totals;  // device copy of the march totals ([1] = number of runs)
+    float step_size;
+    int64_t sample_capacity;
+    const int64_t* sm_packed_info;
+    int64_t* ray_indices;
+    float* t_starts;
+    float* t_ends;
+    // interval mode
+    int64_t edge_capacity;
+    const int64_t* iv_packed_info;
+    float* iv_vals;
+    int64_t* iv_ray_indices;
+    uint8_t* iv_is_left;
+    uint8_t* iv_is_right;
+    float* sm_vals;
+    uint8_t* sm_is_valid;
 };
 
-struct FillSink {
-    const FillParams* fp;
-    Lattice L;
-    int64_t ray;
-    int64_t off;   // next sample slot
-    int64_t eoff;  // next edge slot
-    __device__ __forceinline__ void push(uint32_t, float t_first, uint32_t n)
-    {
-        const ExpandParams& p = fp->e;
-        float t = t_first;
-        for (uint32_t j = 0; j < n; ++j) {
-            const float te = f_add(t, L.dt);
-            if (fp->want_samples && off < p.sample_capacity) {
-                p.ray_indices[off] = ray;
-                p.t_starts[off] = t;
-                p.t_ends[off] = te;
-            }
-            if (fp->want_intervals) {
-                if (off < p.sample_capacity) {
-                    p.ray_indices[off] = ray;
-                    p.sm_vals[off] = f_mul(f_add(te, t), 0.5f);
-                    p.sm_is_valid[off] = 1;
-                }
-                if (eoff < p.edge_capacity) {
-                    p.iv_vals[eoff] = t;
-                    p.iv_ray_indices[eoff] = ray;
-                    p.iv_is_left[eoff] = 1;
-                    p.iv_is_right[eoff] = j == 0 ? 0 : 1;
-                }
-                if (j == n - 1 && eoff + 1 < p.edge_capacity) {
-                    p.iv_vals[eoff + 1] = te;
-                    p.iv_ray_indices[eoff + 1] = ray;
-                    p.iv_is_left[eoff + 1] = 0;
-                    p.iv_is_right[eoff + 1] = 1;
-                }
-            }
-            t = te;
-            ++off;
-            ++eoff;
-        }
-        ++eoff;
-    }
-};
-
-__global__ void __launch_bounds__(128) march_fill_kernel(const FillParams fp)
+template <bool kIntervals>
+__global__ void __launch_bounds__(kExpandThreads) expand_runs_kernel(const ExpandParams p)
 {
-    const MarchParams& p = fp.m;
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= p.n_rays) return;
-    if (p.ws.cnt_runs[r] <= (uint32_t)kRunSlots) return;
-    OccView occ;
-    occ.words = p.words;
-    occ.coarse = p.coarse;
-    occ.g = p.g;
-    const float o[3] = {p.rays_o[3 * (int64_t)r], p.rays_o[3 * (int64_t)r + 1], p.rays_o[3 * (int64_t)r + 2]};
-    const float d[3] = {p.rays_d[3 * (int64_t)r], p.rays_d[3 * (int64_t)r + 1], p.rays_d[3 * (int64_t)r + 2]};
-    FillSink sink;
-    sink.fp = &fp;
-    sink.L = lat_make(p.step_size);
-    sink.ray = r;
-    sink.off = fp.e.sm_packed_info[2 * (int64_t)r];
-    sink.eoff = fp.want_intervals ? fp.e.iv_packed_info[2 * (int64_t)r] : 0;
-    RayMarch m;
-    if (p.t_sorted == nullptr) {
-        march_ray_single(m, sink, occ, o, d, p.near_planes[r], p.far_planes[r], p.aabbs, sink.L, false);
-    } else {
-        const int G = p.g.n_grids;
-        march_ray_sorted(m, sink, occ, o, d, p.near_planes[r], p.far_planes[r], p.aabbs, G,
-                         p.t_sorted + (int64_t)r * 2 * G, p.t_indices + (int64_t)r * 2 * G, p.hits + (int64_t)r * G,
-                         sink.L, false);
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * kExpandThreads + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * kExpandThreads) >> 5;
+    int64_t n_runs = p.totals[1];
+    if (n_runs > p.ws.run_capacity) n_runs = p.ws.run_capacity;  // the host re-runs with a larger pool
+    const Lattice L = lat_make(p.step_size);
+    for (int64_t q = warp0; q < n_runs; q += n_warps) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.ws.pool + q));
+        const int64_t ray = a.x;
+        int64_t off = p.sm_packed_info[2 * ray] + a.y;
+        int64_t eoff = 0;
+        if (kIntervals) {
+            const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.ws.pool + q) + 1);
+            eoff = p.iv_packed_info[2 * ray] + a.y + b.x;
+        }
+        RunIter it;
+        it.t = __uint_as_float(a.w);
+        it.left = a.z;
+        bool first_piece = true;
+        while (it.left > 0) {
+            LatPiece pc;
+            const uint32_t c = run_next_piece(L, it, pc);
+            for (uint32_t j = lane; j < c; j += 32) {
+                const float ts = piece_start(pc, j);
+                const float te = f_add(ts, L.dt);
+                const int64_t k = off + j;
+                if (!kIntervals) {
+                    if (k < p.sample_capacity) {
+                        p.ray_indices[k] = ray;
+                        p.t_starts[k] = ts;
+                        p.t_ends[k] = te;
+                    }
+                } else {
+                    if (k < p.sample_capacity) {
+                        p.ray_indices[k] = ray;                     // samples.ray_indices
+                        p.sm_vals[k] = f_mul(f_add(te, ts), 0.5f);  // reference grid.cu:251
+                        p.sm_is_valid[k] = 1;
+                    }
+                    const int64_t e = eoff + j;
+                    if (e < p.edge_capacity) {  // left edge of sample j (reference grid.cu:219-245)
+                        p.iv_vals[e] = ts;
+                        p.iv_ray_indices[e] = ray;
+                        p.iv_is_left[e] = 1;
+                        p.iv_is_right[e] = (first_piece && j == 0) ? 0 : 1;
+                    }
+                    if (it.left == 0 && j == c - 1 && e + 1 < p.edge_capacity) {  // closing edge of the run
+                        p.iv_vals[e + 1] = te;
+                        p.iv_ray_indices[e + 1] = ray;
+                        p.iv_is_left[e + 1] = 0;
+                        p.iv_is_right[e + 1] = 1;
+                    }
+                }
+            }
+            off += c;
+            eoff += c;
+            first_piece = false;
+        }
     }
 }
 
@@ -734,20 +708,28 @@ int32_t nfa_occ_pack(int32_t n_grids, int32_t rx, int32_t ry, int32_t rz, const 
     return launch_status();
 }
 
-int64_t nfa_march_workspace_bytes(int32_t n_rays) { return n_rays < 0 ? 0 : ws_bytes(n_rays); }
-
-static int32_t fill_march_params(MarchParams& p, int32_t n_rays, const float* rays_o, const float* rays_d,
-                                 const float* near_planes, const float* far_planes, int32_t n_grids, int32_t rx,
-                                 int32_t ry, int32_t rz, const uint64_t* words, const uint32_t* coarse,
-                                 const float* aabbs, const float* t_sorted, const int64_t* t_indices,
-                                 const uint8_t* hits, float step_size, void* workspace)
+int64_t nfa_march_workspace_bytes(int32_t n_rays, int64_t run_capacity)
 {
-    if (n_rays < 0 || n_grids <= 0 || rx <= 0 || ry <= 0 || rz <= 0) return NFA_ERR_ARG;
+    return (n_rays < 0 || run_capacity < 0) ? 0 : ws_bytes(n_rays, run_capacity);
+}
+
+int32_t nfa_march(int32_t n_rays, const float* rays_o, const float* rays_d, const float* near_planes,
+                  const float* far_planes, int32_t n_grids, int32_t rx, int32_t ry, int32_t rz,
+                  const uint64_t* words, const uint32_t* coarse, const float* aabbs, const float* t_sorted,
+                  const int64_t* t_indices, const uint8_t* hits, float step_size, int64_t run_capacity,
+                  void* workspace, int64_t* totals, float* terminate_planes, nfa_stream_t stream)
+{
+    if (n_rays < 0 || n_grids <= 0 || rx <= 0 || ry <= 0 || rz <= 0 || run_capacity < 0) return NFA_ERR_ARG;
+    if (run_capacity > (int64_t)UINT32_MAX) return NFA_ERR_UNSUPPORTED;
     if (!(step_size > 0.0f)) return NFA_ERR_UNSUPPORTED;
-    if (n_rays > 0 && (!rays_o || !rays_d || !near_planes || !far_planes || !words || !coarse || !aabbs || !workspace))
+    if (!totals) return NFA_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n_rays == 0) return (int32_t)cudaMemsetAsync(totals, 0, 4 * sizeof(int64_t), s);
+    if (!rays_o || !rays_d || !near_planes || !far_planes || !words || !coarse || !aabbs || !workspace)
         return NFA_ERR_ARG;
     const bool have_sorted = t_sorted && t_indices && hits;
     if (!have_sorted && n_grids != 1) return NFA_ERR_ARG;
+    MarchParams p;
     p.n_rays = n_rays;
     p.rays_o = rays_o;
     p.rays_d = rays_d;
@@ -762,137 +744,96 @@ static int32_t fill_march_params(MarchParams& p, int32_t n_rays, const float* ra
     p.t_indices = have_sorted ? t_indices : nullptr;
     p.hits = have_sorted ? hits : nullptr;
     p.step_size = step_size;
-    p.ws = ws_view(workspace, n_rays);
-    p.totals = nullptr;
-    p.terminate = nullptr;
-    return NFA_OK;
-}
-
-int32_t nfa_march(int32_t n_rays, const float* rays_o, const float* rays_d, const float* near_planes,
-                  const float* far_planes, int32_t n_grids, int32_t rx, int32_t ry, int32_t rz,
-                  const uint64_t* words, const uint32_t* coarse, const float* aabbs, const float* t_sorted,
-                  const int64_t* t_indices, const uint8_t* hits, float step_size, void* workspace, int64_t* totals,
-                  float* terminate_planes, nfa_stream_t stream)
-{
-    MarchParams p;
-    const int32_t rc = fill_march_params(p, n_rays, rays_o, rays_d, near_planes, far_planes, n_grids, rx, ry, rz,
-                                         words, coarse, aabbs, t_sorted, t_indices, hits, step_size, workspace);
-    if (rc != NFA_OK) return rc;
-    if (!totals) return NFA_ERR_ARG;
+    p.ws = ws_view(workspace, n_rays, run_capacity);
     p.totals = totals;
     p.terminate = terminate_planes;
-    cudaStream_t s = (cudaStream_t)stream;
-    if (n_rays == 0) {
-        return (int32_t)cudaMemsetAsync(totals, 0, 4 * sizeof(int64_t), s);
-    }
     const int tiles = p.ws.n_tiles;
     const size_t coarse_bytes = (size_t)p.coarse_words * 4;
     // keep the brick mip in shared memory while it leaves room for >= 2 CTAs / SM
-    if (coarse_bytes <= 96 * 1024) {
-        if (coarse_bytes > 40 * 1024)
-            cudaFuncSetAttribute(march_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        march_kernel<true><<<tiles, kTileRays, coarse_bytes, s>>>(p);
+    const bool smem_coarse = coarse_bytes <= 96 * 1024;
+    const size_t dyn = smem_coarse ? coarse_bytes : 0;
+#define NFA_LAUNCH_MARCH(S, C)                                                                          \
+    do {                                                                                                \
+        if (dyn > 32 * 1024)                                                                            \
+            cudaFuncSetAttribute(march_kernel<S, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); \
+        march_kernel<S, C><<<tiles, kTileRays, dyn, s>>>(p);                                            \
+    } while (0)
+    if (!have_sorted) {
+        if (smem_coarse) NFA_LAUNCH_MARCH(true, true); else NFA_LAUNCH_MARCH(true, false);
     } else {
-        march_kernel<false><<<tiles, kTileRays, 0, s>>>(p);
+        if (smem_coarse) NFA_LAUNCH_MARCH(false, true); else NFA_LAUNCH_MARCH(false, false);
+    }
+#undef NFA_LAUNCH_MARCH
+    return launch_status();
+}
+
+static inline int expand_grid(int64_t run_capacity)
+{
+    const int64_t ctas = (run_capacity * 32 + kExpandThreads - 1) / kExpandThreads;
+    const int64_t cap = 148 * 8;  // 8 resident CTAs of 256 threads per SM
+    return (int)(ctas < 1 ? 1 : (ctas < cap ? ctas : cap));
+}
+
+int32_t nfa_expand_samples(int32_t n_rays, int64_t run_capacity, const void* workspace, const int64_t* totals,
+                           float step_size, int64_t capacity, int64_t* packed_info, int64_t* ray_indices,
+                           float* t_starts, float* t_ends, nfa_stream_t stream)
+{
+    if (n_rays < 0 || capacity < 0 || run_capacity < 0) return NFA_ERR_ARG;
+    if (n_rays == 0) return NFA_OK;
+    if (!workspace || !packed_info || !totals) return NFA_ERR_ARG;
+    if (capacity > 0 && (!ray_indices || !t_starts || !t_ends)) return NFA_ERR_ARG;
+    if ((((uintptr_t)packed_info) & 15u) != 0) return NFA_ERR_ARG;
+    const Workspace ws = ws_view(const_cast<void*>(workspace), n_rays, run_capacity);
+    cudaStream_t s = (cudaStream_t)stream;
+    offsets_kernel<false><<<ws.n_tiles, kTileRays, 0, s>>>(n_rays, ws, packed_info, nullptr);
+    if (capacity > 0 && run_capacity > 0) {
+        ExpandParams p = {};
+        p.ws = ws;
+        p.totals = totals;
+        p.step_size = step_size;
+        p.sample_capacity = capacity;
+        p.sm_packed_info = packed_info;
+        p.ray_indices = ray_indices;
+        p.t_starts = t_starts;
+        p.t_ends = t_ends;
+        expand_runs_kernel<false><<<expand_grid(run_capacity), kExpandThreads, 0, s>>>(p);
     }
     return launch_status();
 }
 
-int32_t nfa_expand_samples(int32_t n_rays, const void* workspace, float step_size, int64_t capacity,
-                           int64_t* packed_info, int64_t* ray_indices, float* t_starts, float* t_ends,
-                           nfa_stream_t stream)
+int32_t nfa_expand_intervals(int32_t n_rays, int64_t run_capacity, const void* workspace, const int64_t* totals,
+                             float step_size, int64_t edge_capacity, int64_t sample_capacity,
+                             int64_t* iv_packed_info, float* iv_vals, int64_t* iv_ray_indices, uint8_t* iv_is_left,
+                             uint8_t* iv_is_right, int64_t* sm_packed_info, float* sm_vals, int64_t* sm_ray_indices,
+                             uint8_t* sm_is_valid, nfa_stream_t stream)
 {
-    if (n_rays < 0 || capacity < 0) return NFA_ERR_ARG;
+    if (n_rays < 0 || edge_capacity < 0 || sample_capacity < 0 || run_capacity < 0) return NFA_ERR_ARG;
     if (n_rays == 0) return NFA_OK;
-    if (!workspace || !packed_info) return NFA_ERR_ARG;
-    if (capacity > 0 && (!ray_indices || !t_starts || !t_ends)) return NFA_ERR_ARG;
-    if ((((uintptr_t)packed_info) & 15u) != 0) return NFA_ERR_ARG;
-    ExpandParams p = {};
-    p.n_rays = n_rays;
-    p.ws = ws_view(const_cast<void*>(workspace), n_rays);
-    p.step_size = step_size;
-    p.sample_capacity = capacity;
-    p.sm_packed_info = packed_info;
-    p.ray_indices = ray_indices;
-    p.t_starts = t_starts;
-    p.t_ends = t_ends;
-    expand_kernel<false><<<p.ws.n_tiles, kExpandThreads, 0, (cudaStream_t)stream>>>(p);
-    return launch_status();
-}
-
-int32_t nfa_expand_intervals(int32_t n_rays, const void* workspace, float step_size, int64_t edge_capacity,
-                             int64_t sample_capacity, int64_t* iv_packed_info, float* iv_vals,
-                             int64_t* iv_ray_indices, uint8_t* iv_is_left, uint8_t* iv_is_right,
-                             int64_t* sm_packed_info, float* sm_vals, int64_t* sm_ray_indices, uint8_t* sm_is_valid,
-                             nfa_stream_t stream)
-{
-    if (n_rays < 0 || edge_capacity < 0 || sample_capacity < 0) return NFA_ERR_ARG;
-    if (n_rays == 0) return NFA_OK;
-    if (!workspace || !iv_packed_info || !sm_packed_info) return NFA_ERR_ARG;
+    if (!workspace || !iv_packed_info || !sm_packed_info || !totals) return NFA_ERR_ARG;
     if (edge_capacity > 0 && (!iv_vals || !iv_ray_indices || !iv_is_left || !iv_is_right)) return NFA_ERR_ARG;
     if (sample_capacity > 0 && (!sm_vals || !sm_ray_indices || !sm_is_valid)) return NFA_ERR_ARG;
     if (((((uintptr_t)iv_packed_info) | ((uintptr_t)sm_packed_info)) & 15u) != 0) return NFA_ERR_ARG;
-    ExpandParams p = {};
-    p.n_rays = n_rays;
-    p.ws = ws_view(const_cast<void*>(workspace), n_rays);
-    p.step_size = step_size;
-    p.sample_capacity = sample_capacity;
-    p.sm_packed_info = sm_packed_info;
-    p.ray_indices = sm_ray_indices;
-    p.edge_capacity = edge_capacity;
-    p.iv_packed_info = iv_packed_info;
-    p.iv_vals = iv_vals;
-    p.iv_ray_indices = iv_ray_indices;
-    p.iv_is_left = iv_is_left;
-    p.iv_is_right = iv_is_right;
-    p.sm_vals = sm_vals;
-    p.sm_is_valid = sm_is_valid;
-    expand_kernel<true><<<p.ws.n_tiles, kExpandThreads, 0, (cudaStream_t)stream>>>(p);
-    return launch_status();
-}
-
-int32_t nfa_march_fill(int32_t n_rays, const float* rays_o, const float* rays_d, const float* near_planes,
-                       const float* far_planes, int32_t n_grids, int32_t rx, int32_t ry, int32_t rz,
-                       const uint64_t* words, const uint32_t* coarse, const float* aabbs, const float* t_sorted,
-                       const int64_t* t_indices, const uint8_t* hits, float step_size, const void* workspace,
-                       int64_t sample_capacity, const int64_t* sm_packed_info, int64_t* ray_indices, float* t_starts,
-                       float* t_ends, int64_t edge_capacity, const int64_t* iv_packed_info, float* iv_vals,
-                       int64_t* iv_ray_indices, uint8_t* iv_is_left, uint8_t* iv_is_right, float* sm_vals,
-                       int64_t* sm_ray_indices, uint8_t* sm_is_valid, nfa_stream_t stream)
-{
-    FillParams fp = {};
-    const int32_t rc =
-        fill_march_params(fp.m, n_rays, rays_o, rays_d, near_planes, far_planes, n_grids, rx, ry, rz, words, coarse,
-                          aabbs, t_sorted, t_indices, hits, step_size, const_cast<void*>(workspace));
-    if (rc != NFA_OK) return rc;
-    if (n_rays == 0) return NFA_OK;
-    if (!sm_packed_info) return NFA_ERR_ARG;
-    fp.want_samples = t_starts != nullptr;
-    fp.want_intervals = iv_vals != nullptr;
-    if (fp.want_samples == fp.want_intervals) return NFA_ERR_ARG;  // exactly one output group
-    fp.e.n_rays = n_rays;
-    fp.e.sample_capacity = sample_capacity;
-    fp.e.sm_packed_info = const_cast<int64_t*>(sm_packed_info);
-    if (fp.want_samples) {
-        if (!ray_indices || !t_ends) return NFA_ERR_ARG;
-        fp.e.ray_indices = ray_indices;
-        fp.e.t_starts = t_starts;
-        fp.e.t_ends = t_ends;
-    } else {
-        if (!iv_packed_info || !iv_ray_indices || !iv_is_left || !iv_is_right || !sm_vals || !sm_ray_indices ||
-            !sm_is_valid)
-            return NFA_ERR_ARG;
-        fp.e.ray_indices = sm_ray_indices;
-        fp.e.edge_capacity = edge_capacity;
-        fp.e.iv_packed_info = const_cast<int64_t*>(iv_packed_info);
-        fp.e.iv_vals = iv_vals;
-        fp.e.iv_ray_indices = iv_ray_indices;
-        fp.e.iv_is_left = iv_is_left;
-        fp.e.iv_is_right = iv_is_right;
-        fp.e.sm_vals = sm_vals;
-        fp.e.sm_is_valid = sm_is_valid;
+    const Workspace ws = ws_view(const_cast<void*>(workspace), n_rays, run_capacity);
+    cudaStream_t s = (cudaStream_t)stream;
+    offsets_kernel<true><<<ws.n_tiles, kTileRays, 0, s>>>(n_rays, ws, sm_packed_info, iv_packed_info);
+    if (edge_capacity > 0 && run_capacity > 0) {
+        ExpandParams p = {};
+        p.ws = ws;
+        p.totals = totals;
+        p.step_size = step_size;
+        p.sample_capacity = sample_capacity;
+        p.sm_packed_info = sm_packed_info;
+        p.ray_indices = sm_ray_indices;
+        p.edge_capacity = edge_capacity;
+        p.iv_packed_info = iv_packed_info;
+        p.iv_vals = iv_vals;
+        p.iv_ray_indices = iv_ray_indices;
+        p.iv_is_left = iv_is_left;
+        p.iv_is_right = iv_is_right;
+        p.sm_vals = sm_vals;
+        p.sm_is_valid = sm_is_valid;
+        expand_runs_kernel<true><<<expand_grid(run_capacity), kExpandThreads, 0, s>>>(p);
     }
-    march_fill_kernel<<<(n_rays + 127) / 128, 128, 0, (cudaStream_t)stream>>>(fp);
     return launch_status();
 }
 

@@ -108,13 +108,22 @@ def _packed_grid(binaries: Tensor) -> _OccPack:
 
 
 class _MarchScratch:
-    """Per-(device, n_rays) reusable workspace + pinned read-back slot."""
+    """Per-(device, n_rays) reusable workspace (counts, tile sums, run pool) + pinned read-back slot."""
 
     def __init__(self, device, n_rays: int):
-        lib = _lib.load()
-        self.workspace = torch.zeros(lib.nfa_march_workspace_bytes(n_rays), dtype=torch.uint8, device=device)
+        self.device, self.n_rays = device, n_rays
+        self.run_capacity = 0
+        self.workspace = None
         self.totals_dev = torch.zeros(4, dtype=torch.int64, device=device)
         self.totals_host = torch.zeros(4, dtype=torch.int64).pin_memory()
+        self.reserve(2 * n_rays + 1024)
+
+    def reserve(self, run_capacity: int) -> None:
+        if run_capacity > self.run_capacity:
+            lib = _lib.load()
+            self.run_capacity = int(run_capacity)
+            self.workspace = torch.zeros(lib.nfa_march_workspace_bytes(self.n_rays, self.run_capacity),
+                                         dtype=torch.uint8, device=self.device)
 
 
 _scratch_cache: Dict[tuple, _MarchScratch] = {}
@@ -140,7 +149,12 @@ def _march(rays_o: Tensor, rays_d: Tensor, binaries: Tensor, aabbs: Tensor, near
            far_planes: Tensor, step_size: float, t_sorted: Optional[Tensor], t_indices: Optional[Tensor],
            hits: Optional[Tensor], want_intervals: bool, want_terminate: bool,
            capacity_hint: int = 0) -> _MarchResult:
-    """Constant-step traversal: march -> (sync) -> expand."""
+    """Constant-step traversal: march -> expand, with ONE host synchronisation.
+
+    With a `capacity_hint` (size of the previous batch plus head-room) the expand
+    kernels are queued behind the march before the host waits for the totals; only if
+    the batch outgrew the hint (or the run pool) is the cheap tail re-run.
+    """
     device = rays_o.device
     n_rays = rays_o.shape[0]
     n_grids, rx, ry, rz = (int(s) for s in binaries.shape)
@@ -154,53 +168,57 @@ def _march(rays_o: Tensor, rays_d: Tensor, binaries: Tensor, aabbs: Tensor, near
                       _lib.ptr(aabbs), _lib.ptr(t_sorted), _lib.ptr(t_indices), _lib.ptr(hits))
     sc = _scratch(device, n_rays)
     term = torch.empty(n_rays, dtype=torch.float32, device=device) if want_terminate else None
-    geom = (n_grids, rx, ry, rz)
-    march_args = (n_rays, _lib.ptr(rays_o), _lib.ptr(rays_d), _lib.ptr(near_planes), _lib.ptr(far_planes), *geom,
-                  _lib.ptr(occ.words), _lib.ptr(occ.coarse), _lib.ptr(aabbs), _lib.ptr(t_sorted),
-                  _lib.ptr(t_indices), _lib.ptr(hits), float(step_size), _lib.ptr(sc.workspace))
-    _lib.call("nfa_march", device, *march_args, _lib.ptr(sc.totals_dev), _lib.ptr(term))
-    sc.totals_host.copy_(sc.totals_dev, non_blocking=True)
-
-    res = _MarchResult()
-    res.terminate_planes = term
-    res.intervals = res.samples = None
     stream = torch.cuda.current_stream(device)
+    step_size = float(step_size)
+
+    def march():
+        _lib.call("nfa_march", device, n_rays, _lib.ptr(rays_o), _lib.ptr(rays_d), _lib.ptr(near_planes),
+                  _lib.ptr(far_planes), n_grids, rx, ry, rz, _lib.ptr(occ.words), _lib.ptr(occ.coarse),
+                  _lib.ptr(aabbs), _lib.ptr(t_sorted), _lib.ptr(t_indices), _lib.ptr(hits), step_size,
+                  sc.run_capacity, _lib.ptr(sc.workspace), _lib.ptr(sc.totals_dev), _lib.ptr(term))
+        sc.totals_host.copy_(sc.totals_dev, non_blocking=True)
 
     def read_totals():
         stream.synchronize()
-        n, runs, over, stuck = (int(v) for v in sc.totals_host.tolist())
+        n, runs, _, stuck = (int(v) for v in sc.totals_host.tolist())
         if stuck:
             raise RuntimeError(
                 f"traverse_grids: step_size={step_size} is below the float32 resolution of the marching "
                 f"distance on {stuck} ray(s); the march cannot advance (the reference would not terminate).")
-        return n, runs, over
+        return n, runs
 
     packed_info = torch.empty((n_rays, 2), dtype=torch.int64, device=device)
-    if not want_intervals:
-        def expand(cap):
-            ri = torch.empty(cap, dtype=torch.int64, device=device)
-            ts = torch.empty(cap, dtype=torch.float32, device=device)
-            te = torch.empty(cap, dtype=torch.float32, device=device)
-            _lib.call("nfa_expand_samples", device, n_rays, _lib.ptr(sc.workspace), float(step_size), cap,
-                      _lib.ptr(packed_info), _lib.ptr(ri), _lib.ptr(ts), _lib.ptr(te))
-            return ri, ts, te
 
+    def expand_samples(cap):
+        ri = torch.empty(cap, dtype=torch.int64, device=device)
+        ts = torch.empty(cap, dtype=torch.float32, device=device)
+        te = torch.empty(cap, dtype=torch.float32, device=device)
+        _lib.call("nfa_expand_samples", device, n_rays, sc.run_capacity, _lib.ptr(sc.workspace),
+                  _lib.ptr(sc.totals_dev), step_size, cap, _lib.ptr(packed_info), _lib.ptr(ri), _lib.ptr(ts),
+                  _lib.ptr(te))
+        return ri, ts, te
+
+    res = _MarchResult()
+    res.terminate_planes = term
+    res.intervals = res.samples = None
+
+    march()
+    bufs, cap = None, 0
+    if not want_intervals and capacity_hint > 0:
+        cap = int(capacity_hint)
+        bufs = expand_samples(cap)  # speculative: queued before the sync
+    n, runs = read_totals()
+    if runs > sc.run_capacity:  # run pool overflow: rare (very fragmented grids); re-march with room
+        sc.reserve(runs + (runs >> 2) + 1024)
+        march()
+        n, runs = read_totals()
         bufs = None
-        if capacity_hint > 0:
-            bufs = expand(capacity_hint)
-        n, runs, over = read_totals()
-        if bufs is None or n > capacity_hint:
-            bufs = expand(n)
-            cap = n
-        else:
-            cap = capacity_hint
+    if not want_intervals:
+        if bufs is None or n > cap:
+            bufs = expand_samples(n)
         ri, ts, te = bufs
-        if over:
-            _lib.call("nfa_march_fill", device, *march_args, cap, _lib.ptr(packed_info), _lib.ptr(ri), _lib.ptr(ts),
-                      _lib.ptr(te), 0, None, None, None, None, None, None, None, None)
         res.ray_indices, res.t_starts, res.t_ends = ri[:n], ts[:n], te[:n]
     else:
-        n, runs, over = read_totals()
         e = n + runs
         iv_pi = torch.empty((n_rays, 2), dtype=torch.int64, device=device)
         iv_vals = torch.empty(e, dtype=torch.float32, device=device)
@@ -210,13 +228,10 @@ def _march(rays_o: Tensor, rays_d: Tensor, binaries: Tensor, aabbs: Tensor, near
         sm_vals = torch.empty(n, dtype=torch.float32, device=device)
         sm_ray = torch.empty(n, dtype=torch.int64, device=device)
         sm_valid = torch.empty(n, dtype=torch.bool, device=device)
-        _lib.call("nfa_expand_intervals", device, n_rays, _lib.ptr(sc.workspace), float(step_size), e, n,
-                  _lib.ptr(iv_pi), _lib.ptr(iv_vals), _lib.ptr(iv_ray), _lib.ptr(iv_left), _lib.ptr(iv_right),
-                  _lib.ptr(packed_info), _lib.ptr(sm_vals), _lib.ptr(sm_ray), _lib.ptr(sm_valid))
-        if over:
-            _lib.call("nfa_march_fill", device, *march_args, n, _lib.ptr(packed_info), None, None, None,
-                      e, _lib.ptr(iv_pi), _lib.ptr(iv_vals), _lib.ptr(iv_ray), _lib.ptr(iv_left),
-                      _lib.ptr(iv_right), _lib.ptr(sm_vals), _lib.ptr(sm_ray), _lib.ptr(sm_valid))
+        _lib.call("nfa_expand_intervals", device, n_rays, sc.run_capacity, _lib.ptr(sc.workspace),
+                  _lib.ptr(sc.totals_dev), step_size, e, n, _lib.ptr(iv_pi), _lib.ptr(iv_vals), _lib.ptr(iv_ray),
+                  _lib.ptr(iv_left), _lib.ptr(iv_right), _lib.ptr(packed_info), _lib.ptr(sm_vals), _lib.ptr(sm_ray),
+                  _lib.ptr(sm_valid))
         res.intervals = RayIntervals(vals=iv_vals, packed_info=iv_pi, ray_indices=iv_ray, is_left=iv_left,
                                      is_right=iv_right)
         res.samples = RaySamples(vals=sm_vals, packed_info=packed_info, ray_indices=sm_ray, is_valid=sm_valid)

@@ -72,11 +72,42 @@ void sim_occ_pack(int n_grids, int rx, int ry, int rz, const uint8_t* binaries, 
                 }
 }
 
-struct VecSink {
-    std::vector<float>* t;
-    std::vector<uint32_t>* n;
-    void push(uint32_t, float t_first, uint32_t cnt) { t->push_back(t_first); n->push_back(cnt); }
+}  // extern "C"
+
+// descriptor buffer with the same capacity as the device kernel's per-ray slots
+struct HostBuf {
+    enum { K = 8 };
+    float pend[K], open[K];
+    bool joined[K];
+    void put(int j, float p, float o, bool jn) { pend[j] = p; open[j] = o; joined[j] = jn; }
 };
+
+template <class Boxes>
+static float march_one(const Boxes& boxes, const OccView& occ, const float* o, const float* d, float near, float far,
+                       const Lattice& L, LatState& m, std::vector<float>& vt, std::vector<uint32_t>& vn)
+{
+    Walk w;
+    walk_init(w, o, d, near, far);
+    lat_init(m, L, near);
+    HostBuf buf;
+    int n_desc = 0;
+    RunOut out;
+    // same chunked structure as the kernel: walk until the buffer is full, then flush it
+    for (long guard = 0; guard < (1L << 26); ++guard) {
+        while (!w.done && n_desc < HostBuf::K) walk_step(w, boxes, occ, buf, n_desc);
+        for (int j = 0; j < n_desc; ++j) {
+            lat_consume(m, buf.pend[j], buf.open[j], buf.joined[j], out);
+            if (out.valid) { vt.push_back(out.t_first); vn.push_back(out.n); }
+        }
+        n_desc = 0;
+        if (w.done) break;
+    }
+    const float term = lat_finish(m, walk_tail_pend(w), true, out);
+    if (out.valid) { vt.push_back(out.t_first); vn.push_back(out.n); }
+    return term;
+}
+
+extern "C" {
 
 // March all rays; per ray: n_samples, n_runs, terminate plane; runs appended to
 // flat arrays (caller passes capacity; returns total runs or -1 on overflow).
@@ -100,15 +131,16 @@ int64_t sim_march(int32_t n_rays, const float* rays_o, const float* rays_d,
     for (int32_t r = 0; r < n_rays; ++r) {
         vt.clear();
         vn.clear();
-        VecSink sink{&vt, &vn};
-        RayMarch m;
+        LatState m;
         float term;
-        if (t_sorted == nullptr)
-            term = march_ray_single(m, sink, occ, rays_o + 3 * r, rays_d + 3 * r, near_planes[r], far_planes[r], aabbs, L, true);
-        else
-            term = march_ray_sorted(m, sink, occ, rays_o + 3 * r, rays_d + 3 * r, near_planes[r], far_planes[r], aabbs,
-                                    n_grids, t_sorted + (int64_t)r * 2 * n_grids, t_indices + (int64_t)r * 2 * n_grids,
-                                    hits + (int64_t)r * n_grids, L, true);
+        if (t_sorted == nullptr) {
+            SingleBox b{aabbs};
+            term = march_one(b, occ, rays_o + 3 * r, rays_d + 3 * r, near_planes[r], far_planes[r], L, m, vt, vn);
+        } else {
+            SortedBoxes b{aabbs, n_grids, t_sorted + (int64_t)r * 2 * n_grids, t_indices + (int64_t)r * 2 * n_grids,
+                          hits + (int64_t)r * n_grids};
+            term = march_one(b, occ, rays_o + 3 * r, rays_d + 3 * r, near_planes[r], far_planes[r], L, m, vt, vn);
+        }
         n_samples[r] = m.n_samples;
         n_runs[r] = m.n_runs;
         terminate[r] = term;

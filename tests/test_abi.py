@@ -40,7 +40,7 @@ def test_version_and_error_strings_without_gpu():
     assert lib.nfa_occ_words(1, 128, 128, 128) == 32 ** 3
     assert lib.nfa_occ_coarse_words(1, 128, 128, 128) == 1024
     assert lib.nfa_occ_words(2, 30, 17, 5) == 2 * 8 * 5 * 2
-    assert lib.nfa_march_workspace_bytes(65536) > 65536 * 8 * _lib.RUN_SLOTS
+    assert lib.nfa_march_workspace_bytes(65536, 1000) > 65536 * 8 + 1000 * 32
     assert lib.nfa_pack_info_workspace_bytes(10) >= 80
     assert lib.nfa_scan_by_key_workspace_bytes(1 << 20) > 0
 
@@ -52,7 +52,7 @@ def test_argument_errors_do_not_need_a_gpu():
     assert lib.nfa_scan_packed(4, None, None, None, 0, 0, 0, 0, None) == -1
     assert lib.nfa_composite_fwd(3, None, None, None, None, 0, None, None, None, 1, *([None] * 8)) == -1
     assert lib.nfa_intersect_sorted(1, None, None, 64, None, None, None, None, None) == -2  # > 32 boxes: unsupported
-    assert lib.nfa_march_workspace_bytes(-5) == 0
+    assert lib.nfa_march_workspace_bytes(-5, 10) == 0
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
