@@ -128,10 +128,11 @@ int32_t nfa_expand_intervals(int32_t n_rays, int64_t run_capacity, const void* w
  *   normalisation (:157-158) and background blend (:161-162).
  * from_alpha == 0: `sigmas_or_alphas` holds sigmas and t_starts/t_ends are required;
  * from_alpha != 0: it holds alphas (t_starts/t_ends only needed for depths).
+ * n_samples = length N of the per-sample arrays (segments in packed_info index into them).
  * Nullable: rgbs, prefix_trans, bkgd[3], every output.  Per-sample outputs [N]
  * (weights, trans, alphas), per-ray outputs colors [R,3], opacities [R], depths [R];
  * raw [R,5] keeps the un-normalised (colour, opacity, depth) sums for the backward. */
-int32_t nfa_composite_fwd(int32_t n_rays, const int64_t* packed_info,
+int32_t nfa_composite_fwd(int32_t n_rays, int64_t n_samples, const int64_t* packed_info,
                           const float* t_starts, const float* t_ends,
                           const float* sigmas_or_alphas, int32_t from_alpha,
                           const float* rgbs, const float* prefix_trans, const float* bkgd,
@@ -147,7 +148,7 @@ int32_t nfa_composite_fwd(int32_t n_rays, const int64_t* packed_info,
  * Upstream gradients (all nullable): g_colors [R,3], g_opacities [R], g_depths [R] on the
  * values nfa_composite_fwd returned (needs `raw`), g_weights / g_trans / g_alphas [N] on
  * the per-sample outputs.  Outputs: g_in [N] (d/dsigma or d/dalpha), g_rgbs [N,3] (nullable). */
-int32_t nfa_composite_bwd(int32_t n_rays, const int64_t* packed_info,
+int32_t nfa_composite_bwd(int32_t n_rays, int64_t n_samples, const int64_t* packed_info,
                           const float* t_starts, const float* t_ends,
                           const float* sigmas_or_alphas, int32_t from_alpha,
                           const float* rgbs, const float* prefix_trans, const float* bkgd,

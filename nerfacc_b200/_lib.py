@@ -36,10 +36,10 @@ SIGNATURES = {
     "nfa_expand_samples": (_c_i32, [_c_i32, _c_i64, _c_ptr, _c_ptr, _c_f32, _c_i64, _c_ptr, _c_ptr, _c_ptr, _c_ptr,
                                     _c_ptr]),
     "nfa_expand_intervals": (_c_i32, [_c_i32, _c_i64, _c_ptr, _c_ptr, _c_f32, _c_i64, _c_i64] + [_c_ptr] * 10),
-    "nfa_composite_fwd": (_c_i32, [_c_i32, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_ptr, _c_ptr, _c_ptr, _c_i32]
-                          + [_c_ptr] * 8),
-    "nfa_composite_bwd": (_c_i32, [_c_i32, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_ptr, _c_ptr, _c_ptr, _c_i32]
-                          + [_c_ptr] * 10),
+    "nfa_composite_fwd": (_c_i32, [_c_i32, _c_i64, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_ptr, _c_ptr, _c_ptr,
+                                   _c_i32] + [_c_ptr] * 8),
+    "nfa_composite_bwd": (_c_i32, [_c_i32, _c_i64, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_ptr, _c_ptr, _c_ptr,
+                                   _c_i32] + [_c_ptr] * 10),
     "nfa_accumulate_fwd": (_c_i32, [_c_i32, _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_ptr, _c_ptr]),
     "nfa_accumulate_atomic": (_c_i32, [_c_i64, _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_ptr, _c_ptr]),
     "nfa_accumulate_bwd": (_c_i32, [_c_i64, _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_ptr, _c_ptr, _c_ptr, _c_ptr]),
@@ -103,8 +103,13 @@ def require_cuda(t: torch.Tensor, what: str) -> None:
 def call(name: str, device, *args) -> None:
     """Invoke a kernel-launching entry point on `device`'s current stream."""
     global launches
-    lib = load()
-    with torch.cuda.device(device):
-        rc = getattr(lib, name)(*args, stream_ptr(device))
+    fn = getattr(_lib if _lib is not None else load(), name)
+    stream = torch.cuda.current_stream(device).cuda_stream
+    if device.index is None or device.index == torch.cuda.current_device():
+        rc = fn(*args, stream)
+    else:
+        with torch.cuda.device(device):
+            rc = fn(*args, stream)
     launches += 1
-    check(rc, name)
+    if rc != 0:
+        check(rc, name)

@@ -79,6 +79,11 @@ struct CompositeParams {
     float* g_rgbs;   // [N,3] or null
 };
 
+// exp(-x) for x >= 0 through MUFU.EX2 (ex2.approx): the outputs are in [0, 1] and the absolute
+// error stays ~1e-6 for the |x| <= 15 that still give a non-negligible result -- inside the 1e-5
+// parity tolerance -- while the accurate expf costs ~5x the instructions in an issue-bound kernel.
+__device__ __forceinline__ float exp_neg(float x) { return __expf(-x); }
+
 constexpr float kEpsF32 = 1.1920929e-07f;  // torch.finfo(float32).eps, reference volrend.py:158
 
 // per-sample forward quantities for one 32-sample tile of a ray
@@ -106,8 +111,8 @@ __device__ __forceinline__ void tile_forward(const CompositeParams& p, int64_t i
         // reference volrend.py:271-275
         const float sd = v * q.delta;
         const float incl = warp_scan_sum(sd, lane);
-        T = expf(-(carry + (incl - sd)));
-        q.a = 1.0f - expf(-sd);
+        T = exp_neg(carry + (incl - sd));
+        q.a = 1.0f - exp_neg(sd);
         q.x = sd;
         carry += __shfl_sync(kFull, incl, 31);
     } else {
@@ -130,12 +135,12 @@ template <bool kAlpha>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) composite_fwd_kernel(const CompositeParams p)
 {
     const int lane = threadIdx.x & 31;
-    const int r = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-    if (r >= p.n_rays) return;
+    const bool accumulate = p.opac != nullptr || p.colors != nullptr || p.depths != nullptr || p.raw != nullptr;
+    // persistent warps: ray = global warp id, then stride by the number of warps in the grid
+    for (int r = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); r < p.n_rays; r += gridDim.x * kWarpsPerCta) {
     const longlong2 pi = *reinterpret_cast<const longlong2*>(p.packed_info + 2 * (int64_t)r);
     const int64_t start = pi.x;
     const int64_t n = pi.y;
-    const bool accumulate = p.opac != nullptr || p.colors != nullptr || p.depths != nullptr || p.raw != nullptr;
 
     float carry = kAlpha ? 1.0f : 0.0f;
     float aO = 0.f, aD = 0.f, aC0 = 0.f, aC1 = 0.f, aC2 = 0.f;
@@ -161,7 +166,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) composite_fwd_kernel(const 
             aC2 += q.w * c2;
         }
     }
-    if (!accumulate) return;
+    if (!accumulate) continue;
     aO = warp_sum(aO);
     aD = warp_sum(aD);
     aC0 = warp_sum(aC0);
@@ -185,6 +190,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) composite_fwd_kernel(const 
             p.colors[3 * (int64_t)r + 2] = aC2 + b2;
         }
     }
+    }  // ray loop
 }
 
 // Backward.  With g_i = dL/dw_i = gC'.c_i + gO' + gD'.m_i + gW_i  (primes: after
@@ -199,12 +205,11 @@ template <bool kAlpha>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) composite_bwd_kernel(const CompositeParams p)
 {
     const int lane = threadIdx.x & 31;
-    const int r = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-    if (r >= p.n_rays) return;
+    for (int r = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); r < p.n_rays; r += gridDim.x * kWarpsPerCta) {
     const longlong2 pi = *reinterpret_cast<const longlong2*>(p.packed_info + 2 * (int64_t)r);
     const int64_t start = pi.x;
     const int64_t n = pi.y;
-    if (n == 0) return;
+    if (n == 0) continue;
 
     // upstream per-ray gradients, moved back to the raw sums
     float gc0 = 0.f, gc1 = 0.f, gc2 = 0.f, go = 0.f, gd = 0.f;
@@ -289,6 +294,555 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) composite_bwd_kernel(const 
             }
         }
     }
+    }  // ray loop
+}
+
+// ---------------------------------------------------------------------------
+// Vectorised variants (all per-sample pointers 16-byte aligned): a lane owns a
+// group of 4 consecutive samples (global index 4g .. 4g+3), so t_starts / t_ends /
+// sigmas move as one float4 and the 12 colour floats as three; the warp covers 128
+// samples per step with 6 x 512-byte coalesced loads in flight.  Groups are aligned
+// to the ARRAY, not to the ray: the first / last group of a ray may hold samples of
+// its neighbours, which are masked (and written back element-wise).
+// ---------------------------------------------------------------------------
+struct Vec4 {
+    float v[4];
+};
+
+__device__ __forceinline__ Vec4 load4(const float* base, int64_t g, bool full, int64_t n_total)
+{
+    Vec4 r;
+    if (full) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(base) + g);
+        r.v[0] = x.x; r.v[1] = x.y; r.v[2] = x.z; r.v[3] = x.w;
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) r.v[e] = (4 * g + e < n_total) ? __ldg(base + 4 * g + e) : 0.f;
+    }
+    return r;
+}
+
+__device__ __forceinline__ void store4(float* base, int64_t g, const Vec4& x, const bool ok[4], bool all)
+{
+    if (all) {
+        *(reinterpret_cast<float4*>(base) + g) = make_float4(x.v[0], x.v[1], x.v[2], x.v[3]);
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (ok[e]) base[4 * g + e] = x.v[e];
+    }
+}
+
+// forward quantities of one group
+struct GroupFwd {
+    Vec4 delta, mid, a, T, w, x;
+};
+
+template <bool kAlpha>
+__device__ __forceinline__ void group_forward(const CompositeParams& p, int64_t g, bool gvalid, bool full,
+                                              int64_t n_total, const bool ok[4], int lane, float& carry, GroupFwd& q)
+{
+    Vec4 ts, te, v;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) ts.v[e] = te.v[e] = v.v[e] = 0.f;
+    if (gvalid) {
+        v = load4(p.dens, g, full, n_total);
+        if (p.t_starts) {
+            ts = load4(p.t_starts, g, full, n_total);
+            te = load4(p.t_ends, g, full, n_total);
+        }
+    }
+    Vec4 pt;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) pt.v[e] = 1.f;
+    if (p.prefix_trans && gvalid) pt = load4(p.prefix_trans, g, full, n_total);
+    float incl[4];
+    if (!kAlpha) {
+        float run = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            q.delta.v[e] = te.v[e] - ts.v[e];
+            q.mid.v[e] = (ts.v[e] + te.v[e]) * 0.5f;
+            const float sd = ok[e] ? v.v[e] * q.delta.v[e] : 0.f;
+            q.x.v[e] = sd;
+            run += sd;
+            incl[e] = run;
+        }
+        const float tot = warp_scan_sum(run, lane);  // inclusive over lanes
+        const float lane_off = carry + (tot - run);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            q.T.v[e] = exp_neg(lane_off + (incl[e] - q.x.v[e])) * pt.v[e];
+            q.a.v[e] = 1.0f - exp_neg(q.x.v[e]);
+            q.w.v[e] = q.T.v[e] * q.a.v[e];
+        }
+        carry += __shfl_sync(kFull, tot, 31);
+    } else {
+        float run = 1.f;
+        float excl[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            q.delta.v[e] = te.v[e] - ts.v[e];
+            q.mid.v[e] = (ts.v[e] + te.v[e]) * 0.5f;
+            const float om = ok[e] ? 1.0f - v.v[e] : 1.0f;
+            q.x.v[e] = om;
+            excl[e] = run;
+            run *= om;
+        }
+        const float tot = warp_scan_prod(run, lane);
+        float lane_off = __shfl_up_sync(kFull, tot, 1);
+        if (lane == 0) lane_off = 1.0f;
+        lane_off *= carry;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            q.T.v[e] = lane_off * excl[e] * pt.v[e];
+            q.a.v[e] = v.v[e];
+            q.w.v[e] = q.T.v[e] * q.a.v[e];
+        }
+        carry *= __shfl_sync(kFull, tot, 31);
+    }
+}
+
+template <bool kAlpha>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) composite_fwd_vec_kernel(const CompositeParams p, int64_t n_total)
+{
+    const int lane = threadIdx.x & 31;
+    const bool accumulate = p.opac != nullptr || p.colors != nullptr || p.depths != nullptr || p.raw != nullptr;
+    for (int r = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); r < p.n_rays; r += gridDim.x * kWarpsPerCta) {
+    const longlong2 pi = *reinterpret_cast<const longlong2*>(p.packed_info + 2 * (int64_t)r);
+    const int64_t start = pi.x, end = pi.x + pi.y;
+    float carry = kAlpha ? 1.0f : 0.0f;
+    float aO = 0.f, aD = 0.f, aC0 = 0.f, aC1 = 0.f, aC2 = 0.f;
+    if (end > start) {
+        const int64_t g_last = (end - 1) >> 2;
+        for (int64_t gb = start >> 2; gb <= g_last; gb += 32) {
+            const int64_t g = gb + lane;
+            const bool gvalid = g <= g_last;
+            const bool full = 4 * g + 3 < n_total;
+            bool ok[4];
+            {
+                const int lo = (int)max((int64_t)-8, start - 4 * g), hi = (int)min((int64_t)8, end - 4 * g);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) ok[e] = gvalid && e >= lo && e < hi;
+            }
+            const bool all = ok[0] && ok[3] && full;
+            float c[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) c[k] = 0.f;
+            if (p.rgbs && gvalid) {
+                if (full) {
+                    const float4* src = reinterpret_cast<const float4*>(p.rgbs) + 3 * g;
+                    const float4 x0 = __ldg(src), x1 = __ldg(src + 1), x2 = __ldg(src + 2);
+                    c[0] = x0.x; c[1] = x0.y; c[2] = x0.z; c[3] = x0.w;
+                    c[4] = x1.x; c[5] = x1.y; c[6] = x1.z; c[7] = x1.w;
+                    c[8] = x2.x; c[9] = x2.y; c[10] = x2.z; c[11] = x2.w;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 12; ++k)
+                        if (4 * g + k / 3 < n_total) c[k] = __ldg(p.rgbs + 12 * g + k);
+                }
+            }
+            GroupFwd q;
+            group_forward<kAlpha>(p, g, gvalid, full, n_total, ok, lane, carry, q);
+            if (gvalid) {
+                if (p.weights) store4(p.weights, g, q.w, ok, all);
+                if (p.trans) store4(p.trans, g, q.T, ok, all);
+                if (p.alphas) store4(p.alphas, g, q.a, ok, all);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float w = ok[e] ? q.w.v[e] : 0.f;
+                    aO += w;
+                    aD += w * q.mid.v[e];
+                    aC0 += w * c[3 * e];
+                    aC1 += w * c[3 * e + 1];
+                    aC2 += w * c[3 * e + 2];
+                }
+            }
+        }
+    }
+    if (!accumulate) continue;
+    aO = warp_sum(aO);
+    aD = warp_sum(aD);
+    aC0 = warp_sum(aC0);
+    aC1 = warp_sum(aC1);
+    aC2 = warp_sum(aC2);
+    if (lane == 0) {
+        if (p.raw) {
+            float* w = p.raw + 5 * (int64_t)r;
+            w[0] = aC0; w[1] = aC1; w[2] = aC2; w[3] = aO; w[4] = aD;
+        }
+        if (p.opac) p.opac[r] = aO;
+        if (p.depths) p.depths[r] = p.expected_depths ? aD / fmaxf(aO, kEpsF32) : aD;
+        if (p.colors) {
+            float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+            if (p.bkgd) {
+                const float k = 1.0f - aO;
+                b0 = p.bkgd[0] * k; b1 = p.bkgd[1] * k; b2 = p.bkgd[2] * k;
+            }
+            p.colors[3 * (int64_t)r + 0] = aC0 + b0;
+            p.colors[3 * (int64_t)r + 1] = aC1 + b1;
+            p.colors[3 * (int64_t)r + 2] = aC2 + b2;
+        }
+    }
+    }  // ray loop
+}
+
+template <bool kAlpha>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) composite_bwd_vec_kernel(const CompositeParams p, int64_t n_total)
+{
+    const int lane = threadIdx.x & 31;
+    for (int r = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); r < p.n_rays; r += gridDim.x * kWarpsPerCta) {
+    const longlong2 pi = *reinterpret_cast<const longlong2*>(p.packed_info + 2 * (int64_t)r);
+    const int64_t start = pi.x, end = pi.x + pi.y;
+    if (end <= start) continue;
+
+    float gc0 = 0.f, gc1 = 0.f, gc2 = 0.f, go = 0.f, gd = 0.f;
+    if (p.gC) {
+        gc0 = p.gC[3 * (int64_t)r]; gc1 = p.gC[3 * (int64_t)r + 1]; gc2 = p.gC[3 * (int64_t)r + 2];
+    }
+    if (p.gO) go = p.gO[r];
+    if (p.gD) gd = p.gD[r];
+    float rC0 = 0.f, rC1 = 0.f, rC2 = 0.f, rO = 0.f, rD = 0.f;
+    if (p.raw) {
+        const float* w = p.raw + 5 * (int64_t)r;
+        rC0 = w[0]; rC1 = w[1]; rC2 = w[2]; rO = w[3]; rD = w[4];
+    }
+    if (p.bkgd) go -= gc0 * p.bkgd[0] + gc1 * p.bkgd[1] + gc2 * p.bkgd[2];
+    if (p.expected_depths && p.gD) {
+        if (rO > kEpsF32) {
+            go -= gd * rD / (rO * rO);
+            gd = gd / rO;
+        } else {
+            gd = gd / kEpsF32;
+        }
+    }
+    const bool have_rgb = p.rgbs != nullptr && p.gC != nullptr;
+    const int64_t g_first = start >> 2, g_last = (end - 1) >> 2;
+
+    // the general case (gradients on per-sample outputs) needs the ray total first
+    float total;
+    if (p.raw && !p.gW && !p.gT) {
+        total = gc0 * rC0 + gc1 * rC1 + gc2 * rC2 + go * rO + gd * rD;
+    } else {
+        float carry = kAlpha ? 1.0f : 0.0f;
+        float acc = 0.f;
+        for (int64_t gb = g_first; gb <= g_last; gb += 32) {
+            const int64_t g = gb + lane;
+            const bool gvalid = g <= g_last;
+            const bool full = 4 * g + 3 < n_total;
+            bool ok[4];
+            {
+                const int lo = (int)max((int64_t)-8, start - 4 * g), hi = (int)min((int64_t)8, end - 4 * g);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) ok[e] = gvalid && e >= lo && e < hi;
+            }
+            GroupFwd q;
+            group_forward<kAlpha>(p, g, gvalid, full, n_total, ok, lane, carry, q);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (!ok[e]) continue;
+                const int64_t i = 4 * g + e;
+                float gg = go + gd * q.mid.v[e];
+                if (have_rgb) gg += gc0 * __ldg(p.rgbs + 3 * i) + gc1 * __ldg(p.rgbs + 3 * i + 1) + gc2 * __ldg(p.rgbs + 3 * i + 2);
+                if (p.gW) gg += __ldg(p.gW + i);
+                float t = gg * q.w.v[e];
+                if (p.gT) t += __ldg(p.gT + i) * q.T.v[e];
+                acc += t;
+            }
+        }
+        total = warp_sum(acc);
+    }
+
+    float carry = kAlpha ? 1.0f : 0.0f;
+    float pcarry = 0.f;
+    for (int64_t gb = g_first; gb <= g_last; gb += 32) {
+        const int64_t g = gb + lane;
+        const bool gvalid = g <= g_last;
+        const bool full = 4 * g + 3 < n_total;
+        bool ok[4];
+        {
+            const int lo = (int)max((int64_t)-8, start - 4 * g), hi = (int)min((int64_t)8, end - 4 * g);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ok[e] = gvalid && e >= lo && e < hi;
+        }
+        const bool all = ok[0] && ok[3] && full;
+        float c[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) c[k] = 0.f;
+        if (have_rgb && gvalid) {
+            if (full) {
+                const float4* src = reinterpret_cast<const float4*>(p.rgbs) + 3 * g;
+                const float4 x0 = __ldg(src), x1 = __ldg(src + 1), x2 = __ldg(src + 2);
+                c[0] = x0.x; c[1] = x0.y; c[2] = x0.z; c[3] = x0.w;
+                c[4] = x1.x; c[5] = x1.y; c[6] = x1.z; c[7] = x1.w;
+                c[8] = x2.x; c[9] = x2.y; c[10] = x2.z; c[11] = x2.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 12; ++k)
+                    if (4 * g + k / 3 < n_total) c[k] = __ldg(p.rgbs + 12 * g + k);
+            }
+        }
+        GroupFwd q;
+        group_forward<kAlpha>(p, g, gvalid, full, n_total, ok, lane, carry, q);
+        Vec4 gw, gt, ga;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) gw.v[e] = gt.v[e] = ga.v[e] = 0.f;
+        if (gvalid) {
+            if (p.gW) gw = load4(p.gW, g, full, n_total);
+            if (p.gT) gt = load4(p.gT, g, full, n_total);
+            if (p.gA) ga = load4(p.gA, g, full, n_total);
+        }
+        float gg[4], incl[4];
+        float run = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            gg[e] = go + gd * q.mid.v[e] + gc0 * c[3 * e] + gc1 * c[3 * e + 1] + gc2 * c[3 * e + 2] + gw.v[e];
+            const float term = ok[e] ? gg[e] * q.w.v[e] + gt.v[e] * q.T.v[e] : 0.f;
+            run += term;
+            incl[e] = run;
+        }
+        const float tot = warp_scan_sum(run, lane);
+        const float lane_off = pcarry + (tot - run);
+        pcarry += __shfl_sync(kFull, tot, 31);
+        if (gvalid) {
+            Vec4 gi;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float suffix = total - (lane_off + incl[e]);
+                if (!kAlpha) gi.v[e] = q.delta.v[e] * ((gg[e] * q.T.v[e] + ga.v[e]) * (1.0f - q.a.v[e]) - suffix);
+                else gi.v[e] = gg[e] * q.T.v[e] + ga.v[e] - suffix / fmaxf(q.x.v[e], 1e-10f);
+            }
+            store4(p.g_dens, g, gi, ok, all);
+            if (p.g_rgbs) {
+                if (all) {
+                    float4* dst = reinterpret_cast<float4*>(p.g_rgbs) + 3 * g;
+                    dst[0] = make_float4(q.w.v[0] * gc0, q.w.v[0] * gc1, q.w.v[0] * gc2, q.w.v[1] * gc0);
+                    dst[1] = make_float4(q.w.v[1] * gc1, q.w.v[1] * gc2, q.w.v[2] * gc0, q.w.v[2] * gc1);
+                    dst[2] = make_float4(q.w.v[2] * gc2, q.w.v[3] * gc0, q.w.v[3] * gc1, q.w.v[3] * gc2);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (!ok[e]) continue;
+                        const int64_t i = 4 * g + e;
+                        p.g_rgbs[3 * i + 0] = q.w.v[e] * gc0;
+                        p.g_rgbs[3 * i + 1] = q.w.v[e] * gc1;
+                        p.g_rgbs[3 * i + 2] = q.w.v[e] * gc2;
+                    }
+                }
+            }
+        }
+    }
+    }  // ray loop
+}
+
+// ---------------------------------------------------------------------------
+// Hot-path instantiations: density route, colours present, no prefix_trans, every
+// output requested, fewer than 2^31 samples.  Same mapping as the vector kernels
+// above with everything optional compiled out and 32-bit indexing -- these kernels
+// are as much issue-bound as HBM-bound, so instructions per sample matter.
+// ---------------------------------------------------------------------------
+struct HotGroup {
+    float ts[4], te[4], sg[4], c[12];
+};
+
+__device__ __forceinline__ void hot_load(const CompositeParams& p, int g, bool gvalid, int n_total, HotGroup& h)
+{
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h.ts[e] = h.te[e] = h.sg[e] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) h.c[k] = 0.f;
+    if (!gvalid) return;
+    if (4 * g + 3 < n_total) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p.t_starts) + g);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.t_ends) + g);
+        const float4 d = __ldg(reinterpret_cast<const float4*>(p.dens) + g);
+        const float4* src = reinterpret_cast<const float4*>(p.rgbs) + 3 * g;
+        const float4 x0 = __ldg(src), x1 = __ldg(src + 1), x2 = __ldg(src + 2);
+        h.ts[0] = a.x; h.ts[1] = a.y; h.ts[2] = a.z; h.ts[3] = a.w;
+        h.te[0] = b.x; h.te[1] = b.y; h.te[2] = b.z; h.te[3] = b.w;
+        h.sg[0] = d.x; h.sg[1] = d.y; h.sg[2] = d.z; h.sg[3] = d.w;
+        h.c[0] = x0.x; h.c[1] = x0.y; h.c[2] = x0.z; h.c[3] = x0.w;
+        h.c[4] = x1.x; h.c[5] = x1.y; h.c[6] = x1.z; h.c[7] = x1.w;
+        h.c[8] = x2.x; h.c[9] = x2.y; h.c[10] = x2.z; h.c[11] = x2.w;
+    } else {  // only the last group of the whole array can be partial
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int i = 4 * g + e;
+            if (i < n_total) {
+                h.ts[e] = __ldg(p.t_starts + i);
+                h.te[e] = __ldg(p.t_ends + i);
+                h.sg[e] = __ldg(p.dens + i);
+                h.c[3 * e] = __ldg(p.rgbs + 3 * i);
+                h.c[3 * e + 1] = __ldg(p.rgbs + 3 * i + 1);
+                h.c[3 * e + 2] = __ldg(p.rgbs + 3 * i + 2);
+            }
+        }
+    }
+}
+
+// transmittance / alpha / weight of the 4 samples of a group; `carry` = sigma*dt summed so far on the ray
+__device__ __forceinline__ void hot_forward(const HotGroup& h, int lo, int hi, int lane, float& carry, float T[4],
+                                            float a[4], float w[4])
+{
+    float sd[4], incl[4];
+    float run = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        sd[e] = (e >= lo && e < hi) ? h.sg[e] * (h.te[e] - h.ts[e]) : 0.f;
+        run += sd[e];
+        incl[e] = run;
+    }
+    const float tot = warp_scan_sum(run, lane);
+    const float off = carry + (tot - run);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        T[e] = exp_neg(off + (incl[e] - sd[e]));
+        a[e] = 1.0f - exp_neg(sd[e]);
+        w[e] = T[e] * a[e];
+    }
+    carry += __shfl_sync(kFull, tot, 31);
+}
+
+__device__ __forceinline__ void hot_store4(float* base, int g, const float x[4], int lo, int hi, bool all)
+{
+    if (all) {
+        *(reinterpret_cast<float4*>(base) + g) = make_float4(x[0], x[1], x[2], x[3]);
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (e >= lo && e < hi) base[4 * g + e] = x[e];
+    }
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32) composite_fwd_hot_kernel(const CompositeParams p, int n_total)
+{
+    const int lane = threadIdx.x & 31;
+    for (int r = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); r < p.n_rays; r += gridDim.x * kWarpsPerCta) {
+        const longlong2 pi = *reinterpret_cast<const longlong2*>(p.packed_info + 2 * (int64_t)r);
+        const int start = (int)pi.x, end = (int)(pi.x + pi.y);
+        float carry = 0.f, aO = 0.f, aD = 0.f, aC0 = 0.f, aC1 = 0.f, aC2 = 0.f;
+        if (end > start) {
+            const int g_last = (end - 1) >> 2;
+            for (int gb = start >> 2; gb <= g_last; gb += 32) {
+                const int g = gb + lane;
+                const bool gvalid = g <= g_last;
+                const int lo = gvalid ? start - 4 * g : 4, hi = end - 4 * g;  // valid elements: lo <= e < hi
+                HotGroup h;
+                hot_load(p, g, gvalid, n_total, h);
+                float T[4], a[4], w[4];
+                hot_forward(h, lo, hi, lane, carry, T, a, w);
+                if (gvalid) {
+                    const bool all = lo <= 0 && hi >= 4 && 4 * g + 3 < n_total;
+                    hot_store4(p.weights, g, w, lo, hi, all);
+                    hot_store4(p.trans, g, T, lo, hi, all);
+                    hot_store4(p.alphas, g, a, lo, hi, all);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float we = (e >= lo && e < hi) ? w[e] : 0.f;
+                        aO += we;
+                        aD += we * ((h.ts[e] + h.te[e]) * 0.5f);
+                        aC0 += we * h.c[3 * e];
+                        aC1 += we * h.c[3 * e + 1];
+                        aC2 += we * h.c[3 * e + 2];
+                    }
+                }
+            }
+        }
+        aO = warp_sum(aO);
+        aD = warp_sum(aD);
+        aC0 = warp_sum(aC0);
+        aC1 = warp_sum(aC1);
+        aC2 = warp_sum(aC2);
+        if (lane == 0) {
+            float* raw = p.raw + 5 * (int64_t)r;
+            raw[0] = aC0; raw[1] = aC1; raw[2] = aC2; raw[3] = aO; raw[4] = aD;
+            p.opac[r] = aO;
+            p.depths[r] = p.expected_depths ? aD / fmaxf(aO, kEpsF32) : aD;
+            float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+            if (p.bkgd) {
+                const float k = 1.0f - aO;
+                b0 = p.bkgd[0] * k; b1 = p.bkgd[1] * k; b2 = p.bkgd[2] * k;
+            }
+            p.colors[3 * (int64_t)r + 0] = aC0 + b0;
+            p.colors[3 * (int64_t)r + 1] = aC1 + b1;
+            p.colors[3 * (int64_t)r + 2] = aC2 + b2;
+        }
+    }
+}
+
+// backward of the above for upstream gradients on colours / opacities / depths only
+__global__ void __launch_bounds__(kWarpsPerCta * 32) composite_bwd_hot_kernel(const CompositeParams p, int n_total)
+{
+    const int lane = threadIdx.x & 31;
+    for (int r = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); r < p.n_rays; r += gridDim.x * kWarpsPerCta) {
+        const longlong2 pi = *reinterpret_cast<const longlong2*>(p.packed_info + 2 * (int64_t)r);
+        const int start = (int)pi.x, end = (int)(pi.x + pi.y);
+        if (end <= start) continue;
+        float gc0 = 0.f, gc1 = 0.f, gc2 = 0.f, go = 0.f, gd = 0.f;
+        if (p.gC) {
+            gc0 = p.gC[3 * (int64_t)r]; gc1 = p.gC[3 * (int64_t)r + 1]; gc2 = p.gC[3 * (int64_t)r + 2];
+        }
+        if (p.gO) go = p.gO[r];
+        if (p.gD) gd = p.gD[r];
+        const float* raw = p.raw + 5 * (int64_t)r;
+        const float rO = raw[3], rD = raw[4];
+        if (p.bkgd) go -= gc0 * p.bkgd[0] + gc1 * p.bkgd[1] + gc2 * p.bkgd[2];
+        if (p.expected_depths && p.gD) {
+            if (rO > kEpsF32) {
+                go -= gd * rD / (rO * rO);
+                gd = gd / rO;
+            } else {
+                gd = gd / kEpsF32;
+            }
+        }
+        const float total = gc0 * raw[0] + gc1 * raw[1] + gc2 * raw[2] + go * rO + gd * rD;
+        float carry = 0.f, pcarry = 0.f;
+        const int g_last = (end - 1) >> 2;
+        for (int gb = start >> 2; gb <= g_last; gb += 32) {
+            const int g = gb + lane;
+            const bool gvalid = g <= g_last;
+            const int lo = gvalid ? start - 4 * g : 4, hi = end - 4 * g;
+            HotGroup h;
+            hot_load(p, g, gvalid, n_total, h);
+            float T[4], a[4], w[4];
+            hot_forward(h, lo, hi, lane, carry, T, a, w);
+            float gg[4], incl[4];
+            float run = 0.f;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                gg[e] = go + gd * ((h.ts[e] + h.te[e]) * 0.5f) + gc0 * h.c[3 * e] + gc1 * h.c[3 * e + 1] + gc2 * h.c[3 * e + 2];
+                run += (e >= lo && e < hi) ? gg[e] * w[e] : 0.f;
+                incl[e] = run;
+            }
+            const float tot = warp_scan_sum(run, lane);
+            const float off = pcarry + (tot - run);
+            pcarry += __shfl_sync(kFull, tot, 31);
+            if (gvalid) {
+                const bool all = lo <= 0 && hi >= 4 && 4 * g + 3 < n_total;
+                float gi[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    gi[e] = (h.te[e] - h.ts[e]) * (gg[e] * T[e] * (1.0f - a[e]) - (total - (off + incl[e])));
+                hot_store4(p.g_dens, g, gi, lo, hi, all);
+                if (all) {
+                    float4* dst = reinterpret_cast<float4*>(p.g_rgbs) + 3 * g;
+                    dst[0] = make_float4(w[0] * gc0, w[0] * gc1, w[0] * gc2, w[1] * gc0);
+                    dst[1] = make_float4(w[1] * gc1, w[1] * gc2, w[2] * gc0, w[2] * gc1);
+                    dst[2] = make_float4(w[2] * gc2, w[3] * gc0, w[3] * gc1, w[3] * gc2);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (e >= lo && e < hi) {
+                            const int i = 4 * g + e;
+                            p.g_rgbs[3 * i + 0] = w[e] * gc0;
+                            p.g_rgbs[3 * i + 1] = w[e] * gc1;
+                            p.g_rgbs[3 * i + 2] = w[e] * gc2;
+                        }
+                    }
+                }
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -360,6 +914,20 @@ __global__ void __launch_bounds__(256) accumulate_bwd_kernel(
 
 using namespace nfa;
 
+// persistent grid: as many CTAs as are resident at once (occupancy x SM count), never more than one warp per ray
+template <class Kernel>
+static inline int persistent_grid(Kernel k, int32_t n_rays)
+{
+    int per_sm = 0, dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kWarpsPerCta * 32, 0) != cudaSuccess || per_sm < 1)
+        per_sm = 2;
+    const int need = (n_rays + kWarpsPerCta - 1) / kWarpsPerCta;
+    const int cap = per_sm * sms;
+    return need < cap ? need : cap;
+}
+
 static inline int32_t launch_status_c()
 {
     const cudaError_t e = cudaGetLastError();
@@ -368,13 +936,14 @@ static inline int32_t launch_status_c()
 
 extern "C" {
 
-int32_t nfa_composite_fwd(int32_t n_rays, const int64_t* packed_info, const float* t_starts, const float* t_ends,
+int32_t nfa_composite_fwd(int32_t n_rays, int64_t n_samples, const int64_t* packed_info, const float* t_starts,
+                          const float* t_ends,
                           const float* sigmas_or_alphas, int32_t from_alpha, const float* rgbs,
                           const float* prefix_trans, const float* bkgd, int32_t expected_depths, float* weights,
                           float* trans, float* alphas, float* colors, float* opacities, float* depths, float* raw,
                           nfa_stream_t stream)
 {
-    if (n_rays < 0) return NFA_ERR_ARG;
+    if (n_rays < 0 || n_samples < 0) return NFA_ERR_ARG;
     if (n_rays == 0) return NFA_OK;
     if (!packed_info || !sigmas_or_alphas) return NFA_ERR_ARG;
     if (!from_alpha && (!t_starts || !t_ends)) return NFA_ERR_ARG;
@@ -397,20 +966,34 @@ int32_t nfa_composite_fwd(int32_t n_rays, const int64_t* packed_info, const floa
     p.opac = opacities;
     p.depths = depths;
     p.raw = raw;
-    const int blocks = (n_rays + kWarpsPerCta - 1) / kWarpsPerCta;
-    if (from_alpha) composite_fwd_kernel<true><<<blocks, kWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(p);
-    else composite_fwd_kernel<false><<<blocks, kWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(p);
+    const uintptr_t al = (uintptr_t)t_starts | (uintptr_t)t_ends | (uintptr_t)sigmas_or_alphas | (uintptr_t)rgbs |
+                         (uintptr_t)prefix_trans | (uintptr_t)weights | (uintptr_t)trans | (uintptr_t)alphas;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int threads = kWarpsPerCta * 32;
+    const bool aligned = (al & 15u) == 0 && n_samples > 0;
+    const bool hot = aligned && !from_alpha && rgbs && !prefix_trans && weights && trans && alphas && colors &&
+                     opacities && depths && raw && n_samples < (int64_t)0x7fffffff - 8;
+    if (hot) {
+        composite_fwd_hot_kernel<<<persistent_grid(composite_fwd_hot_kernel, n_rays), threads, 0, s>>>(p, (int)n_samples);
+    } else if (aligned) {  // 128-bit path, every option
+        if (from_alpha) composite_fwd_vec_kernel<true><<<persistent_grid(composite_fwd_vec_kernel<true>, n_rays), threads, 0, s>>>(p, n_samples);
+        else composite_fwd_vec_kernel<false><<<persistent_grid(composite_fwd_vec_kernel<false>, n_rays), threads, 0, s>>>(p, n_samples);
+    } else {
+        if (from_alpha) composite_fwd_kernel<true><<<persistent_grid(composite_fwd_kernel<true>, n_rays), threads, 0, s>>>(p);
+        else composite_fwd_kernel<false><<<persistent_grid(composite_fwd_kernel<false>, n_rays), threads, 0, s>>>(p);
+    }
     return launch_status_c();
 }
 
-int32_t nfa_composite_bwd(int32_t n_rays, const int64_t* packed_info, const float* t_starts, const float* t_ends,
+int32_t nfa_composite_bwd(int32_t n_rays, int64_t n_samples, const int64_t* packed_info, const float* t_starts,
+                          const float* t_ends,
                           const float* sigmas_or_alphas, int32_t from_alpha, const float* rgbs,
                           const float* prefix_trans, const float* bkgd, int32_t expected_depths, const float* raw,
                           const float* g_colors, const float* g_opacities, const float* g_depths,
                           const float* g_weights, const float* g_trans, const float* g_alphas, float* g_in,
                           float* g_rgbs, nfa_stream_t stream)
 {
-    if (n_rays < 0) return NFA_ERR_ARG;
+    if (n_rays < 0 || n_samples < 0) return NFA_ERR_ARG;
     if (n_rays == 0) return NFA_OK;
     if (!packed_info || !sigmas_or_alphas || !g_in) return NFA_ERR_ARG;
     if (!from_alpha && (!t_starts || !t_ends)) return NFA_ERR_ARG;
@@ -436,9 +1019,23 @@ int32_t nfa_composite_bwd(int32_t n_rays, const int64_t* packed_info, const floa
     p.gA = g_alphas;
     p.g_dens = g_in;
     p.g_rgbs = g_rgbs;
-    const int blocks = (n_rays + kWarpsPerCta - 1) / kWarpsPerCta;
-    if (from_alpha) composite_bwd_kernel<true><<<blocks, kWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(p);
-    else composite_bwd_kernel<false><<<blocks, kWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(p);
+    const uintptr_t al = (uintptr_t)t_starts | (uintptr_t)t_ends | (uintptr_t)sigmas_or_alphas | (uintptr_t)rgbs |
+                         (uintptr_t)prefix_trans | (uintptr_t)g_weights | (uintptr_t)g_trans | (uintptr_t)g_alphas |
+                         (uintptr_t)g_in | (uintptr_t)g_rgbs;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int threads = kWarpsPerCta * 32;
+    const bool aligned = (al & 15u) == 0 && n_samples > 0;
+    const bool hot = aligned && !from_alpha && rgbs && g_rgbs && raw && !prefix_trans && !g_weights && !g_trans &&
+                     !g_alphas && n_samples < (int64_t)0x7fffffff - 8;
+    if (hot) {
+        composite_bwd_hot_kernel<<<persistent_grid(composite_bwd_hot_kernel, n_rays), threads, 0, s>>>(p, (int)n_samples);
+    } else if (aligned) {  // 128-bit path, every option
+        if (from_alpha) composite_bwd_vec_kernel<true><<<persistent_grid(composite_bwd_vec_kernel<true>, n_rays), threads, 0, s>>>(p, n_samples);
+        else composite_bwd_vec_kernel<false><<<persistent_grid(composite_bwd_vec_kernel<false>, n_rays), threads, 0, s>>>(p, n_samples);
+    } else {
+        if (from_alpha) composite_bwd_kernel<true><<<persistent_grid(composite_bwd_kernel<true>, n_rays), threads, 0, s>>>(p);
+        else composite_bwd_kernel<false><<<persistent_grid(composite_bwd_kernel<false>, n_rays), threads, 0, s>>>(p);
+    }
     return launch_status_c();
 }
 

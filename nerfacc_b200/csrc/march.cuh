@@ -54,24 +54,6 @@ struct OccView {
     OccGeom g;
 };
 
-// Per-thread cursor with a one-brick register cache.
-struct OccCursor {
-    int brick;      // cached brick word index, -1 = none
-    uint64_t word;
-    NFA_HD void reset() { brick = -1; word = 0; }
-    NFA_HD bool test(const OccView& v, int level, int ix, int iy, int iz)
-    {
-        const int b = ((ix >> 2) * v.g.nb[1] + (iy >> 2)) * v.g.nb[2] + (iz >> 2) + level * v.g.wpl;
-        if (b != brick) {
-            brick = b;
-            const uint32_t c = v.coarse[b >> 5];
-            word = ((c >> (b & 31)) & 1u) ? v.words[b] : 0ull;
-        }
-        const int bit = ((ix & 3) << 4) | ((iy & 3) << 2) | (iz & 3);
-        return (word >> bit) & 1ull;
-    }
-};
-
 // ---------------------------------------------------------------------------
 // Ray / box slab test: reference utils_grid.cuh:10-55.
 // ---------------------------------------------------------------------------
@@ -164,16 +146,25 @@ struct Walk {
     int seg_i;       // next crossing index to look at
     int level;
     float seg_hi;
-    bool in_seg;
-    Dda s;
-    OccCursor cur;
-    // stretch under construction
-    bool open;       // inside a stretch (no EMPTY since it began)
-    bool has_occ;    // the current descriptor has seen an occupied cell
-    bool joined;     // the current descriptor continues the previous one (SEG inside a stretch)
-    float d_pend, d_open;
-    float pend_acc;  // skip target accumulated while no stretch is open
-    bool done;
+    // DDA of the current segment, kept in scalars (reference utils_grid.cuh:58-142)
+    float tdx, tdy, tdz;   // next crossing time per axis
+    float dlx, dly, dlz;   // crossing-time increment per axis
+    int remx, remy, remz;  // steps left on the axis before the walk ends (overflow index or grid edge)
+    int sgx, sgy, sgz;     // step direction per axis (-1, 0, +1)
+    // incremental occupancy cursor: current brick word + bit of the current cell inside it
+    int brick;
+    int bit;               // (x&3)<<4 | (y&3)<<2 | (z&3)
+    uint64_t word;
+    // state flags (ints, not bools: the compiler would byte-pack bools and shuffle them around)
+    int in_seg;
+    int open;        // inside a stretch (no EMPTY since it began)
+    int has_occ;     // the current descriptor has seen an occupied cell
+    int joined;      // the current descriptor continues the previous one (SEG inside a stretch)
+    int done;
+    // stretch under construction.  `pend` is the skip target: while no stretch is open it
+    // accumulates (max) the exits of empty cells / segment starts; once a stretch opens it is
+    // frozen and becomes that stretch's pend.
+    float pend, d_open;
 };
 
 NFA_HD void walk_init(Walk& w, const float o[3], const float d[3], float near, float far)
@@ -189,22 +180,62 @@ NFA_HD void walk_init(Walk& w, const float o[3], const float d[3], float near, f
     w.seg_i = 0;
     w.level = 0;
     w.seg_hi = 0.f;
-    w.in_seg = false;
-    w.cur.reset();
-    w.open = false;
-    w.has_occ = false;
-    w.joined = false;
-    w.d_pend = -INFINITY;
+    w.tdx = w.tdy = w.tdz = 0.f;
+    w.dlx = w.dly = w.dlz = 0.f;
+    w.remx = w.remy = w.remz = 0;
+    w.sgx = w.sgy = w.sgz = 0;
+    w.brick = 0;
+    w.bit = 0;
+    w.word = 0;
+    w.in_seg = 0;
+    w.open = 0;
+    w.has_occ = 0;
+    w.joined = 0;
+    w.done = 0;
+    w.pend = -INFINITY;
     w.d_open = 0.f;
-    w.pend_acc = -INFINITY;
-    w.done = false;
+}
+
+NFA_HD void walk_load_brick(Walk& w, const OccView& occ)
+{
+    const uint32_t c = occ.coarse[w.brick >> 5];
+    w.word = ((c >> (w.brick & 31)) & 1u) ? occ.words[w.brick] : 0ull;
+}
+
+// Steps left on one axis: until the index reaches the overflow index (reference
+// utils_grid.cuh:121-139, `current == overflow` ends the walk) or leaves the grid
+// (where the reference itself would read out of bounds).
+NFA_HD int walk_steps_left(int first, int last, int st, int res)
+{
+    const int big = 0x7fffffff;
+    if (st == 0) return first == last ? 1 : big;
+    const int to_ov = (last - first) * st + 1;
+    const int to_edge = st > 0 ? res - first : first + 1;
+    return (to_ov >= 1 && to_ov < to_edge) ? to_ov : to_edge;
+}
+
+NFA_HD void walk_open_segment(Walk& w, const OccView& occ, int level, float lo, float hi, const float* box)
+{
+    Dda s;
+    dda_begin(s, w.o, w.d, w.inv, lo, hi, box, occ.g.res);
+    w.level = level;
+    w.seg_hi = hi;
+    w.tdx = s.td[0]; w.tdy = s.td[1]; w.tdz = s.td[2];
+    w.dlx = s.dl[0]; w.dly = s.dl[1]; w.dlz = s.dl[2];
+    w.sgx = s.st[0]; w.sgy = s.st[1]; w.sgz = s.st[2];
+    w.remx = walk_steps_left(s.cur[0], s.ov[0] - s.st[0], s.st[0], occ.g.res[0]);
+    w.remy = walk_steps_left(s.cur[1], s.ov[1] - s.st[1], s.st[1], occ.g.res[1]);
+    w.remz = walk_steps_left(s.cur[2], s.ov[2] - s.st[2], s.st[2], occ.g.res[2]);
+    w.brick = ((s.cur[0] >> 2) * occ.g.nb[1] + (s.cur[1] >> 2)) * occ.g.nb[2] + (s.cur[2] >> 2) + level * occ.g.wpl;
+    w.bit = ((s.cur[0] & 3) << 4) | ((s.cur[1] & 3) << 2) | (s.cur[2] & 3);
+    walk_load_brick(w, occ);
+    w.in_seg = 1;
 }
 
 // Crossing source for a single grid level: what ray_aabb_intersect + torch.sort
 // produce for n_grids == 1 (reference grid.py:156-162), computed in place.
 struct SingleBox {
     const float* box;
-    NFA_HD int n_grids() const { return 1; }
     NFA_HD const float* aabb(int) const { return box; }
     // next valid segment at or after index i (i is advanced past it); false when exhausted
     NFA_HD bool next(const Walk& w, int& i, int& level, float& lo, float& hi) const
@@ -227,7 +258,6 @@ struct SortedBoxes {
     const float* t_sorted;     // this ray's [2G]
     const int64_t* t_indices;  // this ray's [2G]
     const uint8_t* hits;       // this ray's [G]
-    NFA_HD int n_grids() const { return G; }
     NFA_HD const float* aabb(int level) const { return aabbs + 6 * level; }
     NFA_HD bool next(const Walk& w, int& i, int& level, float& lo, float& hi) const
     {
@@ -252,80 +282,99 @@ struct SortedBoxes {
     }
 };
 
-// One step of the walk: either opens the next segment or processes one cell.
-// Descriptors are appended through `buf.put(j, pend, open, joined)`; the caller
-// stops calling when its buffer is full and resumes after flushing it.
+// Walk until the ray is finished or `cap` descriptors are buffered.  Descriptors are
+// appended through `buf.put(j, pend, open, joined)`; the caller flushes the buffer
+// (phase 2) and calls again to resume.  A descriptor without occupied cells (open =
+// -inf) still carries its conditional skip.
 template <class Boxes, class Buf>
-NFA_HD void walk_step(Walk& w, const Boxes& boxes, const OccView& occ, Buf& buf, int& n_desc)
+NFA_HD void walk_run(Walk& w, const Boxes& boxes, const OccView& occ, Buf& buf, int& n_desc, int cap)
 {
-    if (!w.in_seg) {
-        int level;
-        float lo, hi;
-        if (!boxes.next(w, w.seg_i, level, lo, hi)) {
-            // a descriptor without occupied cells (open = -inf) still carries its conditional skip
-            if (w.open) buf.put(n_desc++, w.d_pend, w.has_occ ? w.d_open : -INFINITY, w.joined);
-            w.open = false;
-            w.done = true;
-            return;
+    while (!w.done && n_desc < cap) {
+        if (!w.in_seg) {
+            int level;
+            float lo, hi;
+            if (!boxes.next(w, w.seg_i, level, lo, hi)) {
+                if (w.open) buf.put(n_desc++, w.pend, w.has_occ ? w.d_open : -INFINITY, w.joined != 0);
+                w.done = 1;
+                return;
+            }
+            // SEG(lo)
+            if (w.open) {
+                buf.put(n_desc++, w.pend, w.has_occ ? w.d_open : -INFINITY, w.joined != 0);
+                w.pend = lo;
+                w.joined = 1;
+                w.has_occ = 0;
+            } else {
+                w.pend = f_max(w.pend, lo);
+            }
+            walk_open_segment(w, occ, level, lo, hi, boxes.aabb(level));
+            continue;
         }
-        // SEG(lo)
-        if (w.open) {
-            buf.put(n_desc++, w.d_pend, w.has_occ ? w.d_open : -INFINITY, w.joined);
-            w.d_pend = lo;
-            w.joined = true;
-            w.has_occ = false;
-        } else {
-            w.pend_acc = f_max(w.pend_acc, lo);
-        }
-        w.level = level;
-        w.seg_hi = hi;
-        dda_begin(w.s, w.o, w.d, w.inv, lo, hi, boxes.aabb(level), occ.g.res);
-        w.in_seg = true;
-        return;
+        // Cells of the current segment: the hot loop, on local scalars.  The body uses
+        // selects instead of branches -- the lanes of a warp follow unrelated rays, so every
+        // branch that depends on the ray (axis choice, occupied / empty) would be serialised.
+        float tdx = w.tdx, tdy = w.tdy, tdz = w.tdz;
+        int remx = w.remx, remy = w.remy, remz = w.remz;
+        int bit = w.bit, brick = w.brick;
+        uint64_t word = w.word;
+        int open = w.open, has_occ = w.has_occ, joined = w.joined;
+        float pend = w.pend, d_open = w.d_open;
+        const float dlx = w.dlx, dly = w.dly, dlz = w.dlz, seg_hi = w.seg_hi;
+        const int sgx = w.sgx, sgy = w.sgy, sgz = w.sgz;
+        const int bx = occ.g.nb[1] * occ.g.nb[2], by = occ.g.nb[2];
+        int in_seg = 1;
+        do {
+            const float tt = f_min(f_min(tdx, f_min(tdy, tdz)), seg_hi);  // grid.cu:185-186
+            const int occd = (int)((word >> bit) & 1ull);
+            if (!occd && open) {  // EMPTY(tt) closes the stretch (rare)
+                buf.put(n_desc++, pend, has_occ ? d_open : -INFINITY, joined != 0);
+                pend = -INFINITY;
+            }
+            // OCC(tt): a stretch opens (pend frozen) or grows; EMPTY(tt): skip target moves on
+            joined = (occd && !open) ? 0 : joined;
+            pend = occd ? pend : f_max(pend, tt);
+            d_open = occd ? tt : d_open;
+            open = occd;
+            has_occ = occd;
+            // utils_grid.cuh:116-142: x only if strictly smallest, else y if strictly below z, else z
+            const bool mx = tdx < tdy && tdx < tdz;
+            const bool my = !mx && (tdy < tdz);
+            const bool mz = !mx && !my;
+            const float nx = f_add(tdx, dlx), ny = f_add(tdy, dly), nz = f_add(tdz, dlz);
+            tdx = mx ? nx : tdx;
+            tdy = my ? ny : tdy;
+            tdz = mz ? nz : tdz;
+            remx -= mx ? 1 : 0;
+            remy -= my ? 1 : 0;
+            remz -= mz ? 1 : 0;
+            if ((mx ? remx : (my ? remy : remz)) == 0) {
+                in_seg = 0;
+            } else {
+                // move the occupancy cursor along the stepped axis
+                const int sh = mx ? 4 : (my ? 2 : 0);
+                const int sg = mx ? sgx : (my ? sgy : sgz);
+                const int t = ((bit >> sh) & 3) + sg;
+                bit = (bit & ~(3 << sh)) | ((t & 3) << sh);
+                if ((unsigned)t > 3u) {  // crossed into the neighbouring brick
+                    brick += sg * (mx ? bx : (my ? by : 1));
+                    const uint32_t c = occ.coarse[brick >> 5];
+                    word = ((c >> (brick & 31)) & 1u) ? occ.words[brick] : 0ull;
+                }
+            }
+        } while (in_seg && n_desc < cap);
+        w.tdx = tdx; w.tdy = tdy; w.tdz = tdz;
+        w.remx = remx; w.remy = remy; w.remz = remz;
+        w.bit = bit; w.brick = brick; w.word = word;
+        w.open = open; w.has_occ = has_occ; w.joined = joined;
+        w.pend = pend; w.d_open = d_open;
+        w.in_seg = in_seg;
     }
-    Dda& s = w.s;
-    // cells outside the grid can only be reached where the reference itself reads out of bounds
-    if ((unsigned)s.cur[0] >= (unsigned)occ.g.res[0] || (unsigned)s.cur[1] >= (unsigned)occ.g.res[1] ||
-        (unsigned)s.cur[2] >= (unsigned)occ.g.res[2]) {
-        w.in_seg = false;
-        return;
-    }
-    const float tt = f_min(f_min(s.td[0], f_min(s.td[1], s.td[2])), w.seg_hi);  // grid.cu:185-186
-    if (w.cur.test(occ, w.level, s.cur[0], s.cur[1], s.cur[2])) {
-        // OCC(tt)
-        if (!w.open) {
-            w.open = true;
-            w.joined = false;
-            w.d_pend = w.pend_acc;
-            w.pend_acc = -INFINITY;
-        }
-        w.d_open = tt;
-        w.has_occ = true;
-    } else {
-        // EMPTY(tt)
-        if (w.open) {
-            buf.put(n_desc++, w.d_pend, w.has_occ ? w.d_open : -INFINITY, w.joined);
-            w.open = false;
-            w.has_occ = false;
-        }
-        w.pend_acc = f_max(w.pend_acc, tt);
-    }
-    // utils_grid.cuh:116-142: x only if strictly smallest, else y if strictly below z, else z
-    int a;
-    if (s.td[0] < s.td[1] && s.td[0] < s.td[2]) a = 0;
-    else if (s.td[1] < s.td[2]) a = 1;
-    else a = 2;
-    bool leave;
-    if (a == 0) { s.cur[0] += s.st[0]; s.td[0] = f_add(s.td[0], s.dl[0]); leave = s.cur[0] == s.ov[0]; }
-    else if (a == 1) { s.cur[1] += s.st[1]; s.td[1] = f_add(s.td[1], s.dl[1]); leave = s.cur[1] == s.ov[1]; }
-    else { s.cur[2] += s.st[2]; s.td[2] = f_add(s.td[2], s.dl[2]); leave = s.cur[2] == s.ov[2]; }
-    if (leave) w.in_seg = false;
 }
 
 // Skip target still pending at the end of the ray (for the terminate plane, grid.cu:274-275).
 NFA_HD float walk_tail_pend(const Walk& w)
 {
-    return w.open ? -INFINITY : w.pend_acc;
+    return w.open ? -INFINITY : w.pend;
 }
 
 // ---------------------------------------------------------------------------

@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(kTileRays) march_kernel(const MarchParams p)
     LatState m;
     walk_init(w, o, d, near, far);
     lat_init(m, L, near);
-    w.done = !active;
+    w.done = active ? 0 : 1;
     SmemBuf buf;
     buf.pend = s_pend;
     buf.open = s_open;
@@ -298,11 +298,8 @@ __global__ void __launch_bounds__(kTileRays) march_kernel(const MarchParams p)
                              kSingle ? nullptr : p.t_indices + rr * 2 * G, kSingle ? nullptr : p.hits + rr * G};
     for (;;) {
         // phase 1: DDA only (divergent, cheap)
-        if (kSingle) {
-            while (!w.done && n_desc < kDescSlots) walk_step(w, single, occ, buf, n_desc);
-        } else {
-            while (!w.done && n_desc < kDescSlots) walk_step(w, sorted, occ, buf, n_desc);
-        }
+        if (kSingle) walk_run(w, single, occ, buf, n_desc, kDescSlots);
+        else walk_run(w, sorted, occ, buf, n_desc, kDescSlots);
         // phase 2: lattice seeks, all lanes in step
         const int maxd = __reduce_max_sync(0xffffffffu, n_desc);
         for (int j = 0; j < maxd; ++j) {
@@ -314,7 +311,7 @@ __global__ void __launch_bounds__(kTileRays) march_kernel(const MarchParams p)
         }
         n_desc = 0;
         buf.joined_mask = 0u;
-        if (__all_sync(0xffffffffu, w.done)) break;
+        if (__all_sync(0xffffffffu, w.done != 0)) break;
     }
     {
         RunOut out;

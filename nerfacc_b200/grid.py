@@ -116,6 +116,7 @@ class _MarchScratch:
         self.workspace = None
         self.totals_dev = torch.zeros(4, dtype=torch.int64, device=device)
         self.totals_host = torch.zeros(4, dtype=torch.int64).pin_memory()
+        self.event = torch.cuda.Event()
         self.reserve(2 * n_rays + 1024)
 
     def reserve(self, run_capacity: int) -> None:
@@ -177,9 +178,12 @@ def _march(rays_o: Tensor, rays_d: Tensor, binaries: Tensor, aabbs: Tensor, near
                   _lib.ptr(aabbs), _lib.ptr(t_sorted), _lib.ptr(t_indices), _lib.ptr(hits), step_size,
                   sc.run_capacity, _lib.ptr(sc.workspace), _lib.ptr(sc.totals_dev), _lib.ptr(term))
         sc.totals_host.copy_(sc.totals_dev, non_blocking=True)
+        sc.event.record(stream)
 
     def read_totals():
-        stream.synchronize()
+        # wait for the totals only: kernels queued behind the copy (the speculative expand)
+        # keep running while the host prepares the next launches
+        sc.event.synchronize()
         n, runs, _, stuck = (int(v) for v in sc.totals_host.tolist())
         if stuck:
             raise RuntimeError(

@@ -64,7 +64,7 @@ class _Composite(torch.autograd.Function):
             raw = torch.empty((n_rays, 5), dtype=torch.float32, device=device)
         else:
             colors = opac = depths = raw = None
-        _lib.call("nfa_composite_fwd", device, n_rays, _lib.ptr(packed_info), _lib.ptr(t_starts), _lib.ptr(t_ends),
+        _lib.call("nfa_composite_fwd", device, n_rays, n, _lib.ptr(packed_info), _lib.ptr(t_starts), _lib.ptr(t_ends),
                   _lib.ptr(dens), int(from_alpha), _lib.ptr(rgbs), _lib.ptr(prefix_trans), _lib.ptr(bkgd),
                   int(expected_depths), _lib.ptr(weights), _lib.ptr(trans),
                   None if from_alpha else _lib.ptr(alphas), _lib.ptr(colors), _lib.ptr(opac), _lib.ptr(depths),
@@ -87,7 +87,7 @@ class _Composite(torch.autograd.Function):
         g_rgbs = torch.empty_like(rgbs) if need_rgbs else None
         if ctx.from_alpha:
             g_a = None  # `alphas` output is the detached input
-        _lib.call("nfa_composite_bwd", device, packed_info.shape[0], _lib.ptr(packed_info), _lib.ptr(t_starts),
+        _lib.call("nfa_composite_bwd", device, packed_info.shape[0], dens.shape[0], _lib.ptr(packed_info), _lib.ptr(t_starts),
                   _lib.ptr(t_ends), _lib.ptr(dens), int(ctx.from_alpha), _lib.ptr(rgbs), _lib.ptr(prefix_trans),
                   _lib.ptr(bkgd), int(ctx.expected_depths), _lib.ptr(raw),
                   _lib.ptr(_f32c(g_c)), _lib.ptr(_f32c(g_o)), _lib.ptr(_f32c(g_d)),

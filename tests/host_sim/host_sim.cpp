@@ -94,7 +94,7 @@ static float march_one(const Boxes& boxes, const OccView& occ, const float* o, c
     RunOut out;
     // same chunked structure as the kernel: walk until the buffer is full, then flush it
     for (long guard = 0; guard < (1L << 26); ++guard) {
-        while (!w.done && n_desc < HostBuf::K) walk_step(w, boxes, occ, buf, n_desc);
+        walk_run(w, boxes, occ, buf, n_desc, HostBuf::K);
         for (int j = 0; j < n_desc; ++j) {
             lat_consume(m, buf.pend[j], buf.open[j], buf.joined[j], out);
             if (out.valid) { vt.push_back(out.t_first); vn.push_back(out.n); }

@@ -50,7 +50,7 @@ def test_argument_errors_do_not_need_a_gpu():
     lib = _lib.load()
     assert lib.nfa_scan_packed(-1, None, None, None, 0, 0, 0, 0, None) == -1
     assert lib.nfa_scan_packed(4, None, None, None, 0, 0, 0, 0, None) == -1
-    assert lib.nfa_composite_fwd(3, None, None, None, None, 0, None, None, None, 1, *([None] * 8)) == -1
+    assert lib.nfa_composite_fwd(3, 10, None, None, None, None, 0, None, None, None, 1, *([None] * 8)) == -1
     assert lib.nfa_intersect_sorted(1, None, None, 64, None, None, None, None, None) == -2  # > 32 boxes: unsupported
     assert lib.nfa_march_workspace_bytes(-5, 10) == 0
 

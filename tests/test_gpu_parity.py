@@ -261,6 +261,71 @@ def test_fused_rendering_vs_oracle(orc, expected_depths, bkgd):
     np.testing.assert_allclose(N(col2), 2 * N(col1), atol=1e-5)
 
 
+def test_vector_and_scalar_kernels_agree(orc):
+    """16-byte aligned inputs take the 128-bit kernels, anything else the scalar ones; both must match the oracle.
+    Also ragged rays: empty rays, 1-sample rays, rays that start / end mid-group."""
+    g = torch.Generator().manual_seed(9)
+    cnts = torch.tensor([0, 1, 3, 4, 5, 0, 127, 128, 129, 2, 0, 0, 33, 64, 1, 7, 250, 0, 31], dtype=torch.int64)
+    starts = torch.cumsum(cnts, 0) - cnts
+    pi = torch.stack([starts, cnts], -1).to(dev)
+    n, R = int(cnts.sum()), len(cnts)
+    for off in (0, 1):  # off=1: views with a 4-byte offset -> scalar kernels
+        def place(t):  # copy into a view whose storage offset is `off` elements (4 bytes): not 16-byte aligned
+            buf = torch.empty((t.shape[0] + off,) + tuple(t.shape[1:]), device=dev)
+            v = buf[off:]
+            v.copy_(t)
+            return v
+        ts = place(torch.rand(n, generator=g).to(dev) * 0.5)
+        te = place(ts + 0.01 + torch.rand(n, generator=g).to(dev) * 0.02)
+        sig = place(8 * torch.rand(n, generator=g).to(dev)).requires_grad_(True)
+        rgb = place(torch.rand(n, 3, generator=g).to(dev)).requires_grad_(True)
+        assert (ts.data_ptr() % 16 != 0) == bool(off)
+        sig_l, rgb_l = sig.detach().clone().requires_grad_(True), rgb.detach().clone().requires_grad_(True)
+        ri = torch.repeat_interleave(torch.arange(R), cnts).to(dev)
+        for use_alpha in (False, True):
+            sig_l.grad = rgb_l.grad = None
+            dens = sig_l if not use_alpha else (sig_l / 10.0)
+            d_in = dens if off == 0 else torch.cat([dens.new_zeros(1), dens])[1:]
+            c_in = rgb_l if off == 0 else torch.cat([rgb_l.new_zeros(1, 3), rgb_l])[1:]
+            fn = (lambda a, b, c: (c_in, d_in))
+            kw = dict(rgb_alpha_fn=fn) if use_alpha else dict(rgb_sigma_fn=fn)
+            col, op, dep, ex = nfa.rendering(ts, te, ri, n_rays=R, **kw)
+            gC, gO, gD = (torch.rand(sh, generator=g).to(dev) for sh in [(R, 3), (R, 1), (R, 1)])
+            gW = torch.rand(n, generator=g).to(dev)
+            ((col * gC).sum() + (op * gO).sum() + (dep * gD).sum() + (ex["weights"] * gW).sum()).backward()
+            if not use_alpha:
+                o = orc.composite(N(ts), N(te), N(dens), N(rgb_l), packed_info=N(pi))
+                gs, gr = orc.composite_backward(N(ts), N(te), N(dens), N(rgb_l), N(pi), gC=N(gC), gO=N(gO).ravel(),
+                                                gD=N(gD).ravel(), gW=N(gW))
+                for got, key in [(ex["weights"], "weights"), (ex["trans"], "trans"), (col, "colors"), (op, "opacities"),
+                                 (dep, "depths")]:
+                    np.testing.assert_allclose(N(got), o[key], atol=1e-5, rtol=0, err_msg=f"{key} off={off}")
+                np.testing.assert_allclose(N(sig_l.grad), gs, atol=2e-5, rtol=1e-4)
+                np.testing.assert_allclose(N(rgb_l.grad), gr, atol=1e-5, rtol=1e-4)
+            else:
+                ow, oT = orc.render_weight_from_alpha(N(dens), packed_info=N(pi))
+                np.testing.assert_allclose(N(ex["weights"]), ow, atol=1e-5, rtol=0)
+                np.testing.assert_allclose(N(ex["trans"]), oT, atol=1e-5, rtol=0)
+                # gradient vs torch autograd on the batched formulation, ray by ray
+                ref = torch.zeros_like(dens)
+                d64 = dens.detach().double().requires_grad_(True)
+                tot = 0
+                for r in range(R):
+                    s0, c0 = int(starts[r]), int(cnts[r])
+                    if c0 == 0:
+                        continue
+                    a = d64[s0:s0 + c0]
+                    T = torch.cumprod(torch.cat([a.new_ones(1), 1 - a[:-1]]), 0)
+                    w = T * a
+                    m = ((ts + te) / 2)[s0:s0 + c0].double()
+                    O = w.sum()
+                    tot = tot + (w[:, None] * rgb_l.detach()[s0:s0 + c0].double() * gC[r].double()).sum() + O * gO[r, 0].double() \
+                        + (w * m).sum() / O.clamp_min(1.1920929e-07) * gD[r, 0].double() + (w * gW[s0:s0 + c0].double()).sum()
+                tot.backward()
+                got = sig_l.grad * 10.0  # d/d(alpha) = 10 * d/d(sig_l)
+                np.testing.assert_allclose(N(got), N(d64.grad), atol=5e-5, rtol=1e-3)
+
+
 def test_general_gradients_prefix_trans_and_alpha_route(orc):
     R = 512
     ri, ts, te, pi = _ball_samples(R)
