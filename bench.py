@@ -25,7 +25,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -51,35 +50,47 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.
+
+    One background `nvidia-smi -lms` process writing to a file: the benchmark step is partly
+    host-bound, so the sampler must not run Python (or spawn processes) while the clock is on.
+    """
+
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+        self.index, self.proc, self.path = index, None, f"/tmp/nfa_clocks_{os.getpid()}.csv"
 
     def start(self):
-        def run():
-            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-            while not self._stop.is_set():
-                try:
-                    out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                         capture_output=True, text=True, timeout=5).stdout.strip()
-                    if out:
-                        self.rows.append([c.strip() for c in out.split(",")])
-                except Exception:
-                    pass
-                self._stop.wait(0.1)
-        self._t = threading.Thread(target=run, daemon=True)
-        self._t.start()
+        try:
+            self.out = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.out, stderr=subprocess.DEVNULL)
+            time.sleep(0.35)  # let it take its first samples before the clock starts
+        except Exception:
+            self.proc = None
 
     def stop(self):
-        self._stop.set()
-        if self._t:
-            self._t.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        rows = []
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            self.out.close()
+            try:
+                rows = [[c.strip() for c in l.split(",")] for l in open(self.path) if l.strip()]
+                os.remove(self.path)
+            except Exception:
+                pass
+        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in rows)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
 

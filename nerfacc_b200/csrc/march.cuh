@@ -51,6 +51,8 @@ NFA_HD OccGeom occ_geom(int n_grids, int rx, int ry, int rz)
 struct OccView {
     const uint64_t* words;   // [n_grids * wpl]
     const uint32_t* coarse;  // [(n_grids * wpl + 31) / 32]; may live in shared memory
+    const int32_t* bounds;   // [n_grids][6] bounding box of the non-empty bricks (brick units,
+                             // min xyz then max xyz, inclusive; min > max: level empty), or null
     OccGeom g;
 };
 
@@ -161,6 +163,9 @@ struct Walk {
     int has_occ;     // the current descriptor has seen an occupied cell
     int joined;      // the current descriptor continues the previous one (SEG inside a stretch)
     int done;
+    // empty-space acceleration (single level, no terminate plane wanted): see walk_open_segment
+    int accel;
+    float t_stop;
     // stretch under construction.  `pend` is the skip target: while no stretch is open it
     // accumulates (max) the exits of empty cells / segment starts; once a stretch opens it is
     // frozen and becomes that stretch's pend.
@@ -192,6 +197,8 @@ NFA_HD void walk_init(Walk& w, const float o[3], const float d[3], float near, f
     w.has_occ = 0;
     w.joined = 0;
     w.done = 0;
+    w.accel = 0;
+    w.t_stop = INFINITY;
     w.pend = -INFINITY;
     w.d_open = 0.f;
 }
@@ -220,12 +227,73 @@ NFA_HD void walk_open_segment(Walk& w, const OccView& occ, int level, float lo, 
     dda_begin(s, w.o, w.d, w.inv, lo, hi, box, occ.g.res);
     w.level = level;
     w.seg_hi = hi;
+    w.t_stop = INFINITY;
+    int remx = walk_steps_left(s.cur[0], s.ov[0] - s.st[0], s.st[0], occ.g.res[0]);
+    int remy = walk_steps_left(s.cur[1], s.ov[1] - s.st[1], s.st[1], occ.g.res[1]);
+    int remz = walk_steps_left(s.cur[2], s.ov[2] - s.st[2], s.st[2], occ.g.res[2]);
+
+    // Empty-space acceleration.  Everything outside the bounding box of the non-empty bricks is
+    // empty, and walking empty cells only moves the skip target forward.  So (a) jump the DDA to
+    // where the ray enters that box -- the crossing times are chains td (+) dl (+) dl ..., i.e.
+    // lattices, and "how many crossings lie before T" / "what is the chain value there" are the
+    // closed-form seeks of lattice.cuh, so the state after the jump is bit-identical to having
+    // stepped -- and (b) stop once the ray has left the box.  Used when nothing after the last
+    // occupied cell is observable: one level, no terminate plane.  The box is grown by one cell,
+    // far more than the rounding of this (inexact) slab test, and the first cell after the jump
+    // is still outside the true box, so it re-establishes the skip target exactly.
+    if (w.accel && occ.bounds != nullptr && !w.open) {
+        const int32_t* bb = occ.bounds + 6 * level;
+        bool dead = bb[0] > bb[3];
+        float t_in = lo, t_out = hi;
+        if (!dead) {
+            float glo[3], ghi[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float voxel = (box[3 + a] - box[a]) / (float)occ.g.res[a];
+                glo[a] = box[a] + (float)(4 * bb[a] - 1) * voxel;
+                ghi[a] = box[a] + (float)(4 * bb[3 + a] + 5) * voxel;
+            }
+            const float gbox[6] = {glo[0], glo[1], glo[2], ghi[0], ghi[1], ghi[2]};
+            float a0, a1;
+            if (slab_test(w.o, w.inv, gbox, lo, hi, a0, a1)) {
+                t_in = a0;
+                t_out = a1;
+            } else {
+                dead = true;
+            }
+        }
+        if (!dead && t_in > lo) {
+            float t[3] = {s.td[0], s.td[1], s.td[2]};
+            uint32_t n[3] = {0u, 0u, 0u};
+            bool ok = true;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                Lattice La = lat_make(s.dl[a]);
+                La.half = 0.0f;  // plain "first chain value >= target"
+                ok = ok && lat_seek(La, t[a], t_in, n[a]);
+            }
+            if (ok) {
+                if (n[0] >= (uint32_t)remx || n[1] >= (uint32_t)remy || n[2] >= (uint32_t)remz) {
+                    dead = true;  // the walk ends before it reaches the occupied region
+                } else {
+                    s.td[0] = t[0]; s.td[1] = t[1]; s.td[2] = t[2];
+                    remx -= (int)n[0]; remy -= (int)n[1]; remz -= (int)n[2];
+                    s.cur[0] += s.st[0] * (int)n[0];
+                    s.cur[1] += s.st[1] * (int)n[1];
+                    s.cur[2] += s.st[2] * (int)n[2];
+                }
+            }
+        }
+        if (dead) {  // nothing occupied on this segment
+            w.in_seg = 0;
+            return;
+        }
+        w.t_stop = t_out;
+    }
     w.tdx = s.td[0]; w.tdy = s.td[1]; w.tdz = s.td[2];
     w.dlx = s.dl[0]; w.dly = s.dl[1]; w.dlz = s.dl[2];
     w.sgx = s.st[0]; w.sgy = s.st[1]; w.sgz = s.st[2];
-    w.remx = walk_steps_left(s.cur[0], s.ov[0] - s.st[0], s.st[0], occ.g.res[0]);
-    w.remy = walk_steps_left(s.cur[1], s.ov[1] - s.st[1], s.st[1], occ.g.res[1]);
-    w.remz = walk_steps_left(s.cur[2], s.ov[2] - s.st[2], s.st[2], occ.g.res[2]);
+    w.remx = remx; w.remy = remy; w.remz = remz;
     w.brick = ((s.cur[0] >> 2) * occ.g.nb[1] + (s.cur[1] >> 2)) * occ.g.nb[2] + (s.cur[2] >> 2) + level * occ.g.wpl;
     w.bit = ((s.cur[0] & 3) << 4) | ((s.cur[1] & 3) << 2) | (s.cur[2] & 3);
     walk_load_brick(w, occ);
@@ -319,7 +387,7 @@ NFA_HD void walk_run(Walk& w, const Boxes& boxes, const OccView& occ, Buf& buf, 
         uint64_t word = w.word;
         int open = w.open, has_occ = w.has_occ, joined = w.joined;
         float pend = w.pend, d_open = w.d_open;
-        const float dlx = w.dlx, dly = w.dly, dlz = w.dlz, seg_hi = w.seg_hi;
+        const float dlx = w.dlx, dly = w.dly, dlz = w.dlz, seg_hi = w.seg_hi, t_stop = w.t_stop;
         const int sgx = w.sgx, sgy = w.sgy, sgz = w.sgz;
         const int bx = occ.g.nb[1] * occ.g.nb[2], by = occ.g.nb[2];
         int in_seg = 1;
@@ -347,8 +415,8 @@ NFA_HD void walk_run(Walk& w, const Boxes& boxes, const OccView& occ, Buf& buf, 
             remx -= mx ? 1 : 0;
             remy -= my ? 1 : 0;
             remz -= mz ? 1 : 0;
-            if ((mx ? remx : (my ? remy : remz)) == 0) {
-                in_seg = 0;
+            if ((mx ? remx : (my ? remy : remz)) == 0 || tt >= t_stop) {
+                in_seg = 0;  // overflow index / grid edge reached, or (accelerated) past the occupied box
             } else {
                 // move the occupancy cursor along the stepped axis
                 const int sh = mx ? 4 : (my ? 2 : 0);

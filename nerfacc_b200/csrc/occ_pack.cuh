@@ -31,6 +31,11 @@ NFA_HD uint64_t occ_brick_word(const uint8_t* level_cells, const OccGeom& g, int
     return w;
 }
 
+// bounds layout: [n_grids][6] int32 = min brick xyz, max brick xyz (inclusive); initialised to
+// (0x7f7f7f7f, 0x80808080) so that an empty level reads min > max.
+constexpr int32_t kBoundsMinInit = 0x7f7f7f7f;
+constexpr int32_t kBoundsMaxInit = (int32_t)0x80808080;
+
 NFA_HD int64_t occ_coarse_words(const OccGeom& g)
 {
     // padded to a multiple of 4 words (16 bytes) so it can be moved with one bulk copy

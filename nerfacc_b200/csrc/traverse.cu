@@ -138,7 +138,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) occ_pack_kernel(OccGeom g, const uint8_t* __restrict__ binaries,
                                                        uint64_t* __restrict__ words, uint32_t* __restrict__ coarse,
-                                                       int64_t n_words, int64_t n_coarse)
+                                                       int32_t* __restrict__ bounds, int64_t n_words, int64_t n_coarse)
 {
     const int64_t cells = (int64_t)g.res[0] * g.res[1] * g.res[2];
     // one thread per brick; a warp's 32 bricks share one coarse word
@@ -154,10 +154,21 @@ __global__ void __launch_bounds__(256) occ_pack_kernel(OccGeom g, const uint8_t*
             const int bx = rem / g.nb[1];
             w = occ_brick_word(binaries + level * cells, g, bx, by, bz);
             words[b] = w;
+            if (w != 0) {  // bounding box of the non-empty bricks (few atomics: occupied bricks only)
+                int32_t* bb = bounds + 6 * level;
+                atomicMin(bb + 0, bx); atomicMin(bb + 1, by); atomicMin(bb + 2, bz);
+                atomicMax(bb + 3, bx); atomicMax(bb + 4, by); atomicMax(bb + 5, bz);
+            }
         }
         const uint32_t any = __ballot_sync(0xffffffffu, w != 0);
         if ((threadIdx.x & 31) == 0) coarse[b >> 5] = any;
     }
+}
+
+__global__ void occ_bounds_init_kernel(int32_t* bounds, int n_grids)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 6 * n_grids) bounds[i] = (i % 6) < 3 ? kBoundsMinInit : kBoundsMaxInit;
 }
 
 // ---------------------------------------------------------------------------
@@ -167,12 +178,14 @@ struct MarchParams {
     int32_t n_rays;
     const float* rays_o;
     const float* rays_d;
-    const float* near_planes;
+    const float* near_planes;  // per ray, or null: near_plane for every ray
     const float* far_planes;
+    float near_plane, far_plane;
     OccGeom g;
     const uint64_t* words;
     const uint32_t* coarse;
     int32_t coarse_words;  // padded count (multiple of 4)
+    const int32_t* bounds;  // occupied-brick bounding boxes (nullable)
     const float* aabbs;
     const float* t_sorted;
     const int64_t* t_indices;
@@ -180,6 +193,7 @@ struct MarchParams {
     float step_size;
     Workspace ws;
     int64_t* totals;
+    int64_t* totals_host;  // optional host-visible mirror (pinned memory), saves a D2H copy node
     float* terminate;
 };
 
@@ -266,8 +280,8 @@ __global__ void __launch_bounds__(kTileRays) march_kernel(const MarchParams p)
     const bool active = tid < nr;
     float near = 0.f, far = 0.f;
     if (active) {
-        near = p.near_planes[r];
-        far = p.far_planes[r];
+        near = p.near_planes ? p.near_planes[r] : p.near_plane;
+        far = p.far_planes ? p.far_planes[r] : p.far_plane;
     }
     mbar_wait(&s_bar, 0);
     __syncthreads();
@@ -276,6 +290,7 @@ __global__ void __launch_bounds__(kTileRays) march_kernel(const MarchParams p)
     OccView occ;
     occ.words = p.words;
     occ.coarse = kSmemCoarse ? s_coarse : p.coarse;
+    occ.bounds = p.bounds;
     occ.g = p.g;
     const Lattice L = lat_make(p.step_size);
     const float o[3] = {active ? s_o[tid * 3 + 0] : 0.f, active ? s_o[tid * 3 + 1] : 0.f, active ? s_o[tid * 3 + 2] : 0.f};
@@ -285,6 +300,8 @@ __global__ void __launch_bounds__(kTileRays) march_kernel(const MarchParams p)
     walk_init(w, o, d, near, far);
     lat_init(m, L, near);
     w.done = active ? 0 : 1;
+    // nothing after the last occupied cell is observable without a terminate plane on one level
+    w.accel = (kSingle && p.terminate == nullptr) ? 1 : 0;
     SmemBuf buf;
     buf.pend = s_pend;
     buf.open = s_open;
@@ -385,8 +402,13 @@ __global__ void __launch_bounds__(kTileRays) march_kernel(const MarchParams p)
             for (int k = 0; k < kTileRays / 32; ++k) v += s_tot[tid][k];
             // totals: [0] samples, [1] runs, [2] run-pool capacity used for this call, [3] stuck rays
             p.totals[tid == 2 ? 3 : tid] = (int64_t)v;
+            if (p.totals_host) p.totals_host[tid == 2 ? 3 : tid] = (int64_t)v;
         }
-        if (tid == 3) p.totals[2] = p.ws.run_capacity;
+        if (tid == 3) {
+            p.totals[2] = p.ws.run_capacity;
+            if (p.totals_host) p.totals_host[2] = p.ws.run_capacity;
+        }
+        __threadfence_system();
         if (tid == 0) {  // leave the workspace reusable
             *p.ws.done = 0u;
             *p.ws.cursor = 0u;
@@ -692,16 +714,17 @@ int64_t nfa_occ_coarse_words(int32_t n_grids, int32_t rx, int32_t ry, int32_t rz
 }
 
 int32_t nfa_occ_pack(int32_t n_grids, int32_t rx, int32_t ry, int32_t rz, const uint8_t* binaries, uint64_t* words,
-                     uint32_t* coarse, nfa_stream_t stream)
+                     uint32_t* coarse, int32_t* bounds, nfa_stream_t stream)
 {
-    if (n_grids <= 0 || rx <= 0 || ry <= 0 || rz <= 0 || !binaries || !words || !coarse) return NFA_ERR_ARG;
+    if (n_grids <= 0 || rx <= 0 || ry <= 0 || rz <= 0 || !binaries || !words || !coarse || !bounds) return NFA_ERR_ARG;
     const OccGeom g = occ_geom(n_grids, rx, ry, rz);
     const int64_t n_words = (int64_t)n_grids * g.wpl;
     if (n_words > (int64_t)INT32_MAX) return NFA_ERR_UNSUPPORTED;
     const int64_t n_coarse = occ_coarse_words(g);
     const int64_t threads = n_coarse * 32;
     const int blocks = (int)((threads + 255) / 256 < 148 * 16 ? (threads + 255) / 256 : 148 * 16);
-    occ_pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(g, binaries, words, coarse, n_words, n_coarse);
+    occ_bounds_init_kernel<<<(6 * n_grids + 127) / 128, 128, 0, (cudaStream_t)stream>>>(bounds, n_grids);
+    occ_pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(g, binaries, words, coarse, bounds, n_words, n_coarse);
     return launch_status();
 }
 
@@ -711,18 +734,24 @@ int64_t nfa_march_workspace_bytes(int32_t n_rays, int64_t run_capacity)
 }
 
 int32_t nfa_march(int32_t n_rays, const float* rays_o, const float* rays_d, const float* near_planes,
-                  const float* far_planes, int32_t n_grids, int32_t rx, int32_t ry, int32_t rz,
-                  const uint64_t* words, const uint32_t* coarse, const float* aabbs, const float* t_sorted,
-                  const int64_t* t_indices, const uint8_t* hits, float step_size, int64_t run_capacity,
-                  void* workspace, int64_t* totals, float* terminate_planes, nfa_stream_t stream)
+                  const float* far_planes, float near_plane, float far_plane, int32_t n_grids, int32_t rx,
+                  int32_t ry, int32_t rz,
+                  const uint64_t* words, const uint32_t* coarse, const int32_t* bounds, const float* aabbs,
+                  const float* t_sorted, const int64_t* t_indices, const uint8_t* hits, float step_size,
+                  int64_t run_capacity, void* workspace, int64_t* totals, int64_t* totals_host,
+                  float* terminate_planes, nfa_stream_t stream)
 {
     if (n_rays < 0 || n_grids <= 0 || rx <= 0 || ry <= 0 || rz <= 0 || run_capacity < 0) return NFA_ERR_ARG;
     if (run_capacity > (int64_t)UINT32_MAX) return NFA_ERR_UNSUPPORTED;
     if (!(step_size > 0.0f)) return NFA_ERR_UNSUPPORTED;
     if (!totals) return NFA_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream;
-    if (n_rays == 0) return (int32_t)cudaMemsetAsync(totals, 0, 4 * sizeof(int64_t), s);
-    if (!rays_o || !rays_d || !near_planes || !far_planes || !words || !coarse || !aabbs || !workspace)
+    if ((near_planes == nullptr) != (far_planes == nullptr)) return NFA_ERR_ARG;
+    if (n_rays == 0) {
+        if (totals_host) totals_host[0] = totals_host[1] = totals_host[2] = totals_host[3] = 0;
+        return (int32_t)cudaMemsetAsync(totals, 0, 4 * sizeof(int64_t), s);
+    }
+    if (!rays_o || !rays_d || !words || !coarse || !aabbs || !workspace)
         return NFA_ERR_ARG;
     const bool have_sorted = t_sorted && t_indices && hits;
     if (!have_sorted && n_grids != 1) return NFA_ERR_ARG;
@@ -732,10 +761,13 @@ int32_t nfa_march(int32_t n_rays, const float* rays_o, const float* rays_d, cons
     p.rays_d = rays_d;
     p.near_planes = near_planes;
     p.far_planes = far_planes;
+    p.near_plane = near_plane;
+    p.far_plane = far_plane;
     p.g = occ_geom(n_grids, rx, ry, rz);
     p.words = words;
     p.coarse = coarse;
     p.coarse_words = (int32_t)occ_coarse_words(p.g);
+    p.bounds = bounds;
     p.aabbs = aabbs;
     p.t_sorted = have_sorted ? t_sorted : nullptr;
     p.t_indices = have_sorted ? t_indices : nullptr;
@@ -743,6 +775,7 @@ int32_t nfa_march(int32_t n_rays, const float* rays_o, const float* rays_d, cons
     p.step_size = step_size;
     p.ws = ws_view(workspace, n_rays, run_capacity);
     p.totals = totals;
+    p.totals_host = totals_host;
     p.terminate = terminate_planes;
     const int tiles = p.ws.n_tiles;
     const size_t coarse_bytes = (size_t)p.coarse_words * 4;

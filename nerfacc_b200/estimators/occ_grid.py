@@ -96,21 +96,27 @@ class OccGridEstimator(AbstractEstimator):
         (transmittance < early_stop_eps) or transparent (alpha < alpha_thre) are dropped.
         Not differentiable.  Semantics: reference occ_grid.py:85-221.
         """
-        near_planes = torch.full_like(rays_o[..., 0], fill_value=near_plane)
-        far_planes = torch.full_like(rays_o[..., 0], fill_value=far_plane)
-        if t_min is not None:
-            near_planes = torch.clamp(near_planes, min=t_min)
-        if t_max is not None:
-            far_planes = torch.clamp(far_planes, max=t_max)
-        if stratified:
-            near_planes += torch.rand_like(near_planes) * render_step_size
-
         n_rays = rays_o.shape[0]
-        if cone_angle == 0.0 and render_step_size > 0.0 and rays_o.is_cuda:
+        fast = cone_angle == 0.0 and render_step_size > 0.0 and rays_o.is_cuda
+        per_ray_planes = t_min is not None or t_max is not None or stratified or not fast
+        if per_ray_planes:
+            near_planes = torch.full_like(rays_o[..., 0], fill_value=near_plane)
+            far_planes = torch.full_like(rays_o[..., 0], fill_value=far_plane)
+            if t_min is not None:
+                near_planes = torch.clamp(near_planes, min=t_min)
+            if t_max is not None:
+                far_planes = torch.clamp(far_planes, max=t_max)
+            if stratified:
+                near_planes += torch.rand_like(near_planes) * render_step_size
+            near_planes, far_planes = near_planes.contiguous().float(), far_planes.contiguous().float()
+        else:
+            near_planes = far_planes = None  # the kernel takes the two scalars directly
+
+        if fast:
             res = _march(rays_o.contiguous().float(), rays_d.contiguous().float(), self.binaries,
-                         self.aabbs.contiguous().float(), near_planes.contiguous().float(),
-                         far_planes.contiguous().float(), float(render_step_size), None, None, None,
-                         want_intervals=False, want_terminate=False, capacity_hint=self._capacity_hint)
+                         self.aabbs.contiguous().float(), near_planes, far_planes, float(render_step_size), None, None,
+                         None, want_intervals=False, want_terminate=False, capacity_hint=self._capacity_hint,
+                         near_plane=float(near_plane), far_plane=float(far_plane))
             ray_indices, t_starts, t_ends, packed_info = res.ray_indices, res.t_starts, res.t_ends, res.packed_info
             # ~6% head-room over the last batch; re-measured every call
             self._capacity_hint = res.n_samples + (res.n_samples >> 4) + 1024

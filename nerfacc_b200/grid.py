@@ -77,7 +77,7 @@ def _ray_aabb_intersect(
 class _OccPack:
     """Brick-packed copy of a bool grid; derived, never persisted."""
 
-    __slots__ = ("words", "coarse", "shape")
+    __slots__ = ("words", "coarse", "bounds", "shape")
 
     def __init__(self, binaries: Tensor):
         lib = _lib.load()
@@ -89,7 +89,9 @@ class _OccPack:
         self.shape = (g, rx, ry, rz)
         self.words = torch.empty(lib.nfa_occ_words(g, rx, ry, rz), dtype=torch.int64, device=device)
         self.coarse = torch.empty(lib.nfa_occ_coarse_words(g, rx, ry, rz), dtype=torch.int32, device=device)
-        _lib.call("nfa_occ_pack", device, g, rx, ry, rz, _lib.ptr(b), _lib.ptr(self.words), _lib.ptr(self.coarse))
+        self.bounds = torch.empty(6 * g, dtype=torch.int32, device=device)
+        _lib.call("nfa_occ_pack", device, g, rx, ry, rz, _lib.ptr(b), _lib.ptr(self.words), _lib.ptr(self.coarse),
+                  _lib.ptr(self.bounds))
 
 
 def _packed_grid(binaries: Tensor) -> _OccPack:
@@ -146,11 +148,13 @@ class _MarchResult:
                  "intervals", "samples", "terminate_planes")
 
 
-def _march(rays_o: Tensor, rays_d: Tensor, binaries: Tensor, aabbs: Tensor, near_planes: Tensor,
-           far_planes: Tensor, step_size: float, t_sorted: Optional[Tensor], t_indices: Optional[Tensor],
+def _march(rays_o: Tensor, rays_d: Tensor, binaries: Tensor, aabbs: Tensor, near_planes: Optional[Tensor],
+           far_planes: Optional[Tensor], step_size: float, t_sorted: Optional[Tensor], t_indices: Optional[Tensor],
            hits: Optional[Tensor], want_intervals: bool, want_terminate: bool,
-           capacity_hint: int = 0) -> _MarchResult:
+           capacity_hint: int = 0, near_plane: float = 0.0, far_plane: float = float("inf")) -> _MarchResult:
     """Constant-step traversal: march -> expand, with ONE host synchronisation.
+
+    `near_planes` / `far_planes` may both be None: every ray then uses the scalars.
 
     With a `capacity_hint` (size of the previous batch plus head-room) the expand
     kernels are queued behind the march before the host waits for the totals; only if
@@ -174,10 +178,10 @@ def _march(rays_o: Tensor, rays_d: Tensor, binaries: Tensor, aabbs: Tensor, near
 
     def march():
         _lib.call("nfa_march", device, n_rays, _lib.ptr(rays_o), _lib.ptr(rays_d), _lib.ptr(near_planes),
-                  _lib.ptr(far_planes), n_grids, rx, ry, rz, _lib.ptr(occ.words), _lib.ptr(occ.coarse),
-                  _lib.ptr(aabbs), _lib.ptr(t_sorted), _lib.ptr(t_indices), _lib.ptr(hits), step_size,
-                  sc.run_capacity, _lib.ptr(sc.workspace), _lib.ptr(sc.totals_dev), _lib.ptr(term))
-        sc.totals_host.copy_(sc.totals_dev, non_blocking=True)
+                  _lib.ptr(far_planes), float(near_plane), float(far_plane), n_grids, rx, ry, rz, _lib.ptr(occ.words),
+                  _lib.ptr(occ.coarse), _lib.ptr(occ.bounds), _lib.ptr(aabbs), _lib.ptr(t_sorted), _lib.ptr(t_indices),
+                  _lib.ptr(hits), step_size, sc.run_capacity, _lib.ptr(sc.workspace), _lib.ptr(sc.totals_dev),
+                  _lib.ptr(sc.totals_host), _lib.ptr(term))
         sc.event.record(stream)
 
     def read_totals():

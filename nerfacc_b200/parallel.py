@@ -29,9 +29,10 @@ def all_reduce_loss(loss: torch.Tensor, average: bool = True) -> torch.Tensor:
 
     4-byte payload: the cost is launch latency, so it is issued on the compute stream.
     """
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return loss.detach()
     out = loss.detach().clone()
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(out, op=dist.ReduceOp.SUM)
-        if average:
-            out /= dist.get_world_size()
+    dist.all_reduce(out, op=dist.ReduceOp.SUM)
+    if average:
+        out /= dist.get_world_size()
     return out

@@ -56,10 +56,13 @@ void sim_expand_run(float t_first, float dt, uint32_t n, float* starts, float* e
 int64_t sim_occ_words(int n_grids, int rx, int ry, int rz) { return (int64_t)n_grids * occ_geom(n_grids, rx, ry, rz).wpl; }
 int64_t sim_occ_coarse_words(int n_grids, int rx, int ry, int rz) { return occ_coarse_words(occ_geom(n_grids, rx, ry, rz)); }
 
-void sim_occ_pack(int n_grids, int rx, int ry, int rz, const uint8_t* binaries, uint64_t* words, uint32_t* coarse)
+void sim_occ_pack(int n_grids, int rx, int ry, int rz, const uint8_t* binaries, uint64_t* words, uint32_t* coarse,
+                  int32_t* bounds)
 {
     OccGeom g = occ_geom(n_grids, rx, ry, rz);
     memset(coarse, 0, sizeof(uint32_t) * occ_coarse_words(g));
+    for (int l = 0; l < n_grids; ++l)
+        for (int a = 0; a < 3; ++a) { bounds[6 * l + a] = kBoundsMinInit; bounds[6 * l + 3 + a] = kBoundsMaxInit; }
     const int64_t cells = (int64_t)rx * ry * rz;
     for (int l = 0; l < n_grids; ++l)
         for (int bx = 0; bx < g.nb[0]; ++bx)
@@ -68,7 +71,14 @@ void sim_occ_pack(int n_grids, int rx, int ry, int rz, const uint8_t* binaries, 
                     const int b = (bx * g.nb[1] + by) * g.nb[2] + bz + l * g.wpl;
                     const uint64_t w = occ_brick_word(binaries + l * cells, g, bx, by, bz);
                     words[b] = w;
-                    if (w) coarse[b >> 5] |= 1u << (b & 31);
+                    if (w) {
+                        coarse[b >> 5] |= 1u << (b & 31);
+                        const int bc[3] = {bx, by, bz};
+                        for (int a = 0; a < 3; ++a) {
+                            if (bc[a] < bounds[6 * l + a]) bounds[6 * l + a] = bc[a];
+                            if (bc[a] > bounds[6 * l + 3 + a]) bounds[6 * l + 3 + a] = bc[a];
+                        }
+                    }
                 }
 }
 
@@ -84,10 +94,11 @@ struct HostBuf {
 
 template <class Boxes>
 static float march_one(const Boxes& boxes, const OccView& occ, const float* o, const float* d, float near, float far,
-                       const Lattice& L, LatState& m, std::vector<float>& vt, std::vector<uint32_t>& vn)
+                       const Lattice& L, LatState& m, std::vector<float>& vt, std::vector<uint32_t>& vn, int accel)
 {
     Walk w;
     walk_init(w, o, d, near, far);
+    w.accel = accel;
     lat_init(m, L, near);
     HostBuf buf;
     int n_desc = 0;
@@ -102,7 +113,7 @@ static float march_one(const Boxes& boxes, const OccView& occ, const float* o, c
         n_desc = 0;
         if (w.done) break;
     }
-    const float term = lat_finish(m, walk_tail_pend(w), true, out);
+    const float term = lat_finish(m, walk_tail_pend(w), accel == 0, out);
     if (out.valid) { vt.push_back(out.t_first); vn.push_back(out.n); }
     return term;
 }
@@ -114,7 +125,7 @@ extern "C" {
 int64_t sim_march(int32_t n_rays, const float* rays_o, const float* rays_d,
                   const float* near_planes, const float* far_planes,
                   int n_grids, int rx, int ry, int rz, const uint64_t* words, const uint32_t* coarse,
-                  const float* aabbs,
+                  const int32_t* bounds, int accel, const float* aabbs,
                   const float* t_sorted, const int64_t* t_indices, const uint8_t* hits,  // NULL => single level inline
                   float step_size,
                   int64_t* n_samples, int64_t* n_runs, float* terminate, int32_t* ok_flags,
@@ -123,6 +134,7 @@ int64_t sim_march(int32_t n_rays, const float* rays_o, const float* rays_d,
     OccView occ;
     occ.words = words;
     occ.coarse = coarse;
+    occ.bounds = bounds;
     occ.g = occ_geom(n_grids, rx, ry, rz);
     const Lattice L = lat_make(step_size);
     int64_t total = 0;
@@ -135,11 +147,12 @@ int64_t sim_march(int32_t n_rays, const float* rays_o, const float* rays_d,
         float term;
         if (t_sorted == nullptr) {
             SingleBox b{aabbs};
-            term = march_one(b, occ, rays_o + 3 * r, rays_d + 3 * r, near_planes[r], far_planes[r], L, m, vt, vn);
+            term = march_one(b, occ, rays_o + 3 * r, rays_d + 3 * r, near_planes[r], far_planes[r], L, m, vt, vn,
+                             accel);
         } else {
             SortedBoxes b{aabbs, n_grids, t_sorted + (int64_t)r * 2 * n_grids, t_indices + (int64_t)r * 2 * n_grids,
                           hits + (int64_t)r * n_grids};
-            term = march_one(b, occ, rays_o + 3 * r, rays_d + 3 * r, near_planes[r], far_planes[r], L, m, vt, vn);
+            term = march_one(b, occ, rays_o + 3 * r, rays_d + 3 * r, near_planes[r], far_planes[r], L, m, vt, vn, 0);
         }
         n_samples[r] = m.n_samples;
         n_runs[r] = m.n_runs;

@@ -70,20 +70,21 @@ def test_stuck_lattice_is_reported(host_sim):
     assert host_sim.sim_seek(1.0e6, 1e-3, 2.0e6, C.byref(t), C.byref(k)) == 0
 
 
-def _sim_sampling(sim, ro, rd, bins, aabbs, near, far, step, multi=None):
+def _sim_sampling(sim, ro, rd, bins, aabbs, near, far, step, multi=None, accel=0):
     G, rx, ry, rz = bins.shape
     R = ro.shape[0]
     words = np.zeros(sim.sim_occ_words(G, rx, ry, rz), np.uint64)
     coarse = np.zeros(sim.sim_occ_coarse_words(G, rx, ry, rz), np.uint32)
     b8 = np.ascontiguousarray(bins.astype(np.uint8))
-    sim.sim_occ_pack(G, rx, ry, rz, _p(b8, U8), _p(words, U64), _p(coarse, U32))
+    bounds = np.zeros(6 * G, np.int32)
+    sim.sim_occ_pack(G, rx, ry, rz, _p(b8, U8), _p(words, U64), _p(coarse, U32), _p(bounds, I32))
     ns, nr = np.zeros(R, np.int64), np.zeros(R, np.int64)
     term, ok = np.zeros(R, np.float32), np.zeros(R, np.int32)
     cap = 2_000_000
     rt, rn = np.zeros(cap, np.float32), np.zeros(cap, np.uint32)
     ts_, ti_, hits_ = (None, None, None) if multi is None else multi
     tot = sim.sim_march(R, _p(ro, F), _p(rd, F), _p(near, F), _p(far, F), G, rx, ry, rz, _p(words, U64), _p(coarse, U32),
-                        _p(aabbs, F), _p(ts_, F), _p(ti_, I64), _p(hits_, U8), C.c_float(step), _p(ns, I64), _p(nr, I64),
+                        _p(bounds, I32), C.c_int(accel), _p(aabbs, F), _p(ts_, F), _p(ti_, I64), _p(hits_, U8), C.c_float(step), _p(ns, I64), _p(nr, I64),
                         _p(term, F), _p(ok, I32), _p(rt, F), _p(rn, U32), C.c_int64(cap))
     assert tot >= 0
     N = int(ns.sum())
@@ -100,22 +101,23 @@ def _sim_sampling(sim, ro, rd, bins, aabbs, near, far, step, multi=None):
     return ri, s, e, ns, nr, term, ok
 
 
-def _compare(sim, orc, ro, rd, bins, aabbs, near, far, step, multi=False):
+def _compare(sim, orc, ro, rd, bins, aabbs, near, far, step, multi=False, accel=0):
     iv, sm, term_o = orc.traverse_grids(ro, rd, bins, aabbs, near_planes=near, far_planes=far, step_size=step)
     m = None
     if multi:
         tm, tM, h = orc.ray_aabb_intersect(ro, rd, aabbs)
         tsrt, tidx = orc.sort_intersections(tm, tM)
         m = (tsrt, tidx, np.ascontiguousarray(h.astype(np.uint8)))
-    ri, s, e, ns, nr, term, ok = _sim_sampling(sim, ro, rd, bins, aabbs, near, far, step, m)
+    ri, s, e, ns, nr, term, ok = _sim_sampling(sim, ro, rd, bins, aabbs, near, far, step, m, accel)
     assert ok.all()
     np.testing.assert_array_equal(ns, sm["packed_info"][:, 1])
     np.testing.assert_array_equal(nr, iv["packed_info"][:, 1] - sm["packed_info"][:, 1])  # runs = edges - samples
     np.testing.assert_array_equal(ri, sm["ray_indices"])
     np.testing.assert_array_equal(s, iv["vals"][iv["is_left"]])
     np.testing.assert_array_equal(e, iv["vals"][iv["is_right"]])
-    d = ~np.isnan(term_o)
-    np.testing.assert_array_equal(term[d], term_o[d])
+    if not accel:  # the accelerated walk stops early: terminate planes are not produced
+        d = ~np.isnan(term_o)
+        np.testing.assert_array_equal(term[d], term_o[d])
     return len(ri)
 
 
@@ -131,6 +133,15 @@ def test_march_ball_scene(host_sim, orc):
     _compare(host_sim, orc, ro[:256], rd[:256], bins, aabbs, near[:256], far[:256], 1e-3)
     frag = bins & (rng.random(bins.shape) > 0.5)
     _compare(host_sim, orc, ro[:512], rd[:512], frag, aabbs, near[:512], far[:512], scenes.BALL_STEP)
+    # empty-space acceleration (jump to / stop at the bounding box of the occupied bricks)
+    _compare(host_sim, orc, ro, rd, bins, aabbs, near, far, scenes.BALL_STEP, accel=1)
+    _compare(host_sim, orc, ro[:512], rd[:512], frag, aabbs, near[:512], far[:512], scenes.BALL_STEP, accel=1)
+    off_centre = np.zeros((1, 128, 128, 128), bool)
+    off_centre[0, 90:120, 5:9, 60:61] = True
+    off_centre[0, 97, 100, 3] = True
+    _compare(host_sim, orc, ro, rd, off_centre, aabbs, near, far, 3e-3, accel=1)
+    _compare(host_sim, orc, ro, rd, off_centre, aabbs, (rng.random(R) * 4).astype(np.float32),
+             (3 + rng.random(R) * 3).astype(np.float32), 3e-3, accel=1)
 
 
 def test_march_nested_random_grids(host_sim, orc):
@@ -147,6 +158,8 @@ def test_march_nested_random_grids(host_sim, orc):
              1e-2, multi=True)
     # single level: crossings computed inline vs supplied sorted arrays
     _compare(host_sim, orc, ro, rd, bins4[:1], a4[:1], zero, inf, 3e-3)
+    _compare(host_sim, orc, ro, rd, bins4[:1], a4[:1], zero, inf, 3e-3, accel=1)
+    _compare(host_sim, orc, ro, rd, odd_single := (rng.random((1, 30, 17, 5)) > 0.7), a4[:1], zero, inf, 4e-3, accel=1)
     _compare(host_sim, orc, ro, rd, bins4[:1], a4[:1], zero, inf, 3e-3, multi=True)
     # resolution not a multiple of the brick size, non-cubic
     odd = rng.random((2, 30, 17, 5)) > 0.3
@@ -169,6 +182,8 @@ def test_march_degenerate_rays(host_sim, orc):
     # empty grid and empty ray batch
     e = np.zeros((1, 8, 8, 8), bool)
     assert _compare(host_sim, orc, ro, rd, e, a4[:1], np.zeros(R, np.float32), np.full(R, np.inf, np.float32), 1e-2) == 0
+    assert _compare(host_sim, orc, ro, rd, e, a4[:1], np.zeros(R, np.float32), np.full(R, np.inf, np.float32), 1e-2, accel=1) == 0
+    _compare(host_sim, orc, ro, rd, bins4[:1], a4[:1], np.zeros(R, np.float32), np.full(R, np.inf, np.float32), 1e-2, accel=1)
 
 
 def test_march_matches_reference_cuda_goldens(host_sim):
@@ -178,7 +193,7 @@ def test_march_matches_reference_cuda_goldens(host_sim):
         R = z["rays_o"].shape[0]
         step = float(z["kw_vals"][0])
         ri, s, e, ns, nr, term, ok = _sim_sampling(host_sim, z["rays_o"], z["rays_d"], golden_bins(z), z["aabbs"],
-                                                   np.zeros(R, np.float32), np.full(R, 1e10, np.float32), step)
+                                                   np.zeros(R, np.float32), np.full(R, 1e10, np.float32), step, accel=1)
         np.testing.assert_array_equal(ns, z["packed_info"][:, 1])
         np.testing.assert_array_equal(s, z["t_starts"])
         np.testing.assert_array_equal(e, z["t_ends"])
