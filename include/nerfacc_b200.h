@@ -28,7 +28,7 @@ extern "C" {
 #define NFA_ERR_ARG (-1)         /* null pointer / negative size / inconsistent sizes */
 #define NFA_ERR_UNSUPPORTED (-2) /* valid request outside what this build implements */
 
-#define NFA_ABI_VERSION 4
+#define NFA_ABI_VERSION 5
 
 typedef void* nfa_stream_t; /* cudaStream_t */
 
@@ -121,6 +121,25 @@ int32_t nfa_expand_intervals(int32_t n_rays, int64_t run_capacity, const void* w
                              uint8_t* iv_is_left, uint8_t* iv_is_right,
                              int64_t* sm_packed_info, float* sm_vals, int64_t* sm_ray_indices,
                              uint8_t* sm_is_valid, nfa_stream_t stream);
+
+/* nfa_traverse_generic: the remaining modes of traverse_grids (nerfacc.cpp:75-96, grid.cu:320-474) --
+ *   cone_angle > 0, step_size <= 0 (one sample per occupied cell), traverse_steps_limit, over_allocate
+ *   and rays_mask -- marched sample by sample, one thread per ray, in the reference's order.
+ *   fill == 0: count pass, writes iv_cnts / sm_cnts [n_rays] (edges / samples per ray).
+ *   fill != 0: writes the arrays at iv_starts / sm_starts (exclusive scans of the counts, or the
+ *   fixed strides of over_allocate), skipping rays whose count is 0, then stores the actual counts.
+ *   Flag / value arrays must be zero-filled by the caller, as data_spec.hpp:62-84 does.
+ *   rays_mask (bool bytes) may be NULL; the crossings t_sorted / t_indices / hits are required. */
+int32_t nfa_traverse_generic(int32_t n_rays, const float* rays_o, const float* rays_d, const uint8_t* rays_mask,
+                             const float* near_planes, const float* far_planes,
+                             int32_t n_grids, int32_t rx, int32_t ry, int32_t rz,
+                             const uint64_t* words, const uint32_t* coarse, const float* aabbs,
+                             const float* t_sorted, const int64_t* t_indices, const uint8_t* hits,
+                             float step_size, float cone_angle, int32_t traverse_steps_limit, int32_t fill,
+                             const int64_t* iv_starts, int64_t* iv_cnts, float* iv_vals, int64_t* iv_ray_indices,
+                             uint8_t* iv_is_left, uint8_t* iv_is_right,
+                             const int64_t* sm_starts, int64_t* sm_cnts, float* sm_vals, int64_t* sm_ray_indices,
+                             uint8_t* sm_is_valid, float* terminate_planes, nfa_stream_t stream);
 
 /* ----------------------------------------------------------------------- */
 /* Volume rendering over the packed layout                                  */

@@ -25,6 +25,7 @@
 #include "../../include/nerfacc_b200.h"
 #include "expand.cuh"
 #include "march.cuh"
+#include "march_generic.cuh"
 #include "occ_pack.cuh"
 
 namespace nfa {
@@ -584,6 +585,74 @@ __global__ void __launch_bounds__(kExpandThreads) expand_runs_kernel(const Expan
 }
 
 // ---------------------------------------------------------------------------
+// generic traversal (march_generic.cuh): cone angle, per-cell sampling, step limit, masks
+// ---------------------------------------------------------------------------
+struct GenericParams {
+    int32_t n_rays;
+    const float* rays_o;
+    const float* rays_d;
+    const uint8_t* rays_mask;  // nullable
+    const float* near_planes;
+    const float* far_planes;
+    OccGeom g;
+    const uint64_t* words;
+    const uint32_t* coarse;
+    const float* aabbs;
+    const float* t_sorted;
+    const int64_t* t_indices;
+    const uint8_t* hits;
+    float step_size, cone_angle;
+    int32_t limit;
+    int32_t fill;
+    const int64_t* iv_starts;
+    int64_t* iv_cnts;
+    float* iv_vals;
+    int64_t* iv_ray;
+    uint8_t* iv_left;
+    uint8_t* iv_right;
+    const int64_t* sm_starts;
+    int64_t* sm_cnts;
+    float* sm_vals;
+    int64_t* sm_ray;
+    uint8_t* sm_valid;
+    float* terminate;
+};
+
+__global__ void __launch_bounds__(128) generic_traverse_kernel(const GenericParams p)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= p.n_rays) return;
+    if (p.rays_mask && !p.rays_mask[r]) return;                       // reference grid.cu:100
+    if (p.fill && (p.iv_cnts[r] == 0 || p.sm_cnts[r] == 0)) return;  // grid.cu:103-106
+    OccView occ;
+    occ.words = p.words;
+    occ.coarse = p.coarse;
+    occ.bounds = nullptr;
+    occ.g = p.g;
+    GenericOut out;
+    out.fill = p.fill != 0;
+    out.ray = r;
+    out.want_iv = true;
+    out.want_sm = true;
+    out.iv_base = p.fill ? p.iv_starts[r] : 0;
+    out.sm_base = p.fill ? p.sm_starts[r] : 0;
+    out.iv_vals = p.iv_vals; out.iv_ray = p.iv_ray; out.iv_left = p.iv_left; out.iv_right = p.iv_right;
+    out.sm_vals = p.sm_vals; out.sm_ray = p.sm_ray; out.sm_valid = p.sm_valid;
+    out.n_edges = 0;
+    out.n_samples = 0;
+    const int G = p.g.n_grids;
+    const SortedBoxes boxes{p.aabbs, G, p.t_sorted + (int64_t)r * 2 * G, p.t_indices + (int64_t)r * 2 * G,
+                            p.hits + (int64_t)r * G};
+    const float o[3] = {p.rays_o[3 * (int64_t)r], p.rays_o[3 * (int64_t)r + 1], p.rays_o[3 * (int64_t)r + 2]};
+    const float d[3] = {p.rays_d[3 * (int64_t)r], p.rays_d[3 * (int64_t)r + 1], p.rays_d[3 * (int64_t)r + 2]};
+    const float term = generic_march_ray(boxes, occ, o, d, p.near_planes[r], p.far_planes[r], p.step_size, p.cone_angle,
+                                         p.limit, out);
+    if (p.terminate) p.terminate[r] = term;
+    p.iv_cnts[r] = out.n_edges;
+    p.sm_cnts[r] = out.n_samples;
+}
+
+// ---------------------------------------------------------------------------
 // ray / box kernels (reference grid.cu:284-313; grid.py:156-162)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) ray_aabb_kernel(int32_t n_rays, const float* __restrict__ rays_o,
@@ -864,6 +933,48 @@ int32_t nfa_expand_intervals(int32_t n_rays, int64_t run_capacity, const void* w
         p.sm_is_valid = sm_is_valid;
         expand_runs_kernel<true><<<expand_grid(run_capacity), kExpandThreads, 0, s>>>(p);
     }
+    return launch_status();
+}
+
+int32_t nfa_traverse_generic(int32_t n_rays, const float* rays_o, const float* rays_d, const uint8_t* rays_mask,
+                             const float* near_planes, const float* far_planes, int32_t n_grids, int32_t rx, int32_t ry,
+                             int32_t rz, const uint64_t* words, const uint32_t* coarse, const float* aabbs,
+                             const float* t_sorted, const int64_t* t_indices, const uint8_t* hits, float step_size,
+                             float cone_angle, int32_t traverse_steps_limit, int32_t fill, const int64_t* iv_starts,
+                             int64_t* iv_cnts, float* iv_vals, int64_t* iv_ray_indices, uint8_t* iv_is_left,
+                             uint8_t* iv_is_right, const int64_t* sm_starts, int64_t* sm_cnts, float* sm_vals,
+                             int64_t* sm_ray_indices, uint8_t* sm_is_valid, float* terminate_planes, nfa_stream_t stream)
+{
+    if (n_rays < 0 || n_grids <= 0 || rx <= 0 || ry <= 0 || rz <= 0) return NFA_ERR_ARG;
+    if (n_rays == 0) return NFA_OK;
+    if (!rays_o || !rays_d || !near_planes || !far_planes || !words || !coarse || !aabbs || !t_sorted || !t_indices ||
+        !hits || !iv_cnts || !sm_cnts)
+        return NFA_ERR_ARG;
+    if (fill && (!iv_starts || !sm_starts)) return NFA_ERR_ARG;
+    GenericParams p;
+    p.n_rays = n_rays;
+    p.rays_o = rays_o;
+    p.rays_d = rays_d;
+    p.rays_mask = rays_mask;
+    p.near_planes = near_planes;
+    p.far_planes = far_planes;
+    p.g = occ_geom(n_grids, rx, ry, rz);
+    p.words = words;
+    p.coarse = coarse;
+    p.aabbs = aabbs;
+    p.t_sorted = t_sorted;
+    p.t_indices = t_indices;
+    p.hits = hits;
+    p.step_size = step_size;
+    p.cone_angle = cone_angle;
+    p.limit = traverse_steps_limit;
+    p.fill = fill;
+    p.iv_starts = iv_starts; p.iv_cnts = iv_cnts; p.iv_vals = iv_vals; p.iv_ray = iv_ray_indices;
+    p.iv_left = iv_is_left; p.iv_right = iv_is_right;
+    p.sm_starts = sm_starts; p.sm_cnts = sm_cnts; p.sm_vals = sm_vals; p.sm_ray = sm_ray_indices;
+    p.sm_valid = sm_is_valid;
+    p.terminate = terminate_planes;
+    generic_traverse_kernel<<<(n_rays + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p);
     return launch_status();
 }
 

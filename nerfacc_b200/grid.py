@@ -292,14 +292,80 @@ def traverse_grids(
 
     fast = (cone_angle == 0.0 and step_size is not None and step_size > 0.0 and traverse_steps_limit <= 0
             and not over_allocate)
-    if not fast:
-        raise NotImplementedError(
-            "nerfacc_b200.traverse_grids: cone_angle > 0, step_size <= 0 and traverse_steps_limit / "
-            "over_allocate are not built yet in this round (constant-step exact-allocation mode only).")
-    # rays_mask is ignored in exact-allocation mode by the reference too (grid.cu:418,450)
-    res = _march(rays_o, rays_d, binaries, aabbs, near_planes, far_planes, float(step_size), t_sorted, t_indices,
-                 hits, want_intervals=True, want_terminate=True)
-    return res.intervals, res.samples, res.terminate_planes
+    if fast:
+        # rays_mask is ignored in exact-allocation mode by the reference too (grid.cu:418,450)
+        res = _march(rays_o, rays_d, binaries, aabbs, near_planes, far_planes, float(step_size), t_sorted, t_indices,
+                     hits, want_intervals=True, want_terminate=True)
+        return res.intervals, res.samples, res.terminate_planes
+    return _traverse_generic(rays_o, rays_d, binaries, aabbs, near_planes, far_planes, float(step_size),
+                             float(cone_angle), int(traverse_steps_limit), bool(over_allocate), rays_mask, t_sorted,
+                             t_indices, hits)
+
+
+def _traverse_generic(rays_o, rays_d, binaries, aabbs, near_planes, far_planes, step_size, cone_angle, limit,
+                      over_allocate, rays_mask, t_sorted, t_indices, hits):
+    """cone_angle > 0, step_size <= 0, step limits, over-allocation, masks: count pass -> scan -> fill pass
+    (one pass into fixed-stride slots when over-allocating), reference grid.cu:364-470."""
+    device = rays_o.device
+    n_rays = rays_o.shape[0]
+    n_grids, rx, ry, rz = (int(s) for s in binaries.shape)
+    occ = _packed_grid(binaries)
+    if t_sorted is None:
+        t_sorted = torch.empty((n_rays, 2 * n_grids), dtype=torch.float32, device=device)
+        t_indices = torch.empty((n_rays, 2 * n_grids), dtype=torch.int64, device=device)
+        hits = torch.empty((n_rays, n_grids), dtype=torch.bool, device=device)
+        if n_rays > 0:
+            _lib.call("nfa_intersect_sorted", device, n_rays, _lib.ptr(rays_o), _lib.ptr(rays_d), n_grids,
+                      _lib.ptr(aabbs), _lib.ptr(t_sorted), _lib.ptr(t_indices), _lib.ptr(hits))
+    if t_indices.dtype != torch.int64:
+        t_indices = t_indices.to(torch.int64)
+    if hits.dtype != torch.bool:
+        hits = hits != 0
+    mask = None
+    if rays_mask is not None:
+        mask = rays_mask.contiguous()
+        if mask.dtype != torch.bool:
+            mask = mask != 0
+    term = torch.empty(n_rays, dtype=torch.float32, device=device)
+
+    def run(fill, use_mask, iv_s, iv_c, sm_s, sm_c, arrays):
+        if n_rays == 0:
+            return
+        _lib.call("nfa_traverse_generic", device, n_rays, _lib.ptr(rays_o), _lib.ptr(rays_d),
+                  _lib.ptr(mask) if use_mask else None, _lib.ptr(near_planes), _lib.ptr(far_planes), n_grids, rx, ry, rz,
+                  _lib.ptr(occ.words), _lib.ptr(occ.coarse), _lib.ptr(aabbs), _lib.ptr(t_sorted), _lib.ptr(t_indices),
+                  _lib.ptr(hits), step_size, cone_angle, limit, int(fill), _lib.ptr(iv_s), _lib.ptr(iv_c),
+                  *[_lib.ptr(a) for a in arrays[:4]], _lib.ptr(sm_s), _lib.ptr(sm_c),
+                  *[_lib.ptr(a) for a in arrays[4:]], _lib.ptr(term) if fill else None)
+
+    if over_allocate:
+        m = torch.ones(n_rays, dtype=torch.int64, device=device) if mask is None else mask.to(torch.int64)
+        iv_cnts, sm_cnts = 2 * limit * m, limit * m
+    else:
+        iv_cnts = torch.zeros(n_rays, dtype=torch.int64, device=device)
+        sm_cnts = torch.zeros(n_rays, dtype=torch.int64, device=device)
+        run(False, False, None, iv_cnts, None, sm_cnts, [None] * 7)
+    iv_starts = torch.cumsum(iv_cnts, 0) - iv_cnts
+    sm_starts = torch.cumsum(sm_cnts, 0) - sm_cnts
+    n_edges = int(iv_cnts.sum().item()) if n_rays else 0
+    n_samples = int(sm_cnts.sum().item()) if n_rays else 0
+    iv_vals = torch.zeros(n_edges, dtype=torch.float32, device=device)
+    iv_ray = torch.zeros(n_edges, dtype=torch.int64, device=device)
+    iv_left = torch.zeros(n_edges, dtype=torch.bool, device=device)
+    iv_right = torch.zeros(n_edges, dtype=torch.bool, device=device)
+    sm_vals = torch.zeros(n_samples, dtype=torch.float32, device=device)
+    sm_ray = torch.zeros(n_samples, dtype=torch.int64, device=device)
+    sm_valid = torch.zeros(n_samples, dtype=torch.bool, device=device)
+    run(True, over_allocate, iv_starts, iv_cnts, sm_starts, sm_cnts,
+        [iv_vals, iv_ray, iv_left, iv_right, sm_vals, sm_ray, sm_valid])
+    if over_allocate:  # reference grid.cu:402-404: starts recomputed from the actual counts
+        iv_starts = torch.cumsum(iv_cnts, 0) - iv_cnts
+        sm_starts = torch.cumsum(sm_cnts, 0) - sm_cnts
+    intervals = RayIntervals(vals=iv_vals, packed_info=torch.stack([iv_starts, iv_cnts], -1), ray_indices=iv_ray,
+                             is_left=iv_left, is_right=iv_right)
+    samples = RaySamples(vals=sm_vals, packed_info=torch.stack([sm_starts, sm_cnts], -1), ray_indices=sm_ray,
+                         is_valid=sm_valid)
+    return intervals, samples, term
 
 
 def _enlarge_aabb(aabb, factor: float) -> Tensor:

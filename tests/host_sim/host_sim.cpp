@@ -12,6 +12,7 @@
 
 #include "../../nerfacc_b200/csrc/occ_pack.cuh"
 #include "../../nerfacc_b200/csrc/expand.cuh"
+#include "../../nerfacc_b200/csrc/march_generic.cuh"
 
 using namespace nfa;
 
@@ -162,6 +163,47 @@ int64_t sim_march(int32_t n_rays, const float* rays_o, const float* rays_d,
         for (size_t q = 0; q < vt.size(); ++q) { run_t[total] = vt[q]; run_n[total] = vn[q]; ++total; }
     }
     return total;
+}
+
+
+// Generic traversal (cone angle, per-cell sampling, step limits, masks): one pass over all rays.
+// fill == 0: counts only (iv_cnts / sm_cnts written); fill == 1: arrays written at iv_starts / sm_starts.
+void sim_generic_pass(int32_t n_rays, const float* rays_o, const float* rays_d, const uint8_t* rays_mask,
+                      const float* near_planes, const float* far_planes,
+                      int n_grids, int rx, int ry, int rz, const uint64_t* words, const uint32_t* coarse,
+                      const float* aabbs, const float* t_sorted, const int64_t* t_indices, const uint8_t* hits,
+                      float step_size, float cone_angle, int32_t limit, int32_t fill,
+                      const int64_t* iv_starts, int64_t* iv_cnts, float* iv_vals, int64_t* iv_ray, uint8_t* iv_left,
+                      uint8_t* iv_right, const int64_t* sm_starts, int64_t* sm_cnts, float* sm_vals, int64_t* sm_ray,
+                      uint8_t* sm_valid, float* terminate)
+{
+    OccView occ;
+    occ.words = words;
+    occ.coarse = coarse;
+    occ.bounds = nullptr;
+    occ.g = occ_geom(n_grids, rx, ry, rz);
+    for (int32_t r = 0; r < n_rays; ++r) {
+        if (rays_mask && !rays_mask[r]) continue;                      // reference grid.cu:100
+        if (fill && (iv_cnts[r] == 0 || sm_cnts[r] == 0)) continue;    // grid.cu:103-106
+        GenericOut out;
+        out.fill = fill != 0;
+        out.ray = r;
+        out.want_iv = true;
+        out.want_sm = true;
+        out.iv_base = fill ? iv_starts[r] : 0;
+        out.sm_base = fill ? sm_starts[r] : 0;
+        out.iv_vals = iv_vals; out.iv_ray = iv_ray; out.iv_left = iv_left; out.iv_right = iv_right;
+        out.sm_vals = sm_vals; out.sm_ray = sm_ray; out.sm_valid = sm_valid;
+        out.n_edges = 0;
+        out.n_samples = 0;
+        SortedBoxes b{aabbs, n_grids, t_sorted + (int64_t)r * 2 * n_grids, t_indices + (int64_t)r * 2 * n_grids,
+                      hits + (int64_t)r * n_grids};
+        const float term = generic_march_ray(b, occ, rays_o + 3 * r, rays_d + 3 * r, near_planes[r], far_planes[r],
+                                             step_size, cone_angle, limit, out);
+        if (terminate) terminate[r] = term;
+        iv_cnts[r] = out.n_edges;
+        sm_cnts[r] = out.n_samples;
+    }
 }
 
 }  // extern "C"

@@ -553,3 +553,77 @@ def test_abi_direct_call_with_raw_pointers():
     torch.cuda.synchronize()
     assert out.tolist() == [[0, 3], [3, 0], [3, 2], [5, 0], [5, 0], [5, 1]]
     assert lib.nfa_pack_info(6, ri.data_ptr(), 6, out.data_ptr() + 8, ws.data_ptr(), None) == -1  # misaligned output
+
+
+# ---------------------------------------------------------------- the other traverse_grids modes (generic kernel)
+
+def _cmp_traverse(orc, ro, rd, bins, aabbs, **kw):
+    tkw = {k: (T(v) if isinstance(v, np.ndarray) else v) for k, v in kw.items()}
+    iv, sm, term = nfa.traverse_grids(T(ro), T(rd), T(bins), T(aabbs), **tkw)
+    o_iv, o_sm, o_term = orc.traverse_grids(ro, rd, bins, aabbs, **kw)
+    np.testing.assert_array_equal(N(iv.packed_info), o_iv["packed_info"])
+    np.testing.assert_array_equal(N(sm.packed_info), o_sm["packed_info"])
+    np.testing.assert_array_equal(N(iv.vals), o_iv["vals"])
+    np.testing.assert_array_equal(N(iv.is_left), o_iv["is_left"])
+    np.testing.assert_array_equal(N(iv.is_right), o_iv["is_right"])
+    np.testing.assert_array_equal(N(iv.ray_indices), o_iv["ray_indices"])
+    np.testing.assert_array_equal(N(sm.vals), o_sm["vals"])
+    np.testing.assert_array_equal(N(sm.is_valid), o_sm["is_valid"])
+    np.testing.assert_array_equal(N(sm.ray_indices), o_sm["ray_indices"])
+    d = ~np.isnan(o_term)
+    np.testing.assert_array_equal(N(term)[d], o_term[d])
+    return int(o_sm["packed_info"][:, 1].sum())
+
+
+def test_traverse_grids_generic_modes(orc):
+    rng = np.random.default_rng(21)
+    R = 200
+    ro = rng.standard_normal((R, 3)).astype(np.float32)
+    rd = rng.standard_normal((R, 3)).astype(np.float32)
+    rd /= np.linalg.norm(rd, axis=1, keepdims=True)
+    bins4 = rng.random((4, 32, 32, 32)) > 0.5
+    a4 = scenes.nested_aabbs(4)
+    assert _cmp_traverse(orc, ro, rd, bins4, a4, step_size=5e-3, cone_angle=0.01) > 0
+    assert _cmp_traverse(orc, ro, rd, bins4, a4, step_size=1e-2, cone_angle=0.004, near_planes=rng.random(R).astype(np.float32),
+                         far_planes=(2 + rng.random(R)).astype(np.float32)) > 0
+    assert _cmp_traverse(orc, ro, rd, bins4, a4, step_size=0.0) > 0       # one sample per occupied cell
+    assert _cmp_traverse(orc, ro, rd, bins4[:1], a4[:1], step_size=-1.0) > 0
+    mask = rng.random(R) > 0.3
+    assert _cmp_traverse(orc, ro, rd, bins4, a4, step_size=1e-2, traverse_steps_limit=37, over_allocate=True, rays_mask=mask) > 0
+    assert _cmp_traverse(orc, ro, rd, bins4, a4, step_size=1e-2, cone_angle=0.003, traverse_steps_limit=5, over_allocate=True) > 0
+    assert _cmp_traverse(orc, ro, rd, bins4, a4, step_size=1e-2, traverse_steps_limit=50, rays_mask=mask) > 0
+    # sampling() with a cone angle goes through the same kernel
+    est = _estimator(bins4, a4)
+    ri, ts, te = est.sampling(T(ro), T(rd), render_step_size=5e-3, cone_angle=0.01)
+    o_ri, o_ts, o_te, _ = orc.occgrid_sampling(ro, rd, bins4, a4, render_step_size=5e-3, cone_angle=0.01)
+    np.testing.assert_array_equal(N(ri), o_ri)
+    np.testing.assert_array_equal(N(ts), o_ts)
+    np.testing.assert_array_equal(N(te), o_te)
+
+
+def test_reference_test_mode_marching():
+    """reference tests/test_grid.py:72-131: two bounded rounds reproduce the one-shot traversal."""
+    from nerfacc_b200.grid import _enlarge_aabb
+    torch.manual_seed(42)
+    n_rays = 10
+    ro = torch.randn((n_rays, 3), device=dev)
+    rd = torch.randn((n_rays, 3), device=dev)
+    rd = rd / rd.norm(dim=-1, keepdim=True)
+    base = torch.tensor([-1.0, -1.0, -1.0, 1.0, 1.0, 1.0], device=dev)
+    aabbs = torch.stack([_enlarge_aabb(base, 2 ** i) for i in range(4)])
+    binaries = torch.rand((4, 32, 32, 32), device=dev) > 0.5
+    iv, sm, _ = nfa.traverse_grids(ro, rd, binaries, aabbs)
+    ts, te = iv.vals[iv.is_left], iv.vals[iv.is_right]
+    acc_s = nfa.accumulate_along_rays(ts, None, sm.ray_indices, n_rays)
+    acc_e = nfa.accumulate_along_rays(te, None, sm.ray_indices, n_rays)
+    _acc_s = _acc_e = 0.0
+    term, mask = None, None
+    for _ in range(2):
+        _iv, _sm, term = nfa.traverse_grids(ro, rd, binaries, aabbs, near_planes=term, traverse_steps_limit=4000,
+                                            over_allocate=True, rays_mask=mask)
+        mask = _sm.packed_info[:, 1] == 4000
+        _ri = _sm.ray_indices[_sm.is_valid]
+        _acc_s = _acc_s + nfa.accumulate_along_rays(_iv.vals[_iv.is_left], None, _ri, n_rays)
+        _acc_e = _acc_e + nfa.accumulate_along_rays(_iv.vals[_iv.is_right], None, _ri, n_rays)
+    assert (~mask).all()
+    assert torch.allclose(_acc_s, acc_s, atol=1e-1) and torch.allclose(acc_e, _acc_e, atol=1e-1)

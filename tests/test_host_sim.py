@@ -197,3 +197,86 @@ def test_march_matches_reference_cuda_goldens(host_sim):
         np.testing.assert_array_equal(ns, z["packed_info"][:, 1])
         np.testing.assert_array_equal(s, z["t_starts"])
         np.testing.assert_array_equal(e, z["t_ends"])
+
+
+# ---------------------------------------------------------------- generic marcher (march_generic.cuh)
+
+def _sim_generic(sim, ro, rd, bins, aabbs, near, far, step, cone, limit=-1, over_allocate=False, mask=None, orc=None):
+    G, rx, ry, rz = bins.shape
+    R = ro.shape[0]
+    words = np.zeros(sim.sim_occ_words(G, rx, ry, rz), np.uint64)
+    coarse = np.zeros(sim.sim_occ_coarse_words(G, rx, ry, rz), np.uint32)
+    bounds = np.zeros(6 * G, np.int32)
+    b8 = np.ascontiguousarray(bins.astype(np.uint8))
+    sim.sim_occ_pack(G, rx, ry, rz, _p(b8, U8), _p(words, U64), _p(coarse, U32), _p(bounds, I32))
+    tm, tM, h = orc.ray_aabb_intersect(ro, rd, aabbs)
+    tsrt, tidx = orc.sort_intersections(tm, tM)
+    hits = np.ascontiguousarray(h.astype(np.uint8))
+    iv_cnts, sm_cnts = np.zeros(R, np.int64), np.zeros(R, np.int64)
+    term = np.full(R, np.nan, np.float32)
+    m8 = None if mask is None else np.ascontiguousarray(mask.astype(np.uint8))
+
+    def run(fill, use_mask, iv_s, sm_s, arrs):
+        sim.sim_generic_pass(R, _p(ro, F), _p(rd, F), _p(m8 if use_mask else None, U8), _p(near, F), _p(far, F), G, rx, ry, rz,
+                             _p(words, U64), _p(coarse, U32), _p(aabbs, F), _p(tsrt, F), _p(tidx, I64), _p(hits, U8),
+                             C.c_float(step), C.c_float(cone), C.c_int32(limit), C.c_int32(fill),
+                             _p(iv_s, I64), _p(iv_cnts, I64), *[_p(a, t) for a, t in arrs[:4]],
+                             _p(sm_s, I64), _p(sm_cnts, I64), *[_p(a, t) for a, t in arrs[4:]], _p(term if fill else None, F))
+
+    if over_allocate:
+        mm = np.ones(R, np.int64) if mask is None else mask.astype(np.int64)
+        iv_cnts[:] = 2 * limit * mm
+        sm_cnts[:] = limit * mm
+    else:
+        run(0, False, None, None, [(None, F), (None, I64), (None, U8), (None, U8), (None, F), (None, I64), (None, U8)])
+    iv_s = (np.cumsum(iv_cnts) - iv_cnts).astype(np.int64)
+    sm_s = (np.cumsum(sm_cnts) - sm_cnts).astype(np.int64)
+    ne, ns = int(iv_cnts.sum()), int(sm_cnts.sum())
+    iv_vals, iv_ray = np.zeros(ne, np.float32), np.zeros(ne, np.int64)
+    iv_l, iv_r = np.zeros(ne, np.uint8), np.zeros(ne, np.uint8)
+    sm_vals, sm_ray, sm_valid = np.zeros(ns, np.float32), np.zeros(ns, np.int64), np.zeros(ns, np.uint8)
+    run(1, over_allocate, iv_s, sm_s, [(iv_vals, F), (iv_ray, I64), (iv_l, U8), (iv_r, U8), (sm_vals, F), (sm_ray, I64), (sm_valid, U8)])
+    return dict(iv_vals=iv_vals, iv_ray=iv_ray, iv_left=iv_l.astype(bool), iv_right=iv_r.astype(bool), iv_cnts=iv_cnts.copy(),
+                sm_vals=sm_vals, sm_ray=sm_ray, sm_valid=sm_valid.astype(bool), sm_cnts=sm_cnts.copy(), term=term)
+
+
+def _check_generic(sim, orc, ro, rd, bins, aabbs, near, far, step, cone, **kw):
+    mine = _sim_generic(sim, ro, rd, bins, aabbs, near, far, step, cone, orc=orc, **kw)
+    iv, sm, term = orc.traverse_grids(ro, rd, bins, aabbs, near_planes=near, far_planes=far, step_size=step, cone_angle=cone,
+                                      traverse_steps_limit=kw.get("limit", -1) if kw.get("limit", -1) > 0 else None,
+                                      over_allocate=kw.get("over_allocate", False), rays_mask=kw.get("mask"))
+    np.testing.assert_array_equal(mine["iv_cnts"], iv["packed_info"][:, 1])
+    np.testing.assert_array_equal(mine["sm_cnts"], sm["packed_info"][:, 1])
+    np.testing.assert_array_equal(mine["iv_vals"], iv["vals"])
+    np.testing.assert_array_equal(mine["iv_left"], iv["is_left"])
+    np.testing.assert_array_equal(mine["iv_right"], iv["is_right"])
+    np.testing.assert_array_equal(mine["iv_ray"], iv["ray_indices"])
+    np.testing.assert_array_equal(mine["sm_vals"], sm["vals"])
+    np.testing.assert_array_equal(mine["sm_valid"], sm["is_valid"])
+    np.testing.assert_array_equal(mine["sm_ray"], sm["ray_indices"])
+    d = ~np.isnan(term)
+    np.testing.assert_array_equal(mine["term"][d], term[d])
+    return int(mine["sm_cnts"].sum())
+
+
+def test_generic_marcher_modes(host_sim, orc):
+    rng = np.random.default_rng(21)
+    R = 120
+    ro = rng.standard_normal((R, 3)).astype(np.float32)
+    rd = rng.standard_normal((R, 3)).astype(np.float32)
+    rd /= np.linalg.norm(rd, axis=1, keepdims=True)
+    bins4 = rng.random((4, 32, 32, 32)) > 0.5
+    a4 = scenes.nested_aabbs(4)
+    zero, inf = np.zeros(R, np.float32), np.full(R, np.inf, np.float32)
+    assert _check_generic(host_sim, orc, ro, rd, bins4, a4, zero, inf, 1e-2, 0.0) > 0          # same as the fast path
+    assert _check_generic(host_sim, orc, ro, rd, bins4, a4, zero, inf, 5e-3, 0.01) > 0         # cone angle
+    assert _check_generic(host_sim, orc, ro, rd, bins4, a4, (rng.random(R)).astype(np.float32),
+                          (2 + rng.random(R)).astype(np.float32), 1e-2, 0.004) > 0
+    assert _check_generic(host_sim, orc, ro, rd, bins4, a4, zero, inf, 0.0, 0.0) > 0           # one sample per cell
+    assert _check_generic(host_sim, orc, ro, rd, bins4[:1], a4[:1], zero, inf, -1.0, 0.0) > 0
+    # bounded marching into fixed-stride slots, with a ray mask (reference examples/utils.py:356-375)
+    mask = rng.random(R) > 0.3
+    assert _check_generic(host_sim, orc, ro, rd, bins4, a4, zero, inf, 1e-2, 0.0, limit=37, over_allocate=True, mask=mask) > 0
+    assert _check_generic(host_sim, orc, ro, rd, bins4, a4, zero, inf, 1e-2, 0.003, limit=5, over_allocate=True) > 0
+    # a limit without over-allocation (two-pass; the mask is ignored there, reference grid.cu:418,450)
+    assert _check_generic(host_sim, orc, ro, rd, bins4, a4, zero, inf, 1e-2, 0.0, limit=50, mask=mask) > 0
