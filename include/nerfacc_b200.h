@@ -28,7 +28,7 @@ extern "C" {
 #define NFA_ERR_ARG (-1)         /* null pointer / negative size / inconsistent sizes */
 #define NFA_ERR_UNSUPPORTED (-2) /* valid request outside what this build implements */
 
-#define NFA_ABI_VERSION 5
+#define NFA_ABI_VERSION 6
 
 typedef void* nfa_stream_t; /* cudaStream_t */
 
@@ -222,6 +222,19 @@ int32_t nfa_scan_by_key(int64_t n, const int64_t* keys, const float* in, float* 
 int64_t nfa_pack_info_workspace_bytes(int32_t n_rays);
 int32_t nfa_pack_info(int64_t n, const int64_t* ray_indices, int32_t n_rays, int64_t* packed_info,
                       void* workspace, nfa_stream_t stream);
+
+/* replaces: the visibility branch of OccGridEstimator.sampling (nerfacc/estimators/occ_grid.py:180-220):
+ *   render_visibility_from_density / _from_alpha (volrend.py:379-494; native exclusive_sum / exclusive_prod on
+ *   packed_info) followed by three boolean mask-selects.  Keeps sample i iff T_i >= early_stop_eps and
+ *   (alpha_thre <= 0 or alpha_i >= alpha_thre); writes the kept (ray_indices, t_starts, t_ends) compacted in
+ *   ray order, their packed_info, and the kept total (device and/or pinned host memory).  The outputs need room
+ *   for n_samples elements (the caller narrows after one sync).  workspace: nfa_visibility_workspace_bytes(). */
+int64_t nfa_visibility_workspace_bytes(int32_t n_rays, int64_t n_samples);
+int32_t nfa_visibility_compact(int32_t n_rays, int64_t n_samples, const int64_t* packed_info,
+                               const float* t_starts, const float* t_ends, const float* sigmas_or_alphas,
+                               int32_t from_alpha, float early_stop_eps, float alpha_thre, void* workspace,
+                               int64_t* new_packed_info, int64_t* out_ray_indices, float* out_t_starts,
+                               float* out_t_ends, int64_t* total_dev, int64_t* total_host, nfa_stream_t stream);
 
 #ifdef __cplusplus
 }

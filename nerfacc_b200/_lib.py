@@ -49,11 +49,14 @@ SIGNATURES = {
     "nfa_scan_packed": (_c_i32, [_c_i32, _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32, _c_i32, _c_ptr]),
     "nfa_scan_by_key_workspace_bytes": (_c_i64, [_c_i64]),
     "nfa_scan_by_key": (_c_i32, [_c_i64, _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32, _c_ptr, _c_ptr]),
+    "nfa_visibility_workspace_bytes": (_c_i64, [_c_i32, _c_i64]),
+    "nfa_visibility_compact": (_c_i32, [_c_i32, _c_i64, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_f32, _c_f32]
+                               + [_c_ptr] * 8),
     "nfa_pack_info_workspace_bytes": (_c_i64, [_c_i32]),
     "nfa_pack_info": (_c_i32, [_c_i64, _c_ptr, _c_i32, _c_ptr, _c_ptr, _c_ptr]),
 }
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 _lib = None
 launches = 0  # number of native kernel-launching calls made through this module (bench.py reports it)

@@ -342,7 +342,9 @@ __global__ void __launch_bounds__(kPackTile) pack_tilesum_kernel(int32_t n_rays,
 __global__ void __launch_bounds__(kPackTile) pack_scan_kernel(int32_t n_rays,
                                                              const unsigned long long* __restrict__ counts,
                                                              const unsigned long long* __restrict__ tile_sums,
-                                                             int64_t* __restrict__ packed_info)
+                                                             int64_t* __restrict__ packed_info,
+                                                             int64_t* __restrict__ total_dev,
+                                                             int64_t* __restrict__ total_host)
 {
     __shared__ unsigned long long s[32];
     __shared__ unsigned long long s_base;
@@ -377,6 +379,104 @@ __global__ void __launch_bounds__(kPackTile) pack_scan_kernel(int32_t n_rays,
         v.x = (long long)(pre + x - c);
         v.y = (long long)c;
         *reinterpret_cast<longlong2*>(packed_info + 2 * (int64_t)r) = v;
+        if (r == n_rays - 1) {  // grand total, optionally straight into pinned host memory
+            if (total_dev) *total_dev = v.x + v.y;
+            if (total_host) {
+                *total_host = v.x + v.y;
+                __threadfence_system();
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Visibility filter + stream compaction (the sigma_fn / alpha_fn branch of
+// OccGridEstimator.sampling, reference estimators/occ_grid.py:180-220 +
+// volrend.py:379-494): keep sample i iff T_i >= early_stop_eps and (alpha_thre <= 0 or
+// alpha_i >= alpha_thre).  The reference runs a scan kernel, ~6 elementwise ops and three
+// synchronising boolean mask-selects; here: mask + per-ray counts, the two-level scan of
+// pack_info, and a ballot compaction that writes the kept samples and their packed_info.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float vis_exp_neg(float x) { return __expf(-x); }
+
+template <bool kAlpha>
+__global__ void __launch_bounds__(kScanWarps * 32) vis_mask_kernel(int32_t n_rays,
+                                                                   const int64_t* __restrict__ packed_info,
+                                                                   const float* __restrict__ t_starts,
+                                                                   const float* __restrict__ t_ends,
+                                                                   const float* __restrict__ dens, float early_stop_eps,
+                                                                   float alpha_thre, uint8_t* __restrict__ mask,
+                                                                   unsigned long long* __restrict__ counts)
+{
+    const int lane = threadIdx.x & 31;
+    for (int r = blockIdx.x * kScanWarps + (threadIdx.x >> 5); r < n_rays; r += gridDim.x * kScanWarps) {
+        const longlong2 pi = *reinterpret_cast<const longlong2*>(packed_info + 2 * (int64_t)r);
+        const int64_t start = pi.x, n = pi.y;
+        float carry = kAlpha ? 1.0f : 0.0f;
+        unsigned kept = 0;
+        for (int64_t base = 0; base < n; base += 32) {
+            const int64_t i = start + base + lane;
+            const bool valid = base + lane < n;
+            float T, a;
+            if (!kAlpha) {
+                const float sd = valid ? __ldg(dens + i) * (__ldg(t_ends + i) - __ldg(t_starts + i)) : 0.f;
+                float incl = sd;
+#pragma unroll
+                for (int s = 1; s < 32; s <<= 1) {
+                    const float y = __shfl_up_sync(kFullMask, incl, s);
+                    if (lane >= s) incl += y;
+                }
+                T = vis_exp_neg(carry + (incl - sd));
+                a = 1.0f - vis_exp_neg(sd);
+                carry += __shfl_sync(kFullMask, incl, 31);
+            } else {
+                a = valid ? __ldg(dens + i) : 0.f;
+                float incl = 1.0f - a;
+#pragma unroll
+                for (int s = 1; s < 32; s <<= 1) {
+                    const float y = __shfl_up_sync(kFullMask, incl, s);
+                    if (lane >= s) incl *= y;
+                }
+                float excl = __shfl_up_sync(kFullMask, incl, 1);
+                if (lane == 0) excl = 1.0f;
+                T = carry * excl;
+                carry *= __shfl_sync(kFullMask, incl, 31);
+            }
+            const bool keep = valid && (T >= early_stop_eps) && (!(alpha_thre > 0.0f) || a >= alpha_thre);
+            if (valid) mask[i] = keep ? 1 : 0;
+            kept += __popc(__ballot_sync(kFullMask, keep));
+        }
+        if (lane == 0) counts[r] = kept;
+    }
+}
+
+__global__ void __launch_bounds__(kScanWarps * 32) vis_compact_kernel(int32_t n_rays,
+                                                                      const int64_t* __restrict__ packed_info,
+                                                                      const int64_t* __restrict__ new_packed_info,
+                                                                      const uint8_t* __restrict__ mask,
+                                                                      const float* __restrict__ t_starts,
+                                                                      const float* __restrict__ t_ends,
+                                                                      int64_t* __restrict__ out_ray,
+                                                                      float* __restrict__ out_ts, float* __restrict__ out_te)
+{
+    const int lane = threadIdx.x & 31;
+    for (int r = blockIdx.x * kScanWarps + (threadIdx.x >> 5); r < n_rays; r += gridDim.x * kScanWarps) {
+        const longlong2 pi = *reinterpret_cast<const longlong2*>(packed_info + 2 * (int64_t)r);
+        const longlong2 po = *reinterpret_cast<const longlong2*>(new_packed_info + 2 * (int64_t)r);
+        if (po.y == 0) continue;
+        int64_t dst = po.x;
+        for (int64_t base = 0; base < pi.y; base += 32) {
+            const int64_t i = pi.x + base + lane;
+            const bool keep = (base + lane < pi.y) && mask[i];
+            const unsigned b = __ballot_sync(kFullMask, keep);
+            if (keep) {
+                const int64_t k = dst + __popc(b & ((1u << lane) - 1u));
+                out_ray[k] = r;
+                out_ts[k] = __ldg(t_starts + i);
+                out_te[k] = __ldg(t_ends + i);
+            }
+            dst += __popc(b);
+        }
     }
 }
 
@@ -486,7 +586,48 @@ int32_t nfa_pack_info(int64_t n, const int64_t* ray_indices, int32_t n_rays, int
         pack_count_kernel<<<blocks, 256, 0, s>>>(n, ray_indices, n_rays, counts);
     }
     pack_tilesum_kernel<<<tiles, kPackTile, 0, s>>>(n_rays, counts, tile_sums);
-    pack_scan_kernel<<<tiles, kPackTile, 0, s>>>(n_rays, counts, tile_sums, packed_info);
+    pack_scan_kernel<<<tiles, kPackTile, 0, s>>>(n_rays, counts, tile_sums, packed_info, nullptr, nullptr);
+    return launch_status_s();
+}
+
+int64_t nfa_visibility_workspace_bytes(int32_t n_rays, int64_t n_samples)
+{
+    if (n_rays <= 0 || n_samples < 0) return 16;
+    const int64_t tiles = (n_rays + kPackTile - 1) / kPackTile;
+    return ((n_samples + 15) & ~(int64_t)15) + (int64_t)n_rays * 8 + tiles * 8 + 16;
+}
+
+int32_t nfa_visibility_compact(int32_t n_rays, int64_t n_samples, const int64_t* packed_info, const float* t_starts,
+                               const float* t_ends, const float* sigmas_or_alphas, int32_t from_alpha,
+                               float early_stop_eps, float alpha_thre, void* workspace, int64_t* new_packed_info,
+                               int64_t* out_ray_indices, float* out_t_starts, float* out_t_ends, int64_t* total_dev,
+                               int64_t* total_host, nfa_stream_t stream)
+{
+    if (n_rays < 0 || n_samples < 0) return NFA_ERR_ARG;
+    if (total_host) *total_host = 0;
+    if (n_rays == 0) return NFA_OK;
+    if (!packed_info || !new_packed_info || !workspace) return NFA_ERR_ARG;
+    if (n_samples > 0 && (!t_starts || !t_ends || !sigmas_or_alphas || !out_ray_indices || !out_t_starts || !out_t_ends))
+        return NFA_ERR_ARG;
+    if (((((uintptr_t)packed_info) | ((uintptr_t)new_packed_info)) & 15u) != 0) return NFA_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    uint8_t* mask = (uint8_t*)workspace;
+    unsigned long long* counts = (unsigned long long*)((char*)workspace + ((n_samples + 15) & ~(int64_t)15));
+    const int tiles = (n_rays + kPackTile - 1) / kPackTile;
+    unsigned long long* tile_sums = counts + n_rays;
+    const int need = (n_rays + kScanWarps - 1) / kScanWarps;
+    const int blocks = need < 148 * 8 ? need : 148 * 8;
+    if (from_alpha)
+        vis_mask_kernel<true><<<blocks, kScanWarps * 32, 0, s>>>(n_rays, packed_info, t_starts, t_ends, sigmas_or_alphas,
+                                                                 early_stop_eps, alpha_thre, mask, counts);
+    else
+        vis_mask_kernel<false><<<blocks, kScanWarps * 32, 0, s>>>(n_rays, packed_info, t_starts, t_ends, sigmas_or_alphas,
+                                                                  early_stop_eps, alpha_thre, mask, counts);
+    pack_tilesum_kernel<<<tiles, kPackTile, 0, s>>>(n_rays, counts, tile_sums);
+    pack_scan_kernel<<<tiles, kPackTile, 0, s>>>(n_rays, counts, tile_sums, new_packed_info, total_dev, total_host);
+    if (n_samples > 0)
+        vis_compact_kernel<<<blocks, kScanWarps * 32, 0, s>>>(n_rays, packed_info, new_packed_info, mask, t_starts, t_ends,
+                                                              out_ray_indices, out_t_starts, out_t_ends);
     return launch_status_s();
 }
 

@@ -584,6 +584,64 @@ __global__ void __launch_bounds__(kExpandThreads) expand_runs_kernel(const Expan
     }
 }
 
+// Samples-only expansion with 128-bit stores: a piece (lattice.cuh) of a run is written as an
+// unaligned head (< 4 samples), a body of output groups [4G, 4G+3] -- one lane per group: a float4 of
+// starts, a float4 of ends, two longlong2 of ray ids -- and a tail.  Same values as the scalar kernel.
+__global__ void __launch_bounds__(kExpandThreads) expand_runs_vec_kernel(const ExpandParams p)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * kExpandThreads + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * kExpandThreads) >> 5;
+    int64_t n_runs = p.totals[1];
+    if (n_runs > p.ws.run_capacity) n_runs = p.ws.run_capacity;
+    const Lattice L = lat_make(p.step_size);
+    for (int64_t q = warp0; q < n_runs; q += n_warps) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.ws.pool + q));
+        const long long ray = a.x;
+        int64_t off = p.sm_packed_info[2 * ray] + a.y;
+        RunIter it;
+        it.t = __uint_as_float(a.w);
+        it.left = a.z;
+        while (it.left > 0) {
+            LatPiece pc;
+            int64_t c = run_next_piece(L, it, pc);
+            if (off + c > p.sample_capacity) c = p.sample_capacity > off ? p.sample_capacity - off : 0;
+            // head: bring `off` to a multiple of 4 (also covers short pieces entirely)
+            const int head = (int)min((int64_t)((4 - (off & 3)) & 3), c);
+            const int64_t body_groups = (c - head) >> 2;
+            const int tail = (int)(c - head - 4 * body_groups);
+            if (lane < head) {
+                const float ts = piece_start(pc, (uint32_t)lane);
+                p.ray_indices[off + lane] = ray;
+                p.t_starts[off + lane] = ts;
+                p.t_ends[off + lane] = f_add(ts, L.dt);
+            }
+            const int64_t g0 = (off + head) >> 2;
+            for (int64_t gi = lane; gi < body_groups; gi += 32) {
+                const uint32_t j = (uint32_t)(head + 4 * gi);
+                float4 s4, e4;
+                s4.x = piece_start(pc, j);     e4.x = f_add(s4.x, L.dt);
+                s4.y = piece_start(pc, j + 1); e4.y = f_add(s4.y, L.dt);
+                s4.z = piece_start(pc, j + 2); e4.z = f_add(s4.z, L.dt);
+                s4.w = piece_start(pc, j + 3); e4.w = f_add(s4.w, L.dt);
+                reinterpret_cast<float4*>(p.t_starts)[g0 + gi] = s4;
+                reinterpret_cast<float4*>(p.t_ends)[g0 + gi] = e4;
+                const longlong2 rr = make_longlong2(ray, ray);
+                reinterpret_cast<longlong2*>(p.ray_indices)[2 * (g0 + gi)] = rr;
+                reinterpret_cast<longlong2*>(p.ray_indices)[2 * (g0 + gi) + 1] = rr;
+            }
+            if (lane < tail) {
+                const int64_t k = off + head + 4 * body_groups + lane;
+                const float ts = piece_start(pc, (uint32_t)(head + 4 * body_groups + lane));
+                p.ray_indices[k] = ray;
+                p.t_starts[k] = ts;
+                p.t_ends[k] = f_add(ts, L.dt);
+            }
+            off += c;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // generic traversal (march_generic.cuh): cone angle, per-cell sampling, step limit, masks
 // ---------------------------------------------------------------------------
@@ -895,7 +953,9 @@ int32_t nfa_expand_samples(int32_t n_rays, int64_t run_capacity, const void* wor
         p.ray_indices = ray_indices;
         p.t_starts = t_starts;
         p.t_ends = t_ends;
-        expand_runs_kernel<false><<<expand_grid(run_capacity), kExpandThreads, 0, s>>>(p);
+        const uintptr_t al = (uintptr_t)ray_indices | (uintptr_t)t_starts | (uintptr_t)t_ends;
+        if ((al & 15u) == 0) expand_runs_vec_kernel<<<expand_grid(run_capacity), kExpandThreads, 0, s>>>(p);
+        else expand_runs_kernel<false><<<expand_grid(run_capacity), kExpandThreads, 0, s>>>(p);
     }
     return launch_status();
 }

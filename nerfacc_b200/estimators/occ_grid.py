@@ -13,6 +13,7 @@ import torch
 from torch import Tensor
 
 from ..grid import _enlarge_aabb, _march, traverse_grids
+from .. import _lib
 from ..pack import _stash_packed_info
 from ..volrend import render_visibility_from_alpha, render_visibility_from_density
 from .base import AbstractEstimator
@@ -131,26 +132,38 @@ class OccGridEstimator(AbstractEstimator):
 
         # drop invisible samples (occ_grid.py:180-220)
         if (alpha_thre > 0.0 or early_stop_eps > 0.0) and (sigma_fn is not None or alpha_fn is not None):
-            alpha_thre = min(alpha_thre, self.occs.mean().item())
-            if sigma_fn is not None:
-                if t_starts.shape[0] != 0:
-                    sigmas = sigma_fn(t_starts, t_ends, ray_indices)
-                else:
-                    sigmas = torch.empty((0,), device=t_starts.device)
-                assert sigmas.shape == t_starts.shape, "sigmas must have shape of (N,)! Got {}".format(sigmas.shape)
-                masks = render_visibility_from_density(
-                    t_starts=t_starts, t_ends=t_ends, sigmas=sigmas, packed_info=packed_info,
-                    early_stop_eps=early_stop_eps, alpha_thre=alpha_thre)
+            if alpha_thre > 0.0:  # min(0, mean) can never enable the alpha test, so the mean is only needed here
+                alpha_thre = min(alpha_thre, self._occs_mean())
+            use_sigma = sigma_fn is not None
+            if t_starts.shape[0] != 0:
+                dens = (sigma_fn if use_sigma else alpha_fn)(t_starts, t_ends, ray_indices)
             else:
-                if t_starts.shape[0] != 0:
-                    alphas = alpha_fn(t_starts, t_ends, ray_indices)
+                dens = torch.empty((0,), device=t_starts.device)
+            assert dens.shape == t_starts.shape, "{} must have shape of (N,)! Got {}".format(
+                "sigmas" if use_sigma else "alphas", dens.shape)
+            if t_starts.is_cuda and dens.dtype == torch.float32:
+                ray_indices, t_starts, t_ends = _visibility_compact(
+                    t_starts, t_ends, dens.detach(), packed_info, from_alpha=not use_sigma,
+                    early_stop_eps=float(early_stop_eps), alpha_thre=float(alpha_thre))
+            else:
+                if use_sigma:
+                    masks = render_visibility_from_density(t_starts=t_starts, t_ends=t_ends, sigmas=dens,
+                                                           packed_info=packed_info, early_stop_eps=early_stop_eps,
+                                                           alpha_thre=alpha_thre)
                 else:
-                    alphas = torch.empty((0,), device=t_starts.device)
-                assert alphas.shape == t_starts.shape, "alphas must have shape of (N,)! Got {}".format(alphas.shape)
-                masks = render_visibility_from_alpha(
-                    alphas=alphas, packed_info=packed_info, early_stop_eps=early_stop_eps, alpha_thre=alpha_thre)
-            ray_indices, t_starts, t_ends = ray_indices[masks], t_starts[masks], t_ends[masks]
+                    masks = render_visibility_from_alpha(alphas=dens, packed_info=packed_info,
+                                                         early_stop_eps=early_stop_eps, alpha_thre=alpha_thre)
+                ray_indices, t_starts, t_ends = ray_indices[masks], t_starts[masks], t_ends[masks]
         return ray_indices, t_starts, t_ends
+
+    def _occs_mean(self) -> float:
+        """`occs.mean()` (reference occ_grid.py:183), cached per version of the buffer: the reference pays a
+        2M-element reduction and a host sync for it on every sampling call."""
+        key = (self.occs.data_ptr(), self.occs._version)
+        if getattr(self, "_occs_mean_key", None) != key:
+            self._occs_mean_val = float(self.occs.mean().item())
+            self._occs_mean_key = key
+        return self._occs_mean_val
 
     # ------------------------------------------------------------------
     # grid maintenance (occ_grid.py:224-404)
@@ -263,6 +276,42 @@ class OccGridEstimator(AbstractEstimator):
             self.occs[cell_ids] = torch.maximum(self.occs[cell_ids] * ema_decay, occ)
         thre = torch.clamp(self.occs[self.occs >= 0].mean(), max=occ_thre)
         self.binaries = (self.occs > thre).view(self.binaries.shape)
+
+
+_vis_scratch = {}
+
+
+def _visibility_compact(t_starts: Tensor, t_ends: Tensor, dens: Tensor, packed_info: Tensor, from_alpha: bool,
+                        early_stop_eps: float, alpha_thre: float):
+    """Fused visibility test + compaction (nfa_visibility_compact): returns the kept
+    (ray_indices, t_starts, t_ends), grouped by ray, with their packed_info attached."""
+    device = t_starts.device
+    n, n_rays = t_starts.shape[0], packed_info.shape[0]
+    lib = _lib.load()
+    pi = packed_info.contiguous()
+    if pi.dtype != torch.int64:
+        pi = pi.to(torch.int64)
+    sc = _vis_scratch.get(device)
+    if sc is None:
+        sc = _vis_scratch[device] = (torch.zeros(1, dtype=torch.int64).pin_memory(), torch.cuda.Event())
+    total_host, event = sc
+    ws = torch.empty(lib.nfa_visibility_workspace_bytes(n_rays, n), dtype=torch.uint8, device=device)
+    new_pi = torch.empty((n_rays, 2), dtype=torch.int64, device=device)
+    out_ri = torch.empty(n, dtype=torch.int64, device=device)
+    out_ts = torch.empty(n, dtype=torch.float32, device=device)
+    out_te = torch.empty(n, dtype=torch.float32, device=device)
+    if n_rays == 0:
+        return out_ri, out_ts, out_te
+    _lib.call("nfa_visibility_compact", device, n_rays, n, _lib.ptr(pi), _lib.ptr(t_starts.contiguous()),
+              _lib.ptr(t_ends.contiguous()), _lib.ptr(dens.contiguous()), int(from_alpha), early_stop_eps, alpha_thre,
+              _lib.ptr(ws), _lib.ptr(new_pi), _lib.ptr(out_ri), _lib.ptr(out_ts), _lib.ptr(out_te), None,
+              _lib.ptr(total_host))
+    event.record(torch.cuda.current_stream(device))
+    event.synchronize()  # the one sync of this stage: the kept count
+    kept = int(total_host.item())
+    out_ri, out_ts, out_te = out_ri[:kept], out_ts[:kept], out_te[:kept]
+    _stash_packed_info(out_ri, new_pi, n_rays)
+    return out_ri, out_ts, out_te
 
 
 def _meshgrid3d(res: Tensor, device: Union[torch.device, str] = "cpu") -> Tensor:

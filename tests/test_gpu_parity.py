@@ -627,3 +627,47 @@ def test_reference_test_mode_marching():
         _acc_e = _acc_e + nfa.accumulate_along_rays(_iv.vals[_iv.is_right], None, _ri, n_rays)
     assert (~mask).all()
     assert torch.allclose(_acc_s, acc_s, atol=1e-1) and torch.allclose(acc_e, _acc_e, atol=1e-1)
+
+
+def test_fused_visibility_compaction(orc):
+    """sampling(sigma_fn=...) / (alpha_fn=...): fused mask + compaction vs masking the oracle's samples."""
+    R = 2048
+    ro, rd = scenes.ball_rays(R)
+    bins, a1 = scenes.ball_grid(64), scenes.nested_aabbs(1)
+    est = _estimator(bins, a1)
+    est.occs.fill_(0.3)
+    o_ri, o_ts, o_te, o_pi = orc.occgrid_sampling(ro, rd, bins, a1, render_step_size=1e-2)
+    g = torch.Generator().manual_seed(2)
+    sig_all = (30 * torch.rand(len(o_ri), generator=g)).to(dev)
+    calls = []
+
+    def sigma_fn(ts, te, ri):
+        calls.append(ts.shape[0])
+        return sig_all
+    for eps, thre in [(1e-2, 0.0), (1e-3, 0.05), (0.0, 0.1)]:
+        ri, ts, te = est.sampling(T(ro), T(rd), sigma_fn=sigma_fn, render_step_size=1e-2, early_stop_eps=eps, alpha_thre=thre)
+        o = orc.composite(o_ts, o_te, N(sig_all), None, packed_info=o_pi)
+        thre_eff = min(thre, 0.3) if thre > 0 else 0.0
+        keep = o["trans"] >= eps
+        if thre_eff > 0:
+            keep &= o["alphas"] >= thre_eff
+        # samples whose T / alpha sit within float noise of a threshold may flip
+        border = (np.abs(o["trans"] - eps) < 2e-6) | ((thre_eff > 0) & (np.abs(o["alphas"] - thre_eff) < 2e-6))
+        got = np.zeros(len(o_ri), bool)
+        # map the kept samples back to positions through (ray, t_start), which is unique
+        key_all = {(int(r), float(t)): i for i, (r, t) in enumerate(zip(o_ri, o_ts))}
+        idx = np.array([key_all[(int(r), float(t))] for r, t in zip(N(ri), N(ts))], dtype=np.int64)
+        got[idx] = True
+        assert (got != keep)[~border].sum() == 0
+        assert (np.diff(idx) > 0).all()                                   # order preserved, grouped by ray
+        np.testing.assert_array_equal(N(te), o_te[idx])
+        pk = N(nfa.pack_info(ri, R))
+        np.testing.assert_array_equal(pk[:, 1], np.bincount(N(ri), minlength=R))
+        np.testing.assert_array_equal(pk[:, 0], np.cumsum(pk[:, 1]) - pk[:, 1])
+    assert calls and all(c == len(o_ri) for c in calls)
+    # alpha_fn route
+    al_all = (0.5 * torch.rand(len(o_ri), generator=g)).to(dev)
+    ri, ts, te = est.sampling(T(ro), T(rd), alpha_fn=lambda a, b, c: al_all, render_step_size=1e-2, early_stop_eps=1e-2)
+    _, oT = orc.render_weight_from_alpha(N(al_all), packed_info=o_pi)
+    keep = oT >= 1e-2
+    assert abs(int(keep.sum()) - ri.numel()) <= 3 and ri.numel() < len(o_ri)
