@@ -28,7 +28,7 @@ extern "C" {
 #define NFA_ERR_ARG (-1)         /* null pointer / negative size / inconsistent sizes */
 #define NFA_ERR_UNSUPPORTED (-2) /* valid request outside what this build implements */
 
-#define NFA_ABI_VERSION 6
+#define NFA_ABI_VERSION 7
 
 typedef void* nfa_stream_t; /* cudaStream_t */
 
@@ -235,6 +235,42 @@ int32_t nfa_visibility_compact(int32_t n_rays, int64_t n_samples, const int64_t*
                                int32_t from_alpha, float early_stop_eps, float alpha_thre, void* workspace,
                                int64_t* new_packed_info, int64_t* out_ray_indices, float* out_t_starts,
                                float* out_t_ends, int64_t* total_dev, int64_t* total_host, nfa_stream_t stream);
+
+/* ----------------------------------------------------------------------- */
+/* PDF: importance sampling and per-ray searchsorted                        */
+/* ----------------------------------------------------------------------- */
+
+/* replaces: importance_sampling(RaySegmentsSpec, cdfs, n_intervals_per_ray [int | Tensor], stratified)
+ *   -- nerfacc.cpp:97-112, pdf.cu:293-426 (kernels :97-243).  Resamples every ray's piecewise-linear CDF
+ *   (edges `vals`, values `cdfs`) to n sample centres and the n+1 edges between them, in one launch.
+ *   input:  batched (in_packed_info NULL, in_edges per ray) or flattened (in_packed_info [n_rays,2] =
+ *           (start, count); max_in_edges >= every count, used to size shared memory);
+ *   output: batched (out_packed_info NULL): sample_vals [n_rays, n_out], iv_vals [n_rays, n_out+1];
+ *           flattened: out_packed_info / iv_packed_info [n_rays,2] give every ray's slice of the samples
+ *           and of the edges (count+1 edges for count > 0, else 0), max_out >= every sample count;
+ *           sample_ray_indices (optional), iv_ray_indices, iv_left, iv_right are then filled too.
+ *   stratified: one jitter per ray = first cuRAND Philox4x32-10 uniform of (seed, subsequence = ray,
+ *           offset) -- pdf.cu:139-145 with the (seed, offset) pair of torch's CUDA generator.
+ *   t_starts / t_ends (optional, batched output): the edges mapped s -> t as PropNetEstimator does
+ *           (estimators/prop_net.py:215-229): t = s*s_max + (1-s)*s_min, or its reciprocal when `lindisp`
+ *           (then s_min = 1/near, s_max = 1/far). */
+int32_t nfa_importance_sampling(int32_t n_rays, const float* vals, const float* cdfs, const int64_t* in_packed_info,
+                                int64_t in_edges, int64_t max_in_edges, const int64_t* out_packed_info,
+                                const int64_t* iv_packed_info, int64_t n_out, int64_t max_out, int32_t stratified,
+                                uint64_t seed, uint64_t offset, float* sample_vals, int64_t* sample_ray_indices,
+                                float* iv_vals, int64_t* iv_ray_indices, uint8_t* iv_left, uint8_t* iv_right,
+                                float* t_starts, float* t_ends, float s_min, float s_max, int32_t lindisp,
+                                nfa_stream_t stream);
+
+/* replaces: searchsorted(query RaySegmentsSpec, key RaySegmentsSpec) -> (ids_left, ids_right)
+ *   -- nerfacc.cpp:113-116, pdf.cu:429-456 (kernel :247-287).  For every query value the pair of key edges of
+ *   the same ray with key[left] <= q < key[right], clipped to the ray's edge range.  Batched operands pass a
+ *   NULL packed_info and their per-ray edge count; a batched query gets positions relative to its ray's keys,
+ *   a flattened one absolute positions.  query_ray_indices is optional (else found from query_packed_info). */
+int32_t nfa_searchsorted(int64_t n_query, const float* query_vals, const int64_t* query_packed_info,
+                         const int64_t* query_ray_indices, int32_t n_rays, int64_t query_edges,
+                         const float* key_vals, const int64_t* key_packed_info, int64_t key_edges,
+                         int64_t* ids_left, int64_t* ids_right, nfa_stream_t stream);
 
 #ifdef __cplusplus
 }

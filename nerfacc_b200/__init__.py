@@ -6,8 +6,10 @@ package through the alias package at the repository root.
 """
 from .data_specs import RayIntervals, RaySamples
 from .estimators.occ_grid import OccGridEstimator
+from .estimators.prop_net import PropNetEstimator
 from .grid import ray_aabb_intersect, traverse_grids
 from .pack import pack_info
+from .pdf import importance_sampling, searchsorted
 from .scan import exclusive_prod, exclusive_sum, inclusive_prod, inclusive_sum
 from .version import __version__
 from .volrend import (
@@ -43,4 +45,7 @@ __all__ = [
     "ray_aabb_intersect",
     "traverse_grids",
     "OccGridEstimator",
+    "PropNetEstimator",
+    "importance_sampling",
+    "searchsorted",
 ]

@@ -52,11 +52,16 @@ SIGNATURES = {
     "nfa_visibility_workspace_bytes": (_c_i64, [_c_i32, _c_i64]),
     "nfa_visibility_compact": (_c_i32, [_c_i32, _c_i64, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_f32, _c_f32]
                                + [_c_ptr] * 8),
+    "nfa_importance_sampling": (_c_i32, [_c_i32, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_i64, _c_ptr, _c_ptr, _c_i64, _c_i64,
+                                         _c_i32, C.c_uint64, C.c_uint64] + [_c_ptr] * 8 + [_c_f32, _c_f32, _c_i32,
+                                                                                          _c_ptr]),
+    "nfa_searchsorted": (_c_i32, [_c_i64, _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_i64, _c_ptr, _c_ptr, _c_i64, _c_ptr,
+                                  _c_ptr, _c_ptr]),
     "nfa_pack_info_workspace_bytes": (_c_i64, [_c_i32]),
     "nfa_pack_info": (_c_i32, [_c_i64, _c_ptr, _c_i32, _c_ptr, _c_ptr, _c_ptr]),
 }
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 _lib = None
 launches = 0  # number of native kernel-launching calls made through this module (bench.py reports it)

@@ -1,0 +1,260 @@
+// pdf.cu -- importance (inverse-transform) sampling along rays and per-ray searchsorted.
+//
+// replaces (paths relative to /root/reference):
+//   nerfacc/cuda/csrc/pdf.cu:97-166   importance_sampling_kernel   (one thread per output sample)
+//   nerfacc/cuda/csrc/pdf.cu:168-243  compute_intervels_kernel     (second launch over the samples)
+//   nerfacc/cuda/csrc/pdf.cu:247-287  searchsorted_kernel
+//   nerfacc/cuda/csrc/pdf.cu:293-456  host wrappers (both importance_sampling overloads, searchsorted)
+//
+// One CTA resamples one ray: its CDF and edge positions are staged in shared memory once, every
+// thread inverts the CDF for its samples with the bound search running out of shared memory, the
+// sample centres stay in shared memory, and the same CTA then writes the edges between neighbouring
+// centres -- one launch and one pass over the inputs instead of two launches whose threads each
+// binary-search global memory.  Optionally the same launch also maps the edges from the normalised
+// axis to ray distance (t_starts / t_ends of the proposal estimator), which otherwise costs six
+// elementwise ATen launches per proposal level.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/nerfacc_b200.h"
+#include "pdf.cuh"
+
+namespace nfa {
+
+constexpr int kIsThreads = 128;
+constexpr int kSearchThreads = 256;
+constexpr int64_t kIsSmemFloats = 50 * 1024;  // 200 KB of the 227 KB a CTA may opt in to
+
+struct IsParams {
+    int32_t n_rays;
+    const float* vals;
+    const float* cdfs;
+    const int64_t* in_packed;   // null: batched input, in_edges per ray
+    int64_t in_edges;
+    const int64_t* out_packed;  // null: batched output, n_out samples per ray; else samples' (start, count)
+    const int64_t* iv_packed;   // intervals' (start, count) when out_packed is given
+    int64_t n_out;
+    int32_t stratified;
+    uint64_t seed, offset;
+    float* sample_vals;
+    int64_t* sample_ray;
+    float* iv_vals;
+    int64_t* iv_ray;
+    uint8_t* iv_left;
+    uint8_t* iv_right;
+    // optional s -> t mapping of the edges (batched output only)
+    float* t_starts;
+    float* t_ends;
+    float s_min, s_max;
+    int32_t lindisp;
+};
+
+template <bool kStage>
+__global__ void __launch_bounds__(kIsThreads) importance_sampling_kernel(IsParams p)
+{
+    extern __shared__ float smem[];
+    for (int32_t ray = blockIdx.x; ray < p.n_rays; ray += gridDim.x) {
+        int64_t base, n_in;
+        if (p.in_packed) {
+            base = p.in_packed[2 * (int64_t)ray];
+            n_in = p.in_packed[2 * (int64_t)ray + 1];
+        } else {
+            base = (int64_t)ray * p.in_edges;
+            n_in = p.in_edges;
+        }
+        int64_t n, s_base, e_base;
+        if (p.out_packed) {
+            s_base = p.out_packed[2 * (int64_t)ray];
+            n = p.out_packed[2 * (int64_t)ray + 1];
+            e_base = p.iv_packed[2 * (int64_t)ray];
+        } else {
+            n = p.n_out;
+            s_base = (int64_t)ray * n;
+            e_base = (int64_t)ray * (n + 1);
+        }
+        if (n <= 0) continue;
+
+        const float* cdf = p.cdfs + base;
+        const float* val = p.vals + base;
+        float* ts = p.sample_vals + s_base;
+        if (kStage) {
+            float* s_cdf = smem;
+            float* s_val = smem + n_in;
+            for (int64_t i = threadIdx.x; i < n_in; i += kIsThreads) {
+                s_cdf[i] = __ldg(cdf + i);
+                s_val[i] = __ldg(val + i);
+            }
+            cdf = s_cdf;
+            val = s_val;
+            ts = smem + 2 * n_in;
+            __syncthreads();
+        }
+
+        const float quiet_nan = __int_as_float(0x7fc00000);
+        const float t_min = n_in > 0 ? val[0] : quiet_nan;
+        const float t_max = n_in > 0 ? val[n_in - 1] : quiet_nan;
+        const float u_floor = n_in > 0 ? cdf[0] : quiet_nan;
+        const float u_ceil = n_in > 0 ? cdf[n_in - 1] : quiet_nan;
+        const float u_step = f_div(f_sub(u_ceil, u_floor), (float)n);
+        const float bias = p.stratified ? philox_uniform(p.seed, (uint64_t)(int64_t)ray, p.offset) : 0.5f;
+
+        for (int64_t sid = threadIdx.x; sid < n; sid += kIsThreads) {
+            const float t = n_in > 0 ? is_invert(cdf, val, 0, n_in - 1, is_u(u_floor, u_step, sid, bias)) : quiet_nan;
+            ts[sid] = t;
+            if (kStage) p.sample_vals[s_base + sid] = t;
+            if (p.sample_ray) p.sample_ray[s_base + sid] = ray;
+        }
+        __syncthreads();  // centres visible to the whole CTA (shared, or this CTA's own global writes)
+
+        for (int64_t k = threadIdx.x; k <= n; k += kIsThreads) {
+            const float e = is_edge(ts, n, k, t_min, t_max);
+            p.iv_vals[e_base + k] = e;
+            if (p.out_packed) {
+                p.iv_ray[e_base + k] = ray;
+                p.iv_left[e_base + k] = k < n;
+                p.iv_right[e_base + k] = k > 0;
+            } else if (p.t_starts) {
+                const float t = stot(e, p.s_min, p.s_max, p.lindisp != 0);
+                if (k < n) p.t_starts[s_base + k] = t;
+                if (k > 0) p.t_ends[s_base + k - 1] = t;
+            }
+        }
+        if (kStage) __syncthreads();  // before the next ray overwrites the staging area
+    }
+}
+
+struct SearchParams {
+    int64_t n_query;
+    const float* q_vals;
+    const int64_t* q_packed;  // null: batched query, q_edges per ray
+    const int64_t* q_ray;     // optional ray id per query item (flattened query)
+    int32_t n_rays;
+    int64_t q_edges;
+    const float* k_vals;
+    const int64_t* k_packed;  // null: batched key, k_edges per ray
+    int64_t k_edges;
+    int64_t* ids_left;
+    int64_t* ids_right;
+};
+
+__global__ void __launch_bounds__(kSearchThreads) searchsorted_kernel(SearchParams p)
+{
+    for (int64_t i = (int64_t)blockIdx.x * kSearchThreads + threadIdx.x; i < p.n_query;
+         i += (int64_t)gridDim.x * kSearchThreads) {
+        int64_t ray;
+        if (!p.q_packed) ray = i / p.q_edges;
+        else if (p.q_ray) ray = p.q_ray[i];
+        else ray = chunk_upper_bound(p.q_packed, p.n_rays, i) - 1;
+        int64_t base, last;
+        if (p.k_packed) {
+            base = p.k_packed[2 * ray];
+            last = base + p.k_packed[2 * ray + 1] - 1;
+        } else {
+            base = ray * p.k_edges;
+            last = base + p.k_edges - 1;
+        }
+        const int64_t pos = upper_bound_f(p.k_vals, base, last, __ldg(p.q_vals + i));
+        int64_t l = pos - 1 < last ? pos - 1 : last;
+        if (l < base) l = base;
+        int64_t r = pos < last ? pos : last;
+        if (r < base) r = base;
+        const int64_t rel = p.q_packed ? 0 : base;  // batched queries get per-ray positions
+        p.ids_left[i] = l - rel;
+        p.ids_right[i] = r - rel;
+    }
+}
+
+}  // namespace nfa
+
+using namespace nfa;
+
+extern "C" {
+
+int32_t nfa_importance_sampling(int32_t n_rays, const float* vals, const float* cdfs, const int64_t* in_packed_info,
+                                int64_t in_edges, int64_t max_in_edges, const int64_t* out_packed_info,
+                                const int64_t* iv_packed_info, int64_t n_out, int64_t max_out, int32_t stratified,
+                                uint64_t seed, uint64_t offset, float* sample_vals, int64_t* sample_ray_indices,
+                                float* iv_vals, int64_t* iv_ray_indices, uint8_t* iv_left, uint8_t* iv_right,
+                                float* t_starts, float* t_ends, float s_min, float s_max, int32_t lindisp,
+                                nfa_stream_t stream)
+{
+    if (n_rays < 0 || in_edges < 0 || n_out < 0 || max_in_edges < 0 || max_out < 0) return NFA_ERR_ARG;
+    if (n_rays == 0) return NFA_OK;
+    if (!sample_vals || !iv_vals) return NFA_ERR_ARG;
+    if (max_in_edges > 0 && (!vals || !cdfs)) return NFA_ERR_ARG;
+    if (out_packed_info && (!iv_packed_info || !iv_ray_indices || !iv_left || !iv_right)) return NFA_ERR_ARG;
+    if ((t_starts != nullptr) != (t_ends != nullptr)) return NFA_ERR_ARG;
+    if (t_starts && out_packed_info) return NFA_ERR_UNSUPPORTED;
+    if (!out_packed_info && n_out == 0) return NFA_OK;
+
+    IsParams p;
+    p.n_rays = n_rays;
+    p.vals = vals;
+    p.cdfs = cdfs;
+    p.in_packed = in_packed_info;
+    p.in_edges = in_edges;
+    p.out_packed = out_packed_info;
+    p.iv_packed = iv_packed_info;
+    p.n_out = n_out;
+    p.stratified = stratified;
+    p.seed = seed;
+    p.offset = offset;
+    p.sample_vals = sample_vals;
+    p.sample_ray = sample_ray_indices;
+    p.iv_vals = iv_vals;
+    p.iv_ray = iv_ray_indices;
+    p.iv_left = iv_left;
+    p.iv_right = iv_right;
+    p.t_starts = t_starts;
+    p.t_ends = t_ends;
+    p.s_min = s_min;
+    p.s_max = s_max;
+    p.lindisp = lindisp;
+
+    const int64_t in_cap = in_packed_info ? max_in_edges : in_edges;
+    const int64_t out_cap = out_packed_info ? max_out : n_out;
+    const int64_t floats = 2 * in_cap + out_cap;
+    const unsigned grid = (unsigned)(n_rays < (1 << 20) ? n_rays : (1 << 20));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (floats <= kIsSmemFloats) {
+        const size_t bytes = (size_t)floats * sizeof(float);
+        if (bytes > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(importance_sampling_kernel<true>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+            if (e != cudaSuccess) return (int32_t)e;
+        }
+        importance_sampling_kernel<true><<<grid, kIsThreads, bytes, s>>>(p);
+    } else {
+        importance_sampling_kernel<false><<<grid, kIsThreads, 0, s>>>(p);
+    }
+    return (int32_t)cudaGetLastError();
+}
+
+int32_t nfa_searchsorted(int64_t n_query, const float* query_vals, const int64_t* query_packed_info,
+                         const int64_t* query_ray_indices, int32_t n_rays, int64_t query_edges,
+                         const float* key_vals, const int64_t* key_packed_info, int64_t key_edges,
+                         int64_t* ids_left, int64_t* ids_right, nfa_stream_t stream)
+{
+    if (n_query < 0 || n_rays < 0 || query_edges < 0 || key_edges < 0) return NFA_ERR_ARG;
+    if (n_query == 0) return NFA_OK;
+    if (!query_vals || !key_vals || !ids_left || !ids_right) return NFA_ERR_ARG;
+    if (!query_packed_info && query_edges == 0) return NFA_ERR_ARG;
+    SearchParams p;
+    p.n_query = n_query;
+    p.q_vals = query_vals;
+    p.q_packed = query_packed_info;
+    p.q_ray = query_ray_indices;
+    p.n_rays = n_rays;
+    p.q_edges = query_edges;
+    p.k_vals = key_vals;
+    p.k_packed = key_packed_info;
+    p.k_edges = key_edges;
+    p.ids_left = ids_left;
+    p.ids_right = ids_right;
+    const int64_t blocks = (n_query + kSearchThreads - 1) / kSearchThreads;
+    const unsigned grid = (unsigned)(blocks < 148 * 64 ? blocks : 148 * 64);
+    searchsorted_kernel<<<grid, kSearchThreads, 0, (cudaStream_t)stream>>>(p);
+    return (int32_t)cudaGetLastError();
+}
+
+}  // extern "C"

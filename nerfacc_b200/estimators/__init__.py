@@ -1,0 +1,1 @@
+"""Sampling estimators (reference nerfacc/estimators/)."""

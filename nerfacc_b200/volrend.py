@@ -132,6 +132,25 @@ def _packed_mode(x: Tensor, packed_info: Optional[Tensor], ray_indices: Optional
     return packed_info is not None or ray_indices is not None
 
 
+_uniform_segments = {}
+
+
+def _batched_segments(x: Tensor, prefix_trans: Optional[Tensor]) -> Optional[Tensor]:
+    """Batched (n_rays, S) CUDA input -> the (n_rays, 2) segments that address it as a packed array, so the
+    batched flavour (the proposal estimator's) runs the same fused kernels.  None = keep the ATen formulation."""
+    if not x.is_cuda or x.dim() != 2 or x.numel() == 0 or x.dtype != torch.float32 or prefix_trans is not None:
+        return None
+    key = (x.shape[0], x.shape[1], x.device)
+    seg = _uniform_segments.get(key)
+    if seg is None:
+        if len(_uniform_segments) > 16:
+            _uniform_segments.clear()
+        starts = torch.arange(x.shape[0], device=x.device, dtype=torch.int64) * x.shape[1]
+        seg = torch.stack([starts, torch.full_like(starts, x.shape[1])], -1).contiguous()
+        _uniform_segments[key] = seg
+    return seg
+
+
 def _composite_packed(dens: Tensor, rgbs: Optional[Tensor], t_starts: Optional[Tensor], t_ends: Optional[Tensor],
                       packed_info: Optional[Tensor], ray_indices: Optional[Tensor], n_rays: Optional[int],
                       prefix_trans: Optional[Tensor], bkgd: Optional[Tensor], from_alpha: bool,
@@ -200,7 +219,25 @@ def rendering(
             extras["sigmas"] = dens
         return colors, opacities, depths, extras
 
-    # batched (or CPU) inputs: the reference's own op sequence
+    seg = _batched_segments(dens, None) if ray_indices is None and rgbs.dtype == torch.float32 else None
+    if seg is not None and t_starts.shape == dens.shape == t_ends.shape:
+        # batched (n_rays, S) on the GPU: the same fused kernels, addressed through uniform segments
+        bk = render_bkgd
+        fuse_bkgd = bk is not None and not bk.requires_grad and bk.numel() == 3 and bk.is_cuda
+        weights, trans, alphas, colors, opacities, depths = _composite_packed(
+            dens.reshape(-1), rgbs.reshape(-1, 3), t_starts.reshape(-1), t_ends.reshape(-1), seg, None, None, None,
+            bk.reshape(3).to(torch.float32) if fuse_bkgd else None,
+            from_alpha=not use_sigma, expected_depths=expected_depths, want_rays=True)
+        if bk is not None and not fuse_bkgd:
+            colors = colors + bk * (1.0 - opacities)
+        weights, trans = weights.view_as(dens), trans.view_as(dens)
+        extras = {"weights": weights, "alphas": dens if not use_sigma else alphas.view_as(dens), "trans": trans,
+                  "rgbs": rgbs}
+        if use_sigma:
+            extras["sigmas"] = dens
+        return colors, opacities, depths, extras
+
+    # batched CPU inputs: the reference's own op sequence
     if use_sigma:
         weights, trans, alphas = render_weight_from_density(t_starts, t_ends, dens, ray_indices=ray_indices,
                                                             n_rays=n_rays)
@@ -231,6 +268,9 @@ def render_transmittance_from_alpha(
         _, trans, _, _, _, _ = _composite_packed(alphas, None, None, None, packed_info, ray_indices, n_rays,
                                                  prefix_trans, None, True, False, False)
         return trans
+    seg = _batched_segments(alphas, prefix_trans)
+    if seg is not None:
+        return render_transmittance_from_alpha(alphas.reshape(-1), packed_info=seg).view_as(alphas)
     trans = exclusive_prod(1 - alphas, packed_info=packed_info, indices=ray_indices)
     if prefix_trans is not None:
         trans = trans * prefix_trans
@@ -251,6 +291,11 @@ def render_transmittance_from_density(
         _, trans, alphas, _, _, _ = _composite_packed(sigmas, None, t_starts, t_ends, packed_info, ray_indices,
                                                       n_rays, prefix_trans, None, False, False, False)
         return trans, alphas
+    seg = _batched_segments(sigmas, prefix_trans)
+    if seg is not None and t_starts.shape == sigmas.shape == t_ends.shape:
+        trans, alphas = render_transmittance_from_density(t_starts.reshape(-1), t_ends.reshape(-1),
+                                                          sigmas.reshape(-1), packed_info=seg)
+        return trans.view_as(sigmas), alphas.view_as(sigmas)
     sigmas_dt = sigmas * (t_ends - t_starts)
     alphas = 1.0 - torch.exp(-sigmas_dt)
     trans = torch.exp(-exclusive_sum(sigmas_dt, packed_info=packed_info, indices=ray_indices))
@@ -271,6 +316,10 @@ def render_weight_from_alpha(
         weights, trans, _, _, _, _ = _composite_packed(alphas, None, None, None, packed_info, ray_indices, n_rays,
                                                        prefix_trans, None, True, False, False)
         return weights, trans
+    seg = _batched_segments(alphas, prefix_trans)
+    if seg is not None:
+        weights, trans = render_weight_from_alpha(alphas.reshape(-1), packed_info=seg)
+        return weights.view_as(alphas), trans.view_as(alphas)
     trans = render_transmittance_from_alpha(alphas, packed_info, ray_indices, n_rays, prefix_trans)
     return trans * alphas, trans
 
@@ -290,6 +339,11 @@ def render_weight_from_density(
                                                             ray_indices, n_rays, prefix_trans, None, False, False,
                                                             False)
         return weights, trans, alphas
+    seg = _batched_segments(sigmas, prefix_trans)
+    if seg is not None and t_starts.shape == sigmas.shape == t_ends.shape:
+        weights, trans, alphas = render_weight_from_density(t_starts.reshape(-1), t_ends.reshape(-1),
+                                                            sigmas.reshape(-1), packed_info=seg)
+        return weights.view_as(sigmas), trans.view_as(sigmas), alphas.view_as(sigmas)
     trans, alphas = render_transmittance_from_density(t_starts, t_ends, sigmas, packed_info, ray_indices, n_rays,
                                                       prefix_trans)
     return trans * alphas, trans, alphas

@@ -536,6 +536,15 @@ ORC_API void orc_accumulate(
             out[ray_indices[i] * dim + c] += values ? weights[i] * values[i * dim + c] : weights[i];
 }
 
+ORC_API void orc_set_num_threads(int32_t n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 ORC_API int32_t orc_num_threads(void)
 {
 #ifdef _OPENMP
@@ -543,4 +552,152 @@ ORC_API int32_t orc_num_threads(void)
 #else
     return 1;
 #endif
+}
+
+/* ------------------------------------------------------------------ */
+/* PDF: importance sampling, searchsorted                              */
+/* ------------------------------------------------------------------ */
+
+/* nerfacc/cuda/csrc/pdf.cu:43-63 upper_bound (data_sort == nullptr) */
+static int64_t pdf_upper_bound(const float *data, int64_t start, int64_t end, float val)
+{
+    while (start < end) {
+        const int64_t mid = start + ((end - start) >> 1);
+        const float mid_val = data[mid];
+        if (!(mid_val > val)) start = mid + 1;
+        else end = mid;
+    }
+    return start;
+}
+
+/* nerfacc/cuda/csrc/pdf.cu:65-80 binary_search_chunk_id */
+static int32_t pdf_chunk_id(int64_t item, int32_t n_chunks, const int64_t *starts /* stride 2 */)
+{
+    int32_t start = 0, end = n_chunks;
+    while (start < end) {
+        const int32_t mid = start + ((end - start) >> 1);
+        if (!(starts[2 * (int64_t)mid] > item)) start = mid + 1;
+        else end = mid;
+    }
+    return start;
+}
+
+static inline int64_t clamp_i64(int64_t v, int64_t lo, int64_t hi) { int64_t m = v < hi ? v : hi; return m > lo ? m : lo; }
+
+/* cuRAND Philox4x32-10 (curand_philox4x32_x.h of the CUDA toolkit the reference links; algorithm of
+ * Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11).
+ * curand_init(seed, subsequence, offset): key = (seed lo, seed hi); counter = 0; the subsequence is added
+ * to the upper 64 counter bits, offset / 4 to the lower 64, offset % 4 selects the output word.
+ * curand_uniform(): x * 2^-32 + 2^-33 as one FMA (SASS of pdf.cu:144). */
+ORC_API uint32_t orc_philox_word(uint64_t seed, uint64_t subsequence, uint64_t offset)
+{
+    uint32_t ctr[4] = {(uint32_t)(offset >> 2), (uint32_t)(offset >> 34), (uint32_t)subsequence, (uint32_t)(subsequence >> 32)};
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    for (int round = 0; round < 10; ++round) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * ctr[0];
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * ctr[2];
+        const uint32_t out[4] = {(uint32_t)(p1 >> 32) ^ ctr[1] ^ key[0], (uint32_t)p1,
+                                 (uint32_t)(p0 >> 32) ^ ctr[3] ^ key[1], (uint32_t)p0};
+        memcpy(ctr, out, sizeof(out));
+        key[0] += 0x9E3779B9u;
+        key[1] += 0xBB67AE85u;
+    }
+    return ctr[offset & 3u];
+}
+
+ORC_API float orc_philox_uniform(uint64_t seed, uint64_t subsequence, uint64_t offset)
+{
+    return fmaf((float)orc_philox_word(seed, subsequence, offset), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+}
+
+/* nerfacc/cuda/csrc/pdf.cu:97-166 importance_sampling_kernel followed by :168-243 compute_intervels_kernel,
+ * one loop iteration per device thread.  in_packed / out_packed NULL = batched.  For flattened output the
+ * edges' (start, count) come in iv_packed (count = n + 1 for n > 0, else 0; pdf.cu:341-344).
+ * A ray resampled to a single sample reads samples.vals[tid + 1] in the reference ("FIXME: out of bounds?",
+ * pdf.cu:208) and never writes its right edge: undefined there, [t_min, t_max] here. */
+ORC_API void orc_importance_sampling(
+    int32_t n_rays, const float *vals, const float *cdfs, const int64_t *in_packed, int64_t in_edges,
+    const int64_t *out_packed, const int64_t *iv_packed, int64_t n_out, int32_t stratified, uint64_t seed,
+    uint64_t offset, float *sample_vals, int64_t *sample_ray, float *iv_vals, int64_t *iv_ray, uint8_t *iv_left,
+    uint8_t *iv_right)
+{
+    for (int32_t ray_id = 0; ray_id < n_rays; ++ray_id) {
+        const int64_t n_samples = out_packed ? out_packed[2 * (int64_t)ray_id + 1] : n_out;
+        const int64_t sbase = out_packed ? out_packed[2 * (int64_t)ray_id] : (int64_t)ray_id * n_out;
+        const int64_t base = in_packed ? in_packed[2 * (int64_t)ray_id] : (int64_t)ray_id * in_edges;
+        const int64_t last = base + (in_packed ? in_packed[2 * (int64_t)ray_id + 1] : in_edges) - 1;
+        const int64_t base_out = out_packed ? iv_packed[2 * (int64_t)ray_id] : (int64_t)ray_id * (n_out + 1);
+        if (n_samples <= 0) continue;
+        /* --- samples --- */
+        for (int64_t sid = 0; sid < n_samples; ++sid) {
+            const int64_t tid = sbase + sid;
+            if (out_packed && sample_ray) sample_ray[tid] = ray_id;
+            const float u_floor = cdfs[base];
+            const float u_ceil = cdfs[last];
+            const float u_step = (u_ceil - u_floor) / (float)n_samples;
+            float bias = 0.5f;
+            if (stratified) bias = orc_philox_uniform(seed, (uint64_t)ray_id, offset);
+            const float u = fmaf((float)sid + bias, u_step, u_floor);
+            const int64_t p = pdf_upper_bound(cdfs, base, last, u);
+            const int64_t p0 = clamp_i64(p - 1, base, last);
+            const int64_t p1 = clamp_i64(p, base, last);
+            const float u_lower = cdfs[p0], u_upper = cdfs[p1];
+            const float t_lower = vals[p0], t_upper = vals[p1];
+            float t;
+            if (u_upper - u_lower < 1e-10f) {
+                t = (t_lower + t_upper) * 0.5f;
+            } else {
+                const float scaling = (t_upper - t_lower) / (u_upper - u_lower);
+                t = fmaf(u - u_lower, scaling, t_lower);
+            }
+            sample_vals[tid] = t;
+        }
+        /* --- edges --- */
+        const float t_min = vals[base], t_max = vals[last];
+        if (n_samples == 1) {
+            iv_vals[base_out] = t_min;
+            iv_vals[base_out + 1] = t_max;
+        }
+        for (int64_t sid = 0; sid < n_samples && n_samples > 1; ++sid) {
+            const int64_t tid = sbase + sid;
+            if (sid == 0) {
+                const float t = sample_vals[tid], t_next = sample_vals[tid + 1];
+                const float half_width = (t_next - t) * 0.5f;
+                iv_vals[base_out] = fmaxf(t - half_width, t_min);
+            } else {
+                const float t = sample_vals[tid], t_prev = sample_vals[tid - 1];
+                iv_vals[base_out + sid] = (t + t_prev) * 0.5f;
+                if (sid == n_samples - 1) {
+                    const float half_width = (t - t_prev) * 0.5f;
+                    iv_vals[base_out + sid + 1] = fminf(t + half_width, t_max);
+                }
+            }
+        }
+        if (out_packed)
+            for (int64_t k = 0; k <= n_samples; ++k) {
+                iv_ray[base_out + k] = ray_id;
+                iv_left[base_out + k] = k < n_samples;
+                iv_right[base_out + k] = k > 0;
+            }
+    }
+}
+
+/* nerfacc/cuda/csrc/pdf.cu:247-287 searchsorted_kernel */
+ORC_API void orc_searchsorted(
+    int64_t n_query, const float *q_vals, const int64_t *q_packed, const int64_t *q_ray, int32_t n_rays,
+    int64_t q_edges, const float *k_vals, const int64_t *k_packed, int64_t k_edges, int64_t *ids_left,
+    int64_t *ids_right)
+{
+    for (int64_t tid = 0; tid < n_query; ++tid) {
+        int64_t ray_id;
+        if (!q_packed) ray_id = tid / q_edges;
+        else if (!q_ray) ray_id = pdf_chunk_id(tid, n_rays, q_packed) - 1;
+        else ray_id = q_ray[tid];
+        const int64_t base = k_packed ? k_packed[2 * ray_id] : ray_id * k_edges;
+        const int64_t last = base + (k_packed ? k_packed[2 * ray_id + 1] : k_edges) - 1;
+        const int64_t p = pdf_upper_bound(k_vals, base, last, q_vals[tid]);
+        const int64_t rel = q_packed ? 0 : base;
+        ids_left[tid] = clamp_i64(p - 1, base, last) - rel;
+        ids_right[tid] = clamp_i64(p, base, last) - rel;
+    }
 }

@@ -46,6 +46,18 @@ def num_threads() -> int:
     return int(lib().orc_num_threads())
 
 
+def set_num_threads(n: int) -> None:
+    """Override OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    lib().orc_set_num_threads(int(n))
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 _F = C.POINTER(C.c_float)
 _D = C.POINTER(C.c_double)
 _I64 = C.POINTER(C.c_int64)
@@ -367,3 +379,73 @@ def accumulate_along_rays(weights, values=None, ray_indices=None, n_rays=None):
     lib().orc_accumulate(C.c_int32(n_rays), C.c_int64(weights.size), _p(ray_indices, _I64), _p(weights, _F),
                          _p(values, _F), C.c_int32(dim), _p(out, _F))
     return out
+
+
+# --------------------------------------------------------------------------
+# pdf.py
+# --------------------------------------------------------------------------
+
+_U8P = C.POINTER(C.c_uint8)
+
+
+def philox_uniform(seed: int, subsequence: int, offset: int) -> float:
+    """First curand_uniform() after curand_init(seed, subsequence, offset) -- pdf.cu:139-145."""
+    fn = lib().orc_philox_uniform
+    fn.restype = C.c_float
+    return float(fn(C.c_uint64(seed), C.c_uint64(subsequence), C.c_uint64(offset)))
+
+
+def importance_sampling(vals, cdfs, n_intervals_per_ray, packed_info=None, stratified=False, seed=0, offset=0):
+    """reference: nerfacc/pdf.py:64-131 -> pdf.cu:293-426.
+
+    ``vals`` / ``cdfs``: batched [n_rays, E] (packed_info None) or flattened [all_edges] with ``packed_info``.
+    ``n_intervals_per_ray``: int -> batched outputs ([n_rays, n+1] edges, [n_rays, n] centres);
+    array [n_rays] -> flattened outputs, returned as two dicts (vals, packed_info, ray_indices, is_left, is_right).
+    """
+    vals, cdfs = _f32(vals), _f32(cdfs)
+    if packed_info is None:
+        assert vals.ndim >= 2
+        n_rays, in_edges = int(np.prod(vals.shape[:-1])), vals.shape[-1]
+        lead = vals.shape[:-1]
+        pin = None
+    else:
+        pin = _i64(packed_info)
+        n_rays, in_edges, lead = pin.shape[0], 0, (pin.shape[0],)
+    fn = lib().orc_importance_sampling
+    if np.ndim(n_intervals_per_ray) == 0:
+        n = int(n_intervals_per_ray)
+        s_vals = np.zeros(lead + (n,), np.float32)
+        e_vals = np.zeros(lead + (n + 1,), np.float32)
+        fn(C.c_int32(n_rays), _p(vals, _F), _p(cdfs, _F), _p(pin, _I64), C.c_int64(in_edges), None, None,
+           C.c_int64(n), C.c_int32(bool(stratified)), C.c_uint64(seed), C.c_uint64(offset), _p(s_vals, _F), None,
+           _p(e_vals, _F), None, None, None)
+        return e_vals, s_vals
+    cnts = _i64(n_intervals_per_ray).reshape(-1)
+    assert cnts.size == n_rays
+    s_pack = np.stack([np.cumsum(cnts) - cnts, cnts], -1).astype(np.int64)
+    e_cnt = (cnts + 1) * (cnts > 0)
+    e_pack = np.stack([np.cumsum(e_cnt) - e_cnt, e_cnt], -1).astype(np.int64)
+    ns, ne = int(cnts.sum()), int(e_cnt.sum())
+    s_vals, s_ray = np.zeros(ns, np.float32), np.zeros(ns, np.int64)
+    e_vals, e_ray = np.zeros(ne, np.float32), np.zeros(ne, np.int64)
+    e_left, e_right = np.zeros(ne, np.uint8), np.zeros(ne, np.uint8)
+    fn(C.c_int32(n_rays), _p(vals, _F), _p(cdfs, _F), _p(pin, _I64), C.c_int64(in_edges), _p(s_pack, _I64),
+       _p(e_pack, _I64), C.c_int64(0), C.c_int32(bool(stratified)), C.c_uint64(seed), C.c_uint64(offset),
+       _p(s_vals, _F), _p(s_ray, _I64), _p(e_vals, _F), _p(e_ray, _I64), _p(e_left, _U8P), _p(e_right, _U8P))
+    return (dict(vals=e_vals, packed_info=e_pack, ray_indices=e_ray, is_left=e_left.astype(bool),
+                 is_right=e_right.astype(bool)),
+            dict(vals=s_vals, packed_info=s_pack, ray_indices=s_ray))
+
+
+def searchsorted(key_vals, query_vals, key_packed_info=None, query_packed_info=None, query_ray_indices=None):
+    """reference: nerfacc/pdf.py:12-61 -> pdf.cu:429-456.  Returns (ids_left, ids_right)."""
+    kv, qv = _f32(key_vals), _f32(query_vals)
+    kp = None if key_packed_info is None else _i64(key_packed_info)
+    qp = None if query_packed_info is None else _i64(query_packed_info)
+    qr = None if query_ray_indices is None else _i64(query_ray_indices)
+    n_rays = qp.shape[0] if qp is not None else int(np.prod(qv.shape[:-1]))
+    left, right = np.zeros(qv.shape, np.int64), np.zeros(qv.shape, np.int64)
+    lib().orc_searchsorted(C.c_int64(qv.size), _p(qv, _F), _p(qp, _I64), _p(qr, _I64), C.c_int32(n_rays),
+                           C.c_int64(qv.shape[-1] if qp is None else 0), _p(kv, _F), _p(kp, _I64),
+                           C.c_int64(kv.shape[-1] if kp is None else 0), _p(left, _I64), _p(right, _I64))
+    return left, right

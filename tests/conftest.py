@@ -44,7 +44,8 @@ def host_sim():
     d = os.path.join(ROOT, "tests", "host_sim")
     so = os.path.join(d, "libhost_sim.so")
     src = os.path.join(d, "host_sim.cpp")
-    hdrs = [os.path.join(ROOT, "nerfacc_b200", "csrc", h) for h in ("lattice.cuh", "march.cuh", "expand.cuh", "occ_pack.cuh", "nfa_math.cuh")]
+    hdrs = [os.path.join(ROOT, "nerfacc_b200", "csrc", h) for h in ("lattice.cuh", "march.cuh", "march_generic.cuh", "expand.cuh", "occ_pack.cuh", "nfa_math.cuh",
+                                                                     "pdf.cuh")]
     newest = max(os.path.getmtime(p) for p in [src] + hdrs)
     if not os.path.exists(so) or os.path.getmtime(so) < newest:
         subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
@@ -57,6 +58,8 @@ def host_sim():
     lib.sim_occ_words.restype = C.c_int64
     lib.sim_occ_coarse_words.restype = C.c_int64
     lib.sim_march.restype = C.c_int64
+    lib.sim_philox_uniform.restype = C.c_float
+    lib.sim_philox_uniform.argtypes = [C.c_uint64] * 3
     return lib
 
 

@@ -13,6 +13,7 @@
 #include "../../nerfacc_b200/csrc/occ_pack.cuh"
 #include "../../nerfacc_b200/csrc/expand.cuh"
 #include "../../nerfacc_b200/csrc/march_generic.cuh"
+#include "../../nerfacc_b200/csrc/pdf.cuh"
 
 using namespace nfa;
 
@@ -203,6 +204,73 @@ void sim_generic_pass(int32_t n_rays, const float* rays_o, const float* rays_d, 
         if (terminate) terminate[r] = term;
         iv_cnts[r] = out.n_edges;
         sm_cnts[r] = out.n_samples;
+    }
+}
+
+// ---- pdf.cuh: the per-ray body of importance_sampling_kernel (pdf.cu), threads serialised
+float sim_philox_uniform(uint64_t seed, uint64_t subsequence, uint64_t offset)
+{
+    return philox_uniform(seed, subsequence, offset);
+}
+
+void sim_importance_sampling(int32_t n_rays, const float* vals, const float* cdfs, const int64_t* in_packed,
+                             int64_t in_edges, const int64_t* out_packed, const int64_t* iv_packed, int64_t n_out,
+                             int32_t stratified, uint64_t seed, uint64_t offset, float* sample_vals,
+                             int64_t* sample_ray, float* iv_vals, int64_t* iv_ray, uint8_t* iv_left, uint8_t* iv_right,
+                             float* t_starts, float* t_ends, float s_min, float s_max, int32_t lindisp)
+{
+    for (int32_t ray = 0; ray < n_rays; ++ray) {
+        const int64_t base = in_packed ? in_packed[2 * (int64_t)ray] : (int64_t)ray * in_edges;
+        const int64_t n_in = in_packed ? in_packed[2 * (int64_t)ray + 1] : in_edges;
+        const int64_t n = out_packed ? out_packed[2 * (int64_t)ray + 1] : n_out;
+        const int64_t s_base = out_packed ? out_packed[2 * (int64_t)ray] : (int64_t)ray * n;
+        const int64_t e_base = out_packed ? iv_packed[2 * (int64_t)ray] : (int64_t)ray * (n + 1);
+        if (n <= 0 || n_in <= 0) continue;
+        const float* cdf = cdfs + base;
+        const float* val = vals + base;
+        float* ts = sample_vals + s_base;
+        const float u_floor = cdf[0], u_ceil = cdf[n_in - 1];
+        const float u_step = f_div(f_sub(u_ceil, u_floor), (float)n);
+        const float bias = stratified ? philox_uniform(seed, (uint64_t)(int64_t)ray, offset) : 0.5f;
+        for (int64_t sid = 0; sid < n; ++sid) {
+            ts[sid] = is_invert(cdf, val, 0, n_in - 1, is_u(u_floor, u_step, sid, bias));
+            if (sample_ray) sample_ray[s_base + sid] = ray;
+        }
+        for (int64_t k = 0; k <= n; ++k) {
+            const float e = is_edge(ts, n, k, val[0], val[n_in - 1]);
+            iv_vals[e_base + k] = e;
+            if (out_packed) {
+                iv_ray[e_base + k] = ray;
+                iv_left[e_base + k] = k < n;
+                iv_right[e_base + k] = k > 0;
+            } else if (t_starts) {
+                const float t = stot(e, s_min, s_max, lindisp != 0);
+                if (k < n) t_starts[s_base + k] = t;
+                if (k > 0) t_ends[s_base + k - 1] = t;
+            }
+        }
+    }
+}
+
+void sim_searchsorted(int64_t n_query, const float* q_vals, const int64_t* q_packed, const int64_t* q_ray,
+                      int32_t n_rays, int64_t q_edges, const float* k_vals, const int64_t* k_packed, int64_t k_edges,
+                      int64_t* ids_left, int64_t* ids_right)
+{
+    for (int64_t i = 0; i < n_query; ++i) {
+        int64_t ray;
+        if (!q_packed) ray = i / q_edges;
+        else if (q_ray) ray = q_ray[i];
+        else ray = chunk_upper_bound(q_packed, n_rays, i) - 1;
+        const int64_t base = k_packed ? k_packed[2 * ray] : ray * k_edges;
+        const int64_t last = base + (k_packed ? k_packed[2 * ray + 1] : k_edges) - 1;
+        const int64_t pos = upper_bound_f(k_vals, base, last, q_vals[i]);
+        int64_t l = pos - 1 < last ? pos - 1 : last;
+        if (l < base) l = base;
+        int64_t r = pos < last ? pos : last;
+        if (r < base) r = base;
+        const int64_t rel = q_packed ? 0 : base;
+        ids_left[i] = l - rel;
+        ids_right[i] = r - rel;
     }
 }
 
