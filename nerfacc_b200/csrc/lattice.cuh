@@ -53,6 +53,18 @@ struct LatPiece {
     bool stuck;      // dt < ulp(t)/2: the reference would never advance
 };
 
+// floor(a / b) for 0 <= a < 2^24, 1 <= b < 2^24.  On the device a round-toward-zero float division is
+// exact here (both operands are exact floats, and below 2^24 the float grid is at least as fine as the
+// integers, so RZ(a/b) lies in [floor(a/b), a/b]) and costs a third of the emulated integer division.
+NFA_HD uint32_t div_u24(uint32_t a, uint32_t b)
+{
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__fdiv_rz((float)a, (float)b);
+#else
+    return a / b;
+#endif
+}
+
 NFA_HD LatPiece lat_piece(const Lattice& L, float t)
 {
     LatPiece p;
@@ -90,7 +102,7 @@ NFA_HD LatPiece lat_piece(const Lattice& L, float t)
         }
     }
     p.inc = I;
-    p.jmax = (0xffffffu - M) / I;
+    p.jmax = div_u24(0xffffffu - M, I);
     p.regular = p.jmax > 0u;
     return p;
 }

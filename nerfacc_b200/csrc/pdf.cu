@@ -6,11 +6,11 @@
 //   nerfacc/cuda/csrc/pdf.cu:247-287  searchsorted_kernel
 //   nerfacc/cuda/csrc/pdf.cu:293-456  host wrappers (both importance_sampling overloads, searchsorted)
 //
-// One CTA resamples one ray: its CDF and edge positions are staged in shared memory once, every
-// thread inverts the CDF for its samples with the bound search running out of shared memory, the
-// sample centres stay in shared memory, and the same CTA then writes the edges between neighbouring
-// centres -- one launch and one pass over the inputs instead of two launches whose threads each
-// binary-search global memory.  Optionally the same launch also maps the edges from the normalised
+// A ray is resampled by one warp (short rays: the proposal-network shapes) or one CTA (long rays): its
+// CDF and edge positions are staged in shared memory once, every thread inverts the CDF for its samples
+// with the bound search running out of shared memory, the sample centres stay in shared memory, and the
+// same threads then write the edges between neighbouring centres -- one launch and one pass over the
+// inputs instead of two launches whose threads each binary-search global memory.  Optionally the same launch also maps the edges from the normalised
 // axis to ray distance (t_starts / t_ends of the proposal estimator), which otherwise costs six
 // elementwise ATen launches per proposal level.
 #include <cuda_runtime.h>
@@ -24,6 +24,7 @@ namespace nfa {
 constexpr int kIsThreads = 128;
 constexpr int kSearchThreads = 256;
 constexpr int64_t kIsSmemFloats = 50 * 1024;  // 200 KB of the 227 KB a CTA may opt in to
+constexpr int64_t kWarpRayFloats = 1024;       // rays whose tables fit 4 KB take the warp-per-ray kernel
 
 struct IsParams {
     int32_t n_rays;
@@ -49,78 +50,111 @@ struct IsParams {
     int32_t lindisp;
 };
 
+// One ray, resampled by `kLanes` cooperating threads (a whole CTA or one warp) whose rank is `tid`.
+// kStage: `stage` holds room for this ray's CDF, edge positions and sample centres.  Per-ray counts and
+// positions are 32-bit (a ray with 2^31 edges does not exist); only the array offsets are 64-bit.
+template <bool kStage, int kLanes, bool kCta, bool kStratified>
+NFA_D void resample_ray(const IsParams& p, int32_t ray, int tid, float* stage)
+{
+    int64_t base;
+    int32_t n_in;
+    if (p.in_packed) {
+        base = p.in_packed[2 * (int64_t)ray];
+        n_in = (int32_t)p.in_packed[2 * (int64_t)ray + 1];
+    } else {
+        base = (int64_t)ray * p.in_edges;
+        n_in = (int32_t)p.in_edges;
+    }
+    int64_t s_base, e_base;
+    int32_t n;
+    if (p.out_packed) {
+        s_base = p.out_packed[2 * (int64_t)ray];
+        n = (int32_t)p.out_packed[2 * (int64_t)ray + 1];
+        e_base = p.iv_packed[2 * (int64_t)ray];
+    } else {
+        n = (int32_t)p.n_out;
+        s_base = (int64_t)ray * n;
+        e_base = s_base + ray;
+    }
+    if (n <= 0) return;  // uniform over the cooperating threads
+
+    const float* cdf = p.cdfs + base;
+    const float* val = p.vals + base;
+    float* const out_s = p.sample_vals + s_base;
+    float* ts = out_s;
+    if (kStage) {
+        float* s_cdf = stage;
+        float* s_val = stage + n_in;
+        for (int32_t i = tid; i < n_in; i += kLanes) {
+            s_cdf[i] = __ldg(cdf + i);
+            s_val[i] = __ldg(val + i);
+        }
+        cdf = s_cdf;
+        val = s_val;
+        ts = stage + 2 * n_in;
+        if (kCta) __syncthreads(); else __syncwarp();
+    }
+
+    const float quiet_nan = __int_as_float(0x7fc00000);
+    const float t_min = n_in > 0 ? val[0] : quiet_nan;
+    const float t_max = n_in > 0 ? val[n_in - 1] : quiet_nan;
+    const float u_floor = n_in > 0 ? cdf[0] : quiet_nan;
+    const float u_ceil = n_in > 0 ? cdf[n_in - 1] : quiet_nan;
+    const float u_step = f_div(f_sub(u_ceil, u_floor), (float)n);
+    const float bias = kStratified ? philox_uniform(p.seed, (uint64_t)(int64_t)ray, p.offset) : 0.5f;
+
+    for (int32_t sid = tid; sid < n; sid += kLanes) {
+        const float t = n_in > 0 ? is_invert<int32_t>(cdf, val, 0, n_in - 1, is_u<int32_t>(u_floor, u_step, sid, bias))
+                                 : quiet_nan;
+        ts[sid] = t;
+        if (kStage) out_s[sid] = t;
+        if (p.sample_ray) p.sample_ray[s_base + sid] = ray;
+    }
+    // centres visible to the cooperating threads (shared memory, or this CTA's own global writes)
+    if (kCta) __syncthreads(); else __syncwarp();
+
+    float* const out_e = p.iv_vals + e_base;
+    for (int32_t k = tid; k <= n; k += kLanes) {
+        const float e = is_edge<int32_t>(ts, n, k, t_min, t_max);
+        out_e[k] = e;
+        if (p.out_packed) {
+            p.iv_ray[e_base + k] = ray;
+            p.iv_left[e_base + k] = k < n;
+            p.iv_right[e_base + k] = k > 0;
+        } else if (p.t_starts) {
+            const float t = stot(e, p.s_min, p.s_max, p.lindisp != 0);
+            if (k < n) p.t_starts[s_base + k] = t;
+            if (k > 0) p.t_ends[s_base + k - 1] = t;
+        }
+    }
+    if (kStage) {  // before the next ray overwrites the staging area
+        if (kCta) __syncthreads(); else __syncwarp();
+    }
+}
+
+// CTA per ray: long rays (hundreds of edges / samples).  kStage = false searches global memory (rays whose
+// tables exceed shared memory).
 template <bool kStage>
 __global__ void __launch_bounds__(kIsThreads) importance_sampling_kernel(IsParams p)
 {
     extern __shared__ float smem[];
     for (int32_t ray = blockIdx.x; ray < p.n_rays; ray += gridDim.x) {
-        int64_t base, n_in;
-        if (p.in_packed) {
-            base = p.in_packed[2 * (int64_t)ray];
-            n_in = p.in_packed[2 * (int64_t)ray + 1];
-        } else {
-            base = (int64_t)ray * p.in_edges;
-            n_in = p.in_edges;
-        }
-        int64_t n, s_base, e_base;
-        if (p.out_packed) {
-            s_base = p.out_packed[2 * (int64_t)ray];
-            n = p.out_packed[2 * (int64_t)ray + 1];
-            e_base = p.iv_packed[2 * (int64_t)ray];
-        } else {
-            n = p.n_out;
-            s_base = (int64_t)ray * n;
-            e_base = (int64_t)ray * (n + 1);
-        }
-        if (n <= 0) continue;
-
-        const float* cdf = p.cdfs + base;
-        const float* val = p.vals + base;
-        float* ts = p.sample_vals + s_base;
-        if (kStage) {
-            float* s_cdf = smem;
-            float* s_val = smem + n_in;
-            for (int64_t i = threadIdx.x; i < n_in; i += kIsThreads) {
-                s_cdf[i] = __ldg(cdf + i);
-                s_val[i] = __ldg(val + i);
-            }
-            cdf = s_cdf;
-            val = s_val;
-            ts = smem + 2 * n_in;
-            __syncthreads();
-        }
-
-        const float quiet_nan = __int_as_float(0x7fc00000);
-        const float t_min = n_in > 0 ? val[0] : quiet_nan;
-        const float t_max = n_in > 0 ? val[n_in - 1] : quiet_nan;
-        const float u_floor = n_in > 0 ? cdf[0] : quiet_nan;
-        const float u_ceil = n_in > 0 ? cdf[n_in - 1] : quiet_nan;
-        const float u_step = f_div(f_sub(u_ceil, u_floor), (float)n);
-        const float bias = p.stratified ? philox_uniform(p.seed, (uint64_t)(int64_t)ray, p.offset) : 0.5f;
-
-        for (int64_t sid = threadIdx.x; sid < n; sid += kIsThreads) {
-            const float t = n_in > 0 ? is_invert(cdf, val, 0, n_in - 1, is_u(u_floor, u_step, sid, bias)) : quiet_nan;
-            ts[sid] = t;
-            if (kStage) p.sample_vals[s_base + sid] = t;
-            if (p.sample_ray) p.sample_ray[s_base + sid] = ray;
-        }
-        __syncthreads();  // centres visible to the whole CTA (shared, or this CTA's own global writes)
-
-        for (int64_t k = threadIdx.x; k <= n; k += kIsThreads) {
-            const float e = is_edge(ts, n, k, t_min, t_max);
-            p.iv_vals[e_base + k] = e;
-            if (p.out_packed) {
-                p.iv_ray[e_base + k] = ray;
-                p.iv_left[e_base + k] = k < n;
-                p.iv_right[e_base + k] = k > 0;
-            } else if (p.t_starts) {
-                const float t = stot(e, p.s_min, p.s_max, p.lindisp != 0);
-                if (k < n) p.t_starts[s_base + k] = t;
-                if (k > 0) p.t_ends[s_base + k - 1] = t;
-            }
-        }
-        if (kStage) __syncthreads();  // before the next ray overwrites the staging area
+        if (p.stratified) resample_ray<kStage, kIsThreads, true, true>(p, ray, threadIdx.x, smem);
+        else resample_ray<kStage, kIsThreads, true, false>(p, ray, threadIdx.x, smem);
     }
+}
+
+// Warp per ray, kIsWarps rays in flight per CTA: the proposal-network shapes (tens of edges and samples per
+// ray, 10^5..10^6 rays), where a CTA per ray would leave most of its threads idle between two barriers.
+constexpr int kIsWarps = 8;
+template <bool kStratified>
+__global__ void __launch_bounds__(kIsWarps * 32) importance_sampling_warp_kernel(IsParams p, int32_t floats_per_ray)
+{
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* stage = smem + (size_t)warp * floats_per_ray;
+    for (int64_t ray = (int64_t)blockIdx.x * kIsWarps + warp; ray < p.n_rays; ray += (int64_t)gridDim.x * kIsWarps)
+        resample_ray<true, 32, false, kStratified>(p, (int32_t)ray, lane, stage);
 }
 
 struct SearchParams {
@@ -153,7 +187,7 @@ __global__ void __launch_bounds__(kSearchThreads) searchsorted_kernel(SearchPara
             base = ray * p.k_edges;
             last = base + p.k_edges - 1;
         }
-        const int64_t pos = upper_bound_f(p.k_vals, base, last, __ldg(p.q_vals + i));
+        const int64_t pos = upper_bound_f<int64_t>(p.k_vals, base, last, __ldg(p.q_vals + i));
         int64_t l = pos - 1 < last ? pos - 1 : last;
         if (l < base) l = base;
         int64_t r = pos < last ? pos : last;
@@ -214,8 +248,18 @@ int32_t nfa_importance_sampling(int32_t n_rays, const float* vals, const float* 
     const int64_t in_cap = in_packed_info ? max_in_edges : in_edges;
     const int64_t out_cap = out_packed_info ? max_out : n_out;
     const int64_t floats = 2 * in_cap + out_cap;
-    const unsigned grid = (unsigned)(n_rays < (1 << 20) ? n_rays : (1 << 20));
     cudaStream_t s = (cudaStream_t)stream;
+    if (floats <= kWarpRayFloats) {
+        // short rays: a warp each; persistent CTAs sized to fill the machine
+        const size_t bytes = (size_t)floats * kIsWarps * sizeof(float);
+        const int64_t want = ((int64_t)n_rays + kIsWarps - 1) / kIsWarps;
+        const int64_t cap = 148 * 8 * 4;
+        const unsigned grid = (unsigned)(want < cap ? want : cap);
+        if (stratified) importance_sampling_warp_kernel<true><<<grid, kIsWarps * 32, bytes, s>>>(p, (int32_t)floats);
+        else importance_sampling_warp_kernel<false><<<grid, kIsWarps * 32, bytes, s>>>(p, (int32_t)floats);
+        return (int32_t)cudaGetLastError();
+    }
+    const unsigned grid = (unsigned)(n_rays < (1 << 20) ? n_rays : (1 << 20));
     if (floats <= kIsSmemFloats) {
         const size_t bytes = (size_t)floats * sizeof(float);
         if (bytes > 48 * 1024) {

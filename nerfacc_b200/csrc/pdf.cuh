@@ -15,10 +15,11 @@
 namespace nfa {
 
 // first index in [start, end) whose value is > v (end if none); same probe order as pdf.cu:43-63
-NFA_HD int64_t upper_bound_f(const float* a, int64_t start, int64_t end, float v)
+template <class Index>
+NFA_HD Index upper_bound_f(const float* a, Index start, Index end, float v)
 {
     while (start < end) {
-        const int64_t mid = start + ((end - start) >> 1);
+        const Index mid = start + ((end - start) >> 1);
         if (!(a[mid] > v)) start = mid + 1;
         else end = mid;
     }
@@ -73,18 +74,20 @@ NFA_HD float philox_uniform(uint64_t seed, uint64_t subsequence, uint64_t offset
 }
 
 // Position of sample `sid` on the CDF axis (pdf.cu:135-146).
-NFA_HD float is_u(float u_floor, float u_step, int64_t sid, float bias)
+template <class Index>
+NFA_HD float is_u(float u_floor, float u_step, Index sid, float bias)
 {
     return f_fma(f_add((float)sid, bias), u_step, u_floor);
 }
 
 // Invert the piecewise-linear CDF at u over edges [base, last] (pdf.cu:148-165).
-NFA_HD float is_invert(const float* cdfs, const float* vals, int64_t base, int64_t last, float u)
+template <class Index>
+NFA_HD float is_invert(const float* cdfs, const float* vals, Index base, Index last, float u)
 {
-    const int64_t p = upper_bound_f(cdfs, base, last, u);
-    int64_t p0 = p - 1 < last ? p - 1 : last;
+    const Index p = upper_bound_f<Index>(cdfs, base, last, u);
+    Index p0 = p - 1 < last ? p - 1 : last;
     if (p0 < base) p0 = base;
-    int64_t p1 = p < last ? p : last;
+    Index p1 = p < last ? p : last;
     if (p1 < base) p1 = base;
     const float u_lower = cdfs[p0], u_upper = cdfs[p1];
     const float t_lower = vals[p0], t_upper = vals[p1];
@@ -97,7 +100,8 @@ NFA_HD float is_invert(const float* cdfs, const float* vals, int64_t base, int64
 // Edge k (0..n) between the n sample centres ts[0..n) of one ray (pdf.cu:203-241).  n == 1 is
 // undefined in the reference (it reads the next ray's first sample and never writes the right edge);
 // here a single sample spans the whole input range.
-NFA_HD float is_edge(const float* ts, int64_t n, int64_t k, float t_min, float t_max)
+template <class Index>
+NFA_HD float is_edge(const float* ts, Index n, Index k, float t_min, float t_max)
 {
     if (n == 1) return k == 0 ? t_min : t_max;
     if (k == 0) {

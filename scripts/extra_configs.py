@@ -1,0 +1,121 @@
+"""BASELINE.json configs 3 and 4 on one GPU, for either implementation (same public API):
+
+    python scripts/extra_configs.py ours            # this repo (nerfacc_b200)
+    python scripts/extra_configs.py reference-cuda  # the unmodified reference CUDA build in baseline/_ref
+
+config 3: 256^3 occ-grid, 1 048 576 rays, inference-only (sampling + no-grad compositing)
+config 4: importance sampling, 262 144 rays x 64 -> 32 samples (kernel alone, and one PropNet level end to end)
+Times with CUDA events after warm-up; prints one JSON line per config and appends them to
+gpurun_out/extra_configs_<impl>.json.  Informational (bench.py stays on config 2).
+"""
+import importlib.util
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+impl = sys.argv[1] if len(sys.argv) > 1 else "ours"
+if impl == "reference-cuda":
+    sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+    import nerfacc as nf
+    assert "baseline/_ref" in nf.__file__
+    from nerfacc.data_specs import RayIntervals
+    from nerfacc.estimators.prop_net import PropNetEstimator
+    from nerfacc.pdf import importance_sampling
+else:
+    sys.path.insert(0, ROOT)
+    import nerfacc_b200 as nf
+    from nerfacc_b200.data_specs import RayIntervals
+    from nerfacc_b200.estimators.prop_net import PropNetEstimator
+    from nerfacc_b200.pdf import importance_sampling
+_spec = importlib.util.spec_from_file_location("scenes", os.path.join(ROOT, "nerfacc_b200", "scenes.py"))
+scenes = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(scenes)
+
+dev = torch.device("cuda:0")
+lines = []
+
+
+def timed(fn, iters=20, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e-3
+
+
+def emit(**kw):
+    kw["impl"] = impl
+    lines.append(kw)
+    print(json.dumps(kw), flush=True)
+
+
+# ---------------------------------------------------------------- config 3
+R3, G3 = 1 << 20, 256
+ro, rd = scenes.ball_rays(R3, seed=7)
+est = nf.OccGridEstimator(torch.from_numpy(scenes.ROI_AABB), resolution=G3).to(dev)
+est.binaries = torch.from_numpy(scenes.ball_grid(G3)).to(dev)
+tro, trd = torch.from_numpy(ro).to(dev), torch.from_numpy(rd).to(dev)
+step3 = 2.6e-3  # half of config 2's step on a grid twice as fine
+with torch.no_grad():
+    ri, ts, te = est.sampling(tro, trd, render_step_size=step3)
+    N3 = ri.numel()
+    sig = 5 * torch.rand(N3, device=dev)
+    rgb = torch.rand(N3, 3, device=dev)
+
+    def infer():
+        ri_, ts_, te_ = est.sampling(tro, trd, render_step_size=step3)
+        return nf.rendering(ts_, te_, ri_, n_rays=R3, rgb_sigma_fn=lambda a, b, c: (rgb, sig))
+
+    def samp():
+        return est.sampling(tro, trd, render_step_size=step3)
+
+    def comp():
+        return nf.rendering(ts, te, ri, n_rays=R3, rgb_sigma_fn=lambda a, b, c: (rgb, sig))
+
+    t_all, t_s, t_c = timed(infer, 10), timed(samp, 10), timed(comp, 10)
+emit(config="3: 256^3 occ-grid, 1048576 rays, inference-only", n_samples=N3, samples_per_ray=N3 / R3,
+     step_ms=t_all * 1e3, sampling_ms=t_s * 1e3, compositing_ms=t_c * 1e3, gsamples_per_s=N3 / t_all / 1e9)
+del ri, ts, te, sig, rgb
+torch.cuda.empty_cache()
+
+# ---------------------------------------------------------------- config 4
+R4 = 262144
+torch.manual_seed(3)
+edges = torch.sort(torch.rand(R4, 65, device=dev), -1)[0]
+edges[:, 0], edges[:, -1] = 0.0, 1.0
+w = torch.rand(R4, 64, device=dev) ** 4 + 1e-3
+cdfs = torch.cat([torch.zeros(R4, 1, device=dev), torch.cumsum(w, -1)], -1)
+cdfs = (cdfs / cdfs[:, -1:]).contiguous()
+iv_in = RayIntervals(vals=edges)
+for strat in (False, True):
+    t = timed(lambda: importance_sampling(iv_in, cdfs, 32, strat), 50, 5)
+    # algorithmic bytes: read edges + cdfs (2 x 65 floats), write 32 centres + 33 edges, per ray
+    by = R4 * 4 * (2 * 65 + 32 + 33)
+    emit(config="4: importance_sampling 262144 rays x 64 -> 32", stratified=strat, us=t * 1e6,
+         gsamples_per_s=R4 * 32 / t / 1e9, algorithmic_gb_per_s=by / t / 1e9)
+
+
+def prop_fn(t_starts, t_ends):
+    mid = (t_starts + t_ends) * 0.5
+    return 4.0 * torch.exp(-((mid - 3.0) / 1.0) ** 2)
+
+
+pn = PropNetEstimator().to(dev)
+t = timed(lambda: pn.sampling([prop_fn], [64], 32, n_rays=R4, near_plane=0.2, far_plane=50.0, sampling_type="lindisp",
+                              stratified=True), 20, 3)
+emit(config="4: PropNetEstimator.sampling 262144 rays, one proposal level 64 -> 32 final", ms=t * 1e3,
+     gsamples_per_s=R4 * 32 / t / 1e9)
+
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+with open(os.path.join(ROOT, "gpurun_out", f"extra_configs_{impl}.json"), "w") as f:
+    for ln in lines:
+        f.write(json.dumps(ln) + "\n")

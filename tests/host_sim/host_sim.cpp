@@ -233,11 +233,11 @@ void sim_importance_sampling(int32_t n_rays, const float* vals, const float* cdf
         const float u_step = f_div(f_sub(u_ceil, u_floor), (float)n);
         const float bias = stratified ? philox_uniform(seed, (uint64_t)(int64_t)ray, offset) : 0.5f;
         for (int64_t sid = 0; sid < n; ++sid) {
-            ts[sid] = is_invert(cdf, val, 0, n_in - 1, is_u(u_floor, u_step, sid, bias));
+            ts[sid] = is_invert<int64_t>(cdf, val, 0, n_in - 1, is_u<int64_t>(u_floor, u_step, sid, bias));
             if (sample_ray) sample_ray[s_base + sid] = ray;
         }
         for (int64_t k = 0; k <= n; ++k) {
-            const float e = is_edge(ts, n, k, val[0], val[n_in - 1]);
+            const float e = is_edge<int64_t>(ts, n, k, val[0], val[n_in - 1]);
             iv_vals[e_base + k] = e;
             if (out_packed) {
                 iv_ray[e_base + k] = ray;
@@ -263,7 +263,7 @@ void sim_searchsorted(int64_t n_query, const float* q_vals, const int64_t* q_pac
         else ray = chunk_upper_bound(q_packed, n_rays, i) - 1;
         const int64_t base = k_packed ? k_packed[2 * ray] : ray * k_edges;
         const int64_t last = base + (k_packed ? k_packed[2 * ray + 1] : k_edges) - 1;
-        const int64_t pos = upper_bound_f(k_vals, base, last, q_vals[i]);
+        const int64_t pos = upper_bound_f<int64_t>(k_vals, base, last, q_vals[i]);
         int64_t l = pos - 1 < last ? pos - 1 : last;
         if (l < base) l = base;
         int64_t r = pos < last ? pos : last;
