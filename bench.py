@@ -42,6 +42,20 @@ GRID_RES = 128
 B_TRAVERSE, B_FWD, B_BWD, B_RAY = 16, 44, 48, 88
 
 
+def load_traffic(kernel, n_samples):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/r1_traffic.json), or None when
+    the capture was taken on a different sample count."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        if abs(t["n_samples"] - n_samples) > 0.01 * n_samples or kernel not in t:
+            return None
+        return t[kernel]["dram_read"] + t[kernel]["dram_write"]
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -197,6 +211,8 @@ def main():
     def field(t_starts, t_ends, ray_indices):  # stands in for the user's radiance field
         return rgbs, sigmas
 
+    pending = [None]  # the loss reduction of the previous step, read one step late as a logger would
+
     def step(host_inputs: bool):
         if host_inputs:
             o, d = ro_h.to(dev, non_blocking=True), rd_h.to(dev, non_blocking=True)
@@ -205,13 +221,17 @@ def main():
         ri_, ts_, te_ = est.sampling(o, d, render_step_size=step_size)
         colors, opac, depth, _ = nfa.rendering(ts_, te_, ri_, n_rays=R, rgb_sigma_fn=field)
         loss = torch.nn.functional.mse_loss(colors, target)
+        red = parallel.all_reduce_loss_async(loss)  # the only collective of the path; overlaps the backward
         sigmas.grad = None
         rgbs.grad = None
         with torch.autograd.set_multithreading_enabled(False):  # one GPU per process: skip the engine's thread hop
             loss.backward()
-        tot = parallel.all_reduce_loss(loss)  # the only collective of the path
         if host_inputs:
-            loss_host.copy_(tot, non_blocking=True)
+            loss_host.copy_(red.result(), non_blocking=True)  # this step's reduced loss goes back to the host
+        else:
+            if pending[0] is not None:
+                pending[0].result()
+            pending[0] = red
         return ri_.numel()
 
     def timed(host_inputs: bool, steps: int, warmup: int, clocks=None):
@@ -228,6 +248,9 @@ def main():
         n = 0
         for _ in range(steps):
             n += step(host_inputs)
+        if pending[0] is not None:  # the last step's collective completes inside the timed region
+            pending[0].result()
+            pending[0] = None
         e1.record()
         if world > 1:
             dist.barrier()
@@ -298,7 +321,8 @@ def main():
         dom = max(["composite_bwd", "composite_fwd"], key=lambda k: stages[k][1])
         by, tt = stages[dom]
         roof = {"bound": "hbm", "kernel": dom, "achieved": by / tt / 1e9, "peak": peak, "peak_kind": peak_kind,
-                "unit": "GB/s", "frac": by / tt / 1e9 / peak, "traffic": None,
+                "unit": "GB/s", "frac": by / tt / 1e9 / peak, "algorithmic_bytes": by,
+                "traffic": load_traffic(dom, N),
                 "stages_us": {k: round(v[1] * 1e6, 1) for k, v in stages.items()},
                 "stages_gbs": {k: round(v[0] / v[1] / 1e9, 1) for k, v in stages.items()},
                 "step_frac_of_roofline": ((B_TRAVERSE + B_FWD + B_BWD) * N + B_RAY * R) / (ms / args.steps * 1e-3) / 1e9 / peak}

@@ -113,18 +113,32 @@ NFA_D void resample_ray(const IsParams& p, int32_t ray, int tid, float* stage)
     // centres visible to the cooperating threads (shared memory, or this CTA's own global writes)
     if (kCta) __syncthreads(); else __syncwarp();
 
+    // edges 0 .. n-1 by the thread of the same index; the thread holding the last one adds the closing edge n
+    // (a separate pass over k = n would cost a whole extra loop trip when n is a multiple of the group size)
     float* const out_e = p.iv_vals + e_base;
-    for (int32_t k = tid; k <= n; k += kLanes) {
+    for (int32_t k = tid; k < n; k += kLanes) {
         const float e = is_edge<int32_t>(ts, n, k, t_min, t_max);
         out_e[k] = e;
+        float e_close = 0.f;
+        const bool closes = k == n - 1;
+        if (closes) {
+            e_close = is_edge<int32_t>(ts, n, n, t_min, t_max);
+            out_e[n] = e_close;
+        }
         if (p.out_packed) {
             p.iv_ray[e_base + k] = ray;
-            p.iv_left[e_base + k] = k < n;
+            p.iv_left[e_base + k] = 1;
             p.iv_right[e_base + k] = k > 0;
+            if (closes) {
+                p.iv_ray[e_base + n] = ray;
+                p.iv_left[e_base + n] = 0;
+                p.iv_right[e_base + n] = 1;
+            }
         } else if (p.t_starts) {
             const float t = stot(e, p.s_min, p.s_max, p.lindisp != 0);
-            if (k < n) p.t_starts[s_base + k] = t;
+            p.t_starts[s_base + k] = t;
             if (k > 0) p.t_ends[s_base + k - 1] = t;
+            if (closes) p.t_ends[s_base + k] = stot(e_close, p.s_min, p.s_max, p.lindisp != 0);
         }
     }
     if (kStage) {  // before the next ray overwrites the staging area

@@ -243,12 +243,13 @@ __global__ void __launch_bounds__(kTileRays) march_kernel(const MarchParams p)
     __shared__ unsigned long long s_red_samples[kTileRays / 32];
     __shared__ uint32_t s_red_runs[kTileRays / 32], s_red_flags[kTileRays / 32];
     __shared__ bool s_last;
+    __shared__ uint32_t s_sort[kTileRays];
+    static_assert(kTileRays <= 128, "the sort key packs the thread id in 7 bits");
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int tile = blockIdx.x;
     const int r0 = tile * kTileRays;
     const int nr = min(kTileRays, p.n_rays - r0);
-    const int r = r0 + tid;
 
     // ---- stage the ray tile (and the brick mip) into shared memory: TMA bulk copies + mbarrier
     const float* g_o = p.rays_o + (int64_t)r0 * 3;
@@ -278,14 +279,55 @@ __global__ void __launch_bounds__(kTileRays) march_kernel(const MarchParams p)
     if (kSmemCoarse && !bulk_coarse) {
         for (int i = tid; i < p.coarse_words; i += kTileRays) s_coarse[i] = p.coarse[i];
     }
-    const bool active = tid < nr;
+    mbar_wait(&s_bar, 0);
+    __syncthreads();
+
+    // ---- order the tile's rays by expected walk length, so the 32 lanes of a warp finish together.
+    // A warp runs as long as its longest ray; with rays in input order 34 % of the lanes of the cell loop idle
+    // (ncu: 21 of 32 threads per instruction).  The estimate (cells crossed between the slab hits of the box
+    // the walk is confined to) only decides which thread takes which ray -- every output is indexed by ray id.
+    int rt = tid;
+    if (kSingle) {
+        uint32_t key = 0;
+        if (tid < nr) {
+            const float* box = p.aabbs;
+            const bool have_bb = p.bounds != nullptr && p.terminate == nullptr && p.bounds[0] <= p.bounds[3];
+            float tn = p.near_planes ? p.near_planes[r0 + tid] : p.near_plane;
+            float tf = p.far_planes ? p.far_planes[r0 + tid] : p.far_plane;
+            float cells = 0.f;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float voxel = (box[3 + a] - box[a]) / (float)p.g.res[a];
+                const float lo = have_bb ? box[a] + (float)(4 * p.bounds[a] - 1) * voxel : box[a];
+                const float hi = have_bb ? box[a] + (float)(4 * p.bounds[3 + a] + 5) * voxel : box[3 + a];
+                const float oa = s_o[tid * 3 + a], da = s_d[tid * 3 + a];
+                const float inv = 1.0f / da;
+                const float t0 = (lo - oa) * inv, t1 = (hi - oa) * inv;
+                tn = fmaxf(tn, fminf(t0, t1));
+                tf = fminf(tf, fmaxf(t0, t1));
+                cells += fabsf(da) / voxel;
+            }
+            const float est = cells * (tf - tn);
+            if (est > 0.f) key = est < 16777215.f ? (uint32_t)est : 16777215u;  // NaN / miss -> 0
+        }
+        const uint32_t mine = (key << 7) | (uint32_t)tid;  // unique, ties in input order
+        s_sort[tid] = mine;
+        __syncthreads();
+        int rank = 0;
+#pragma unroll 8
+        for (int j = 0; j < kTileRays; ++j) rank += s_sort[j] < mine ? 1 : 0;
+        __syncthreads();
+        s_sort[rank] = (uint32_t)tid;
+        __syncthreads();
+        rt = (int)s_sort[tid];
+    }
+    const int r = r0 + rt;
+    const bool active = rt < nr;
     float near = 0.f, far = 0.f;
     if (active) {
         near = p.near_planes ? p.near_planes[r] : p.near_plane;
         far = p.far_planes ? p.far_planes[r] : p.far_plane;
     }
-    mbar_wait(&s_bar, 0);
-    __syncthreads();
 
     // ---- two-phase march (march.cuh) ---------------------------------------
     OccView occ;
@@ -294,8 +336,8 @@ __global__ void __launch_bounds__(kTileRays) march_kernel(const MarchParams p)
     occ.bounds = p.bounds;
     occ.g = p.g;
     const Lattice L = lat_make(p.step_size);
-    const float o[3] = {active ? s_o[tid * 3 + 0] : 0.f, active ? s_o[tid * 3 + 1] : 0.f, active ? s_o[tid * 3 + 2] : 0.f};
-    const float d[3] = {active ? s_d[tid * 3 + 0] : 1.f, active ? s_d[tid * 3 + 1] : 1.f, active ? s_d[tid * 3 + 2] : 1.f};
+    const float o[3] = {active ? s_o[rt * 3 + 0] : 0.f, active ? s_o[rt * 3 + 1] : 0.f, active ? s_o[rt * 3 + 2] : 0.f};
+    const float d[3] = {active ? s_d[rt * 3 + 0] : 1.f, active ? s_d[rt * 3 + 1] : 1.f, active ? s_d[rt * 3 + 2] : 1.f};
     Walk w;
     LatState m;
     walk_init(w, o, d, near, far);

@@ -24,15 +24,37 @@ def shard_rays(rays_o: torch.Tensor, rays_d: torch.Tensor, rank: int, world_size
     return rays_o[b:e], rays_d[b:e]
 
 
-def all_reduce_loss(loss: torch.Tensor, average: bool = True) -> torch.Tensor:
-    """Sum (or mean) of the per-rank scalar loss; a detached copy, the local graph is untouched.
+class LossReduction:
+    """Handle of an in-flight all-reduce of the scalar loss (see :func:`all_reduce_loss_async`)."""
 
-    4-byte payload: the cost is launch latency, so it is issued on the compute stream.
+    def __init__(self, value: torch.Tensor, work, scale: float):
+        self._value, self._work, self._scale = value, work, scale
+
+    def result(self) -> torch.Tensor:
+        """The reduced loss.  Orders the current stream after the collective (no host sync on CUDA)."""
+        if self._work is not None:
+            self._work.wait()
+            self._work = None
+            if self._scale != 1.0:
+                self._value *= self._scale
+        return self._value
+
+
+def all_reduce_loss_async(loss: torch.Tensor, average: bool = True) -> LossReduction:
+    """Start the sum (or mean) of the per-rank scalar loss and return a handle.
+
+    Call it as soon as the loss exists -- before ``backward()`` -- and read ``result()`` when the number is
+    needed (logging, usually a step later): the 4-byte exchange then runs on NCCL's stream next to the backward
+    kernels instead of stalling the compute stream until the slowest rank arrives.  The value is a detached copy;
+    the local autograd graph is untouched.
     """
     if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
-        return loss.detach()
+        return LossReduction(loss.detach(), None, 1.0)
     out = loss.detach().clone()
-    dist.all_reduce(out, op=dist.ReduceOp.SUM)
-    if average:
-        out /= dist.get_world_size()
-    return out
+    work = dist.all_reduce(out, op=dist.ReduceOp.SUM, async_op=True)
+    return LossReduction(out, work, 1.0 / dist.get_world_size() if average else 1.0)
+
+
+def all_reduce_loss(loss: torch.Tensor, average: bool = True) -> torch.Tensor:
+    """Sum (or mean) of the per-rank scalar loss, complete on return (stream-ordered on CUDA)."""
+    return all_reduce_loss_async(loss, average).result()

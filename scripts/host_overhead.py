@@ -42,6 +42,7 @@ import cProfile, pstats
 pr = cProfile.Profile()
 pr.enable()
 for _ in range(200):
+    ri, ts, te = est.sampling(tro, trd, render_step_size=scenes.BALL_STEP)
     col, op, dep, ex = nfa.rendering(ts, te, ri, n_rays=R, rgb_sigma_fn=field)
     loss = torch.nn.functional.mse_loss(col, tgt)
     sig.grad = None; rgb.grad = None
@@ -49,4 +50,5 @@ for _ in range(200):
         loss.backward()
 torch.cuda.synchronize()
 pr.disable()
-st = pstats.Stats(pr); st.sort_stats("cumulative").print_stats(28)
+st = pstats.Stats(pr); st.sort_stats("cumulative").print_stats(30)
+st.sort_stats("tottime").print_stats(30)

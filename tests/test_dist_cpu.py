@@ -24,6 +24,9 @@ def _worker(rank, world, port, n_rays, q):
     o, d = parallel.shard_rays(rays, -rays, rank, world)
     local = o.sum()  # stands in for the per-rank loss
     tot = parallel.all_reduce_loss(local, average=False)
+    handle = parallel.all_reduce_loss_async(local, average=True)  # started early, read late
+    assert abs(float(handle.result()) * world - float(tot)) < 1e-3 * max(1.0, abs(float(tot)))
+    assert float(handle.result()) == float(handle.result())  # idempotent
     q.put((rank, o.shape[0], float(o[0, 0]) if o.shape[0] else -1.0, float(local), float(tot)))
     dist.destroy_process_group()
 
