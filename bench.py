@@ -221,17 +221,21 @@ def main():
         ri_, ts_, te_ = est.sampling(o, d, render_step_size=step_size)
         colors, opac, depth, _ = nfa.rendering(ts_, te_, ri_, n_rays=R, rgb_sigma_fn=field)
         loss = torch.nn.functional.mse_loss(colors, target)
-        red = parallel.all_reduce_loss_async(loss)  # the only collective of the path; overlaps the backward
+        # the only collective of the path: it overlaps the backward, and its host-side enqueue is parked until the
+        # next sampling() waits for its march (the step is host-bound, that wait is the host's only idle time)
+        red = parallel.all_reduce_loss_async(loss, defer=world > 1)
         sigmas.grad = None
         rgbs.grad = None
         with torch.autograd.set_multithreading_enabled(False):  # one GPU per process: skip the engine's thread hop
             loss.backward()
-        if host_inputs:
-            loss_host.copy_(red.result(), non_blocking=True)  # this step's reduced loss goes back to the host
-        else:
-            if pending[0] is not None:
-                pending[0].result()
-            pending[0] = red
+        prev, pending[0] = pending[0], red
+        if world == 1:
+            prev, pending[0] = red, None  # nothing to wait for: read this step's loss now
+        if prev is not None:
+            if host_inputs:
+                loss_host.copy_(prev.result(), non_blocking=True)  # reduced loss back to the host (a step late if N > 1)
+            else:
+                prev.result()
         return ri_.numel()
 
     def timed(host_inputs: bool, steps: int, warmup: int, clocks=None):
@@ -248,8 +252,10 @@ def main():
         n = 0
         for _ in range(steps):
             n += step(host_inputs)
-        if pending[0] is not None:  # the last step's collective completes inside the timed region
-            pending[0].result()
+        if pending[0] is not None:  # the last step's collective (and read-back) completes inside the timed region
+            last = pending[0].result()
+            if host_inputs:
+                loss_host.copy_(last, non_blocking=True)
             pending[0] = None
         e1.record()
         if world > 1:

@@ -67,6 +67,17 @@ _lib = None
 launches = 0  # number of native kernel-launching calls made through this module (bench.py reports it)
 
 
+# Host work that may run while the host would otherwise wait for the GPU: the march has to finish before the
+# batch size is known (the one sync of a sampling call), which leaves the host ~80 us of idle time per step.
+# parallel.all_reduce_loss_async(defer=True) parks the NCCL enqueue of the previous step's loss here.
+idle_tasks: list = []
+
+
+def run_idle_tasks() -> None:
+    while idle_tasks:
+        idle_tasks.pop(0)()
+
+
 def load():
     """Load the shared library (once) and bind every entry point."""
     global _lib

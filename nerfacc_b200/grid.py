@@ -187,6 +187,8 @@ def _march(rays_o: Tensor, rays_d: Tensor, binaries: Tensor, aabbs: Tensor, near
     def read_totals():
         # wait for the totals only: kernels queued behind the copy (the speculative expand)
         # keep running while the host prepares the next launches
+        if _lib.idle_tasks:
+            _lib.run_idle_tasks()  # deferred host work fills the wait for the march
         sc.event.synchronize()
         n, runs, _, stuck = (int(v) for v in sc.totals_host.tolist())
         if stuck:

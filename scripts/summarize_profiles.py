@@ -20,8 +20,18 @@ P("| kernel | launches | mean us | share |"); P("|---|---:|---:|---:|")
 for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
     P(f"| `{k}` | {len(v)} | {sum(v)/len(v):.1f} | {100*sum(v)/tot:.1f}% |")
 # 2. full profiles
-raw = subprocess.run(["ncu", "-i", f"gpurun_out/{tag}_kernels.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rr = list(csv.reader(raw.splitlines()))
+import glob
+rr = []
+for rep in sorted(glob.glob(f"gpurun_out/{tag}_kernels*.ncu-rep")):  # config-2 step, then the PDF kernels
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    part = list(csv.reader(raw.splitlines()))
+    if not rr:
+        rr = part
+    elif part[0] == rr[0]:
+        rr += part[2:]
+    else:  # different metric sets: align on the first report's header
+        idx = [part[0].index(h) if h in part[0] else None for h in rr[0]]
+        rr += [[row[i] if i is not None else "" for i in idx] for row in part[2:]]
 hdr, units = rr[0], rr[1]
 want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",

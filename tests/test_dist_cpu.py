@@ -27,6 +27,17 @@ def _worker(rank, world, port, n_rays, q):
     handle = parallel.all_reduce_loss_async(local, average=True)  # started early, read late
     assert abs(float(handle.result()) * world - float(tot)) < 1e-3 * max(1.0, abs(float(tot)))
     assert float(handle.result()) == float(handle.result())  # idempotent
+    # deferred enqueue: parked until the library is about to wait for the GPU (or until the value is asked for)
+    from nerfacc_b200 import _lib
+    h1 = parallel.all_reduce_loss_async(local, average=False, defer=True)
+    h2 = parallel.all_reduce_loss_async(local * 2, average=False, defer=True)
+    assert len(_lib.idle_tasks) == 2
+    assert abs(float(h2.result()) - 2 * float(tot)) < 1e-3 * max(1.0, abs(float(tot)))  # runs h1 first, then h2
+    assert not _lib.idle_tasks
+    assert abs(float(h1.result()) - float(tot)) < 1e-3 * max(1.0, abs(float(tot)))
+    h3 = parallel.all_reduce_loss_async(local, average=False, defer=True)
+    _lib.run_idle_tasks()  # what sampling() does while the march runs
+    assert abs(float(h3.result()) - float(tot)) < 1e-3 * max(1.0, abs(float(tot)))
     q.put((rank, o.shape[0], float(o[0, 0]) if o.shape[0] else -1.0, float(local), float(tot)))
     dist.destroy_process_group()
 
