@@ -40,6 +40,7 @@ GRID_RES = 128
 
 # algorithmic bytes (SURVEY.md 8d / DESIGN.md "Roofline")
 B_TRAVERSE, B_FWD, B_BWD, B_RAY = 16, 44, 48, 88
+LOSS_LAG = 2  # steps between starting the loss all-reduce and consuming its result (N > 1)
 
 
 def load_traffic(kernel, n_samples):
@@ -211,7 +212,10 @@ def main():
     def field(t_starts, t_ends, ray_indices):  # stands in for the user's radiance field
         return rgbs, sigmas
 
-    pending = [None]  # the loss reduction of the previous step, read one step late as a logger would
+    # Loss reductions in flight.  The reduced loss is consumed LOSS_LAG steps late, as a logger would: reading it
+    # makes the compute stream wait for that collective, i.e. for the slowest rank to have reached it, so a lag
+    # of one step turns every bit of host jitter on any rank into a stall on all of them.
+    pending = []
 
     def step(host_inputs: bool):
         if host_inputs:
@@ -228,14 +232,12 @@ def main():
         rgbs.grad = None
         with torch.autograd.set_multithreading_enabled(False):  # one GPU per process: skip the engine's thread hop
             loss.backward()
-        prev, pending[0] = pending[0], red
-        if world == 1:
-            prev, pending[0] = red, None  # nothing to wait for: read this step's loss now
-        if prev is not None:
+        pending.append(red)
+        lag = LOSS_LAG if world > 1 else 0  # a single process has nothing to wait for: read this step's loss now
+        if len(pending) > lag:
+            done = pending.pop(0).result()
             if host_inputs:
-                loss_host.copy_(prev.result(), non_blocking=True)  # reduced loss back to the host (a step late if N > 1)
-            else:
-                prev.result()
+                loss_host.copy_(done, non_blocking=True)  # the reduced loss goes back to the host
         return ri_.numel()
 
     def timed(host_inputs: bool, steps: int, warmup: int, clocks=None):
@@ -252,11 +254,10 @@ def main():
         n = 0
         for _ in range(steps):
             n += step(host_inputs)
-        if pending[0] is not None:  # the last step's collective (and read-back) completes inside the timed region
-            last = pending[0].result()
+        while pending:  # the trailing collectives (and read-backs) complete inside the timed region
+            done = pending.pop(0).result()
             if host_inputs:
-                loss_host.copy_(last, non_blocking=True)
-            pending[0] = None
+                loss_host.copy_(done, non_blocking=True)
         e1.record()
         if world > 1:
             dist.barrier()
