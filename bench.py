@@ -40,7 +40,10 @@ GRID_RES = 128
 
 # algorithmic bytes (SURVEY.md 8d / DESIGN.md "Roofline")
 B_TRAVERSE, B_FWD, B_BWD, B_RAY = 16, 44, 48, 88
-LOSS_LAG = 2  # steps between starting the loss all-reduce and consuming its result (N > 1)
+LOSS_LAG = int(os.environ.get("NFA_BENCH_LOSS_LAG", "1"))  # steps between starting the loss all-reduce and consuming its result (N > 1)
+CLOCK_LOAD_STEPS = int(os.environ.get("NFA_BENCH_CLOCK_LOAD_STEPS", "1500"))  # ~0.5 s of untimed steps in front of the value arm so nvidia-smi samples fall under load
+COLLECTIVE = os.environ.get("NFA_BENCH_NO_COLLECTIVE", "0") == "0"  # debugging aid: time N ranks without the all-reduce
+LOSS_DEFER = os.environ.get("NFA_BENCH_LOSS_DEFER", "1") != "0"  # park its host-side enqueue in the next march wait
 
 
 def load_traffic(kernel, n_samples):
@@ -57,6 +60,25 @@ def load_traffic(kernel, n_samples):
         return None
 
 
+def pin_to_gpu_numa_node(index: int) -> None:
+    """Run this process on the CPUs next to its GPU (one process per GPU; torchrun does not pin).  The step is
+    host-bound: launches and pinned-memory copies from the far socket cost tens of microseconds per step."""
+    try:
+        bus = torch.cuda.get_device_properties(index).pci_bus_id
+        dom = torch.cuda.get_device_properties(index).pci_domain_id
+        dev_id = torch.cuda.get_device_properties(index).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev_id:02x}.0/local_cpulist"
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except (OSError, ValueError, AttributeError):
+        pass
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -65,10 +87,14 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.
+    """nvidia-smi clocks / throttle reasons sampled under the benchmark's load.
 
-    One background `nvidia-smi -lms` process writing to a file: the benchmark step is partly
-    host-bound, so the sampler must not run Python (or spawn processes) while the clock is on.
+    One background `nvidia-smi -lms 200` process (the profiling recipe's clocks line) started when the program
+    starts and stopped right after the timed region.  The step is partly host-bound, so nothing here runs
+    Python, sleeps or spawns processes near the timed region: an idle gap in front of it would let the GPU
+    drop its clocks, and a 30-step region lasts ~10 ms, shorter than any sampling period -- so the value arm
+    runs `CLOCK_LOAD_STEPS` extra untimed steps (on every rank) in front of the region and the samples kept are
+    the ones taken during that load and the region itself.
     """
 
     QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -80,17 +106,19 @@ class ClockSampler:
     def start(self):
         try:
             self.out = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu=timestamp,{self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=self.out, stderr=subprocess.DEVNULL)
-            time.sleep(0.35)  # let it take its first samples before the clock starts
         except Exception:
             self.proc = None
+
+    def mark_load(self):
+        """Samples from now on are taken under load."""
+        self.t_load = time.time()
 
     def stop(self):
         rows = []
         if self.proc is not None:
-            time.sleep(0.15)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=5)
@@ -98,7 +126,17 @@ class ClockSampler:
                 self.proc.kill()
             self.out.close()
             try:
-                rows = [[c.strip() for c in l.split(",")] for l in open(self.path) if l.strip()]
+                import datetime
+                for l in open(self.path):
+                    c = [x.strip() for x in l.split(",")]
+                    if len(c) < 7:
+                        continue
+                    try:  # "2026/09/22 21:54:03.123"
+                        ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    except ValueError:
+                        continue
+                    if ts >= getattr(self, "t_load", 0.0) + 0.05:
+                        rows.append(c[1:])
                 os.remove(self.path)
             except Exception:
                 pass
@@ -182,8 +220,13 @@ def main():
     from nerfacc_b200 import _lib, parallel, scenes
 
     assert torch.cuda.is_available(), "bench.py (ours) needs a GPU; there is no CPU fallback"
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    if clocks:
+        clocks.start()  # long before the timed region: spawning a process next to it skews the ranks
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    pin_to_gpu_numa_node(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -217,9 +260,34 @@ def main():
     # of one step turns every bit of host jitter on any rank into a stall on all of them.
     pending = []
 
+    # e2e arm: every step's rays come from pinned host memory.  The copy of step k+1 is issued on a copy stream as
+    # soon as step k's march has consumed its rays (double buffer), so it overlaps step k's compositing -- what a
+    # data loader does; one H2D copy of the full ray batch per step stays inside the timed region.
+    copy_stream = torch.cuda.Stream(device=dev)
+    stage = [(torch.empty_like(ro_d), torch.empty_like(rd_d)) for _ in range(2)]
+    staged = {"event": None, "slot": 0}
+
+    def prefetch_rays():
+        slot = staged["slot"] ^ 1
+        with torch.cuda.stream(copy_stream):
+            stage[slot][0].copy_(ro_h, non_blocking=True)
+            stage[slot][1].copy_(rd_h, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        staged["event"], staged["slot"] = ev, slot
+
+    def read_back(value):
+        loss_host.copy_(value, non_blocking=True)  # the (reduced) loss goes back to the host
+
     def step(host_inputs: bool):
         if host_inputs:
-            o, d = ro_h.to(dev, non_blocking=True), rd_h.to(dev, non_blocking=True)
+            if staged["event"] is None:
+                prefetch_rays()  # first step of the arm: nothing was prefetched yet
+            torch.cuda.current_stream(dev).wait_event(staged["event"])
+            o, d = stage[staged["slot"]]
+            # the copy of the NEXT step's rays is started while this step's sampling() waits for its march: the
+            # buffer it overwrites was last read by the previous step's march, which is complete by then
+            nfa.defer_until_wait(prefetch_rays)
         else:
             o, d = ro_d, rd_d
         ri_, ts_, te_ = est.sampling(o, d, render_step_size=step_size)
@@ -227,24 +295,26 @@ def main():
         loss = torch.nn.functional.mse_loss(colors, target)
         # the only collective of the path: it overlaps the backward, and its host-side enqueue is parked until the
         # next sampling() waits for its march (the step is host-bound, that wait is the host's only idle time)
-        red = parallel.all_reduce_loss_async(loss, defer=world > 1)
+        red = parallel.all_reduce_loss_async(loss, defer=LOSS_DEFER and world > 1) if COLLECTIVE else \
+            parallel.LossReduction(loss.detach(), 1.0, reduce=False)
         sigmas.grad = None
         rgbs.grad = None
         with torch.autograd.set_multithreading_enabled(False):  # one GPU per process: skip the engine's thread hop
             loss.backward()
         pending.append(red)
-        lag = LOSS_LAG if world > 1 else 0  # a single process has nothing to wait for: read this step's loss now
-        if len(pending) > lag:
-            done = pending.pop(0).result()
+        if len(pending) > LOSS_LAG:  # consumed LOSS_LAG steps late, as a logger would
+            done = pending.pop(0)
             if host_inputs:
-                loss_host.copy_(done, non_blocking=True)  # the reduced loss goes back to the host
+                nfa.defer_until_wait(lambda: read_back(done.result()))  # D2H read in the next march wait
+            else:
+                done.result()
         return ri_.numel()
 
-    def timed(host_inputs: bool, steps: int, warmup: int, clocks=None):
-        for _ in range(warmup):
-            step(host_inputs)
+    def timed(host_inputs: bool, steps: int, warmup: int, clocks=None, load_steps: int = 0):
         if clocks:
-            clocks.start()  # spawns a process: keep it outside the region and before the barrier (rank skew)
+            clocks.mark_load()
+        for _ in range(warmup + load_steps):  # the same count on every rank: steps contain a collective
+            step(host_inputs)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -254,10 +324,11 @@ def main():
         n = 0
         for _ in range(steps):
             n += step(host_inputs)
-        while pending:  # the trailing collectives (and read-backs) complete inside the timed region
+        _lib.run_idle_tasks()  # deferred chores of the last step, then the trailing collectives / read-backs:
+        while pending:         # everything completes inside the timed region
             done = pending.pop(0).result()
             if host_inputs:
-                loss_host.copy_(done, non_blocking=True)
+                read_back(done)
         e1.record()
         if world > 1:
             dist.barrier()
@@ -274,8 +345,7 @@ def main():
             ms, n = float(tm[0]), float(t[1])
         return ms, float(n), _lib.launches - l0, ck
 
-    clocks = ClockSampler(local_rank) if rank == 0 else None
-    ms, n_samples, launches, ck = timed(False, args.steps, args.warmup, clocks)
+    ms, n_samples, launches, ck = timed(False, args.steps, args.warmup, clocks, CLOCK_LOAD_STEPS)
     value = n_samples / (ms * 1e-3)
     ms_e2e, n_e2e, _, _ = timed(True, args.steps, 2)
     e2e_value = n_e2e / (ms_e2e * 1e-3)
@@ -336,6 +406,7 @@ def main():
         if not args.no_cpu_baseline:
             from oracle import oracle as orc
             orc.build()
+            os.sched_setaffinity(0, all_cpus)  # the CPU baseline may use every host core again
             orc.set_num_threads(orc.host_cores())
             n_cpu = 4096
             bins, aabbs = scenes.ball_grid(GRID_RES), scenes.nested_aabbs(1)

@@ -4,6 +4,7 @@ The public names below are the subset of /root/reference/nerfacc/__init__.py tha
 lies on the hot path; `import nerfacc` resolves to this
 package through the alias package at the repository root.
 """
+from ._lib import defer_until_wait
 from .data_specs import RayIntervals, RaySamples
 from .estimators.occ_grid import OccGridEstimator
 from .estimators.prop_net import PropNetEstimator
@@ -50,4 +51,5 @@ __all__ = [
     "importance_sampling",
     "searchsorted",
     "distortion",
+    "defer_until_wait",
 ]

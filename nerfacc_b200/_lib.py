@@ -78,6 +78,14 @@ def run_idle_tasks() -> None:
         idle_tasks.pop(0)()
 
 
+def defer_until_wait(fn) -> None:
+    """Run `fn()` the next time the library is about to wait for the GPU (inside the next sampling call,
+    between queueing the march and waiting for its sample count).  Meant for host-side chores that need not
+    happen now -- starting a copy of the next batch, a collective on last step's loss, a read-back for the
+    logger -- on a step whose host side is the bottleneck."""
+    idle_tasks.append(fn)
+
+
 def load():
     """Load the shared library (once) and bind every entry point."""
     global _lib

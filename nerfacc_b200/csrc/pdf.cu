@@ -53,8 +53,8 @@ struct IsParams {
 // One ray, resampled by `kLanes` cooperating threads (a whole CTA or one warp) whose rank is `tid`.
 // kStage: `stage` holds room for this ray's CDF, edge positions and sample centres.  Per-ray counts and
 // positions are 32-bit (a ray with 2^31 edges does not exist); only the array offsets are 64-bit.
-template <bool kStage, int kLanes, bool kCta, bool kStratified>
-NFA_D void resample_ray(const IsParams& p, int32_t ray, int tid, float* stage)
+template <bool kStage, int kLanes, bool kCta>
+NFA_D void resample_ray(const IsParams& p, int32_t ray, int tid, float* stage, float bias)
 {
     int64_t base;
     int32_t n_in;
@@ -101,7 +101,6 @@ NFA_D void resample_ray(const IsParams& p, int32_t ray, int tid, float* stage)
     const float u_floor = n_in > 0 ? cdf[0] : quiet_nan;
     const float u_ceil = n_in > 0 ? cdf[n_in - 1] : quiet_nan;
     const float u_step = f_div(f_sub(u_ceil, u_floor), (float)n);
-    const float bias = kStratified ? philox_uniform(p.seed, (uint64_t)(int64_t)ray, p.offset) : 0.5f;
 
     for (int32_t sid = tid; sid < n; sid += kLanes) {
         const float t = n_in > 0 ? is_invert<int32_t>(cdf, val, 0, n_in - 1, is_u<int32_t>(u_floor, u_step, sid, bias))
@@ -153,22 +152,34 @@ __global__ void __launch_bounds__(kIsThreads) importance_sampling_kernel(IsParam
 {
     extern __shared__ float smem[];
     for (int32_t ray = blockIdx.x; ray < p.n_rays; ray += gridDim.x) {
-        if (p.stratified) resample_ray<kStage, kIsThreads, true, true>(p, ray, threadIdx.x, smem);
-        else resample_ray<kStage, kIsThreads, true, false>(p, ray, threadIdx.x, smem);
+        const float bias = p.stratified ? philox_uniform(p.seed, (uint64_t)(int64_t)ray, p.offset) : 0.5f;
+        resample_ray<kStage, kIsThreads, true>(p, ray, threadIdx.x, smem, bias);
     }
 }
 
 // Warp per ray, kIsWarps rays in flight per CTA: the proposal-network shapes (tens of edges and samples per
 // ray, 10^5..10^6 rays), where a CTA per ray would leave most of its threads idle between two barriers.
 constexpr int kIsWarps = 8;
+// A warp takes up to 32 consecutive rays at a time (fewer when there are not enough rays to fill the machine): lane l draws the jitter of ray l (one Philox4x32-10 block is ~100
+// instructions; drawn per ray by all 32 lanes it was a quarter of the kernel), then the rays are resampled one
+// after the other with the jitter handed over by shuffle.
 template <bool kStratified>
-__global__ void __launch_bounds__(kIsWarps * 32) importance_sampling_warp_kernel(IsParams p, int32_t floats_per_ray)
+__global__ void __launch_bounds__(kIsWarps * 32) importance_sampling_warp_kernel(IsParams p, int32_t floats_per_ray,
+                                                                                 int32_t chunk /* rays per turn, <= 32 */)
 {
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* stage = smem + (size_t)warp * floats_per_ray;
-    for (int64_t ray = (int64_t)blockIdx.x * kIsWarps + warp; ray < p.n_rays; ray += (int64_t)gridDim.x * kIsWarps)
-        resample_ray<true, 32, false, kStratified>(p, (int32_t)ray, lane, stage);
+    for (int64_t ray0 = ((int64_t)blockIdx.x * kIsWarps + warp) * chunk; ray0 < p.n_rays;
+         ray0 += (int64_t)gridDim.x * kIsWarps * chunk) {
+        const int n = (int)min((int64_t)chunk, p.n_rays - ray0);
+        float jitter = 0.5f;
+        if (kStratified && lane < n) jitter = philox_uniform(p.seed, (uint64_t)(ray0 + lane), p.offset);
+        for (int i = 0; i < n; ++i) {
+            const float bias = kStratified ? __shfl_sync(0xffffffffu, jitter, i) : 0.5f;
+            resample_ray<true, 32, false>(p, (int32_t)(ray0 + i), lane, stage, bias);
+        }
+    }
 }
 
 struct SearchParams {
@@ -266,11 +277,15 @@ int32_t nfa_importance_sampling(int32_t n_rays, const float* vals, const float* 
     if (floats <= kWarpRayFloats) {
         // short rays: a warp each; persistent CTAs sized to fill the machine
         const size_t bytes = (size_t)floats * kIsWarps * sizeof(float);
-        const int64_t want = ((int64_t)n_rays + kIsWarps - 1) / kIsWarps;
+        int64_t chunk = (int64_t)n_rays / (148 * 64);  // rays per warp if every SM held 64 warps
+        chunk = chunk < 1 ? 1 : (chunk > 32 ? 32 : chunk);
+        const int64_t want = ((int64_t)n_rays + chunk * kIsWarps - 1) / (chunk * kIsWarps);
         const int64_t cap = 148 * 8 * 4;
         const unsigned grid = (unsigned)(want < cap ? want : cap);
-        if (stratified) importance_sampling_warp_kernel<true><<<grid, kIsWarps * 32, bytes, s>>>(p, (int32_t)floats);
-        else importance_sampling_warp_kernel<false><<<grid, kIsWarps * 32, bytes, s>>>(p, (int32_t)floats);
+        if (stratified)
+            importance_sampling_warp_kernel<true><<<grid, kIsWarps * 32, bytes, s>>>(p, (int32_t)floats, (int32_t)chunk);
+        else
+            importance_sampling_warp_kernel<false><<<grid, kIsWarps * 32, bytes, s>>>(p, (int32_t)floats, (int32_t)chunk);
         return (int32_t)cudaGetLastError();
     }
     const unsigned grid = (unsigned)(n_rays < (1 << 20) ? n_rays : (1 << 20));

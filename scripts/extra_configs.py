@@ -58,6 +58,31 @@ def emit(**kw):
     print(json.dumps(kw), flush=True)
 
 
+# ---------------------------------------------------------------- config 2 + visibility filter (row f1)
+R2 = 65536
+ro2, rd2 = scenes.ball_rays(R2)
+est2 = nf.OccGridEstimator(torch.from_numpy(scenes.ROI_AABB), resolution=128).to(dev)
+est2.binaries = torch.from_numpy(scenes.ball_grid(128)).to(dev)
+est2.occs = est2.binaries.float().flatten() * 0.5
+tro2, trd2 = torch.from_numpy(ro2).to(dev), torch.from_numpy(rd2).to(dev)
+
+
+def sigma_fn(t_starts, t_ends, ray_indices):
+    return 3.0 + 0.0 * t_starts  # constant density: rays saturate after ~3 units of optical depth
+
+
+with torch.no_grad():
+    ri2, _, _ = est2.sampling(tro2, trd2, render_step_size=scenes.BALL_STEP)
+    rv2, _, _ = est2.sampling(tro2, trd2, sigma_fn=sigma_fn, render_step_size=scenes.BALL_STEP, early_stop_eps=1e-2,
+                              alpha_thre=1e-2)
+    t_v = timed(lambda: est2.sampling(tro2, trd2, sigma_fn=sigma_fn, render_step_size=scenes.BALL_STEP,
+                                      early_stop_eps=1e-2, alpha_thre=1e-2), 20)
+    t_p = timed(lambda: est2.sampling(tro2, trd2, render_step_size=scenes.BALL_STEP), 20)
+emit(config="2 + f1: sampling with sigma_fn visibility filter (early_stop_eps=1e-2, alpha_thre=1e-2), 65536 rays",
+     n_before=ri2.numel(), n_kept=rv2.numel(), filtered_us=t_v * 1e6, plain_us=t_p * 1e6)
+del est2, ri2, rv2
+torch.cuda.empty_cache()
+
 # ---------------------------------------------------------------- config 3
 R3, G3 = 1 << 20, 256
 ro, rd = scenes.ball_rays(R3, seed=7)
