@@ -43,6 +43,8 @@ B_TRAVERSE, B_FWD, B_BWD, B_RAY = 16, 44, 48, 88
 LOSS_LAG = int(os.environ.get("NFA_BENCH_LOSS_LAG", "1"))  # steps between starting the loss all-reduce and consuming its result (N > 1)
 CLOCK_LOAD_STEPS = int(os.environ.get("NFA_BENCH_CLOCK_LOAD_STEPS", "1500"))  # ~0.5 s of untimed steps in front of the value arm so nvidia-smi samples fall under load
 COLLECTIVE = os.environ.get("NFA_BENCH_NO_COLLECTIVE", "0") == "0"  # debugging aid: time N ranks without the all-reduce
+LOSS_TRANSPORT = os.environ.get("NFA_BENCH_LOSS_TRANSPORT", "peer")  # "peer": NVLink mailbox (csrc/peer.cu); "nccl": dist.all_reduce
+NOWAIT = os.environ.get("NFA_BENCH_LOSS_NOWAIT", "0") != "0"  # debugging aid: never consume the reduced loss inside the loop
 LOSS_DEFER = os.environ.get("NFA_BENCH_LOSS_DEFER", "1") != "0"  # park its host-side enqueue in the next march wait
 
 
@@ -295,14 +297,15 @@ def main():
         loss = torch.nn.functional.mse_loss(colors, target)
         # the only collective of the path: it overlaps the backward, and its host-side enqueue is parked until the
         # next sampling() waits for its march (the step is host-bound, that wait is the host's only idle time)
-        red = parallel.all_reduce_loss_async(loss, defer=LOSS_DEFER and world > 1) if COLLECTIVE else \
+        red = parallel.all_reduce_loss_async(loss, defer=LOSS_DEFER and world > 1, transport=LOSS_TRANSPORT) \
+            if COLLECTIVE else \
             parallel.LossReduction(loss.detach(), 1.0, reduce=False)
         sigmas.grad = None
         rgbs.grad = None
         with torch.autograd.set_multithreading_enabled(False):  # one GPU per process: skip the engine's thread hop
             loss.backward()
         pending.append(red)
-        if len(pending) > LOSS_LAG:  # consumed LOSS_LAG steps late, as a logger would
+        if len(pending) > LOSS_LAG and not NOWAIT:  # consumed LOSS_LAG steps late, as a logger would
             done = pending.pop(0)
             if host_inputs:
                 nfa.defer_until_wait(lambda: read_back(done.result()))  # D2H read in the next march wait
@@ -346,6 +349,13 @@ def main():
         return ms, float(n), _lib.launches - l0, ck
 
     ms, n_samples, launches, ck = timed(False, args.steps, args.warmup, clocks, CLOCK_LOAD_STEPS)
+    loss_route = "none (1 GPU)"
+    if world > 1:
+        mb = parallel.PeerMailbox._instances.get((dev.type, dev.index))
+        if mb is not None:
+            mb.check()
+        loss_route = ("NVLink peer mailbox (csrc/peer.cu)" if mb is not None else "NCCL all_reduce") + \
+            f", deferred into the march wait, read {LOSS_LAG} step(s) late"
     value = n_samples / (ms * 1e-3)
     ms_e2e, n_e2e, _, _ = timed(True, args.steps, 2)
     e2e_value = n_e2e / (ms_e2e * 1e-3)
@@ -428,6 +438,7 @@ def main():
             "config": {"workload": f"{GRID_RES}^3 occ-grid (ball, 6.5% occupied), {RAYS_PER_GPU} rays/GPU, "
                                    f"{N / R:.1f} samples/ray, traverse + composite fwd+bwd",
                        "n_samples_per_gpu": N, "render_step_size": step_size, "parallelism": f"ray-shard dp{world}",
+                       "loss_all_reduce": loss_route,
                        "l2": "per-step working set ~0.9 GB > 126 MB L2 (inputs larger than L2); per-kernel "
                              "roofline timings flush L2 before each launch"},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(R * 24),
@@ -439,6 +450,7 @@ def main():
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        parallel.PeerMailbox.shutdown()
         dist.destroy_process_group()
 
 

@@ -28,7 +28,7 @@ extern "C" {
 #define NFA_ERR_ARG (-1)         /* null pointer / negative size / inconsistent sizes */
 #define NFA_ERR_UNSUPPORTED (-2) /* valid request outside what this build implements */
 
-#define NFA_ABI_VERSION 7
+#define NFA_ABI_VERSION 8
 
 typedef void* nfa_stream_t; /* cudaStream_t */
 
@@ -271,6 +271,31 @@ int32_t nfa_searchsorted(int64_t n_query, const float* query_vals, const int64_t
                          const int64_t* query_ray_indices, int32_t n_rays, int64_t query_edges,
                          const float* key_vals, const int64_t* key_packed_info, int64_t key_edges,
                          int64_t* ids_left, int64_t* ids_right, nfa_stream_t stream);
+
+/* ----------------------------------------------------------------------- */
+/* Data-parallel exchange: sum of per-rank scalars over NVLink peer memory  */
+/* ----------------------------------------------------------------------- */
+
+/* No counterpart in the reference (it is single-GPU; SURVEY.md section 8(e) gives the ray-sharded path exactly one
+ * exchange, the all-reduce of the scalar training loss).  Every rank owns a mailbox of `turns` x `world` 8-byte words
+ * in its own device memory.  The four calls below are the only ones in this library that allocate / map memory:
+ * CUDA IPC can export plain cudaMalloc allocations only, not memory of the caller's pool.
+ *   create:  allocate + zero the mailbox, return it and its 64-byte CUDA IPC handle (exchanged by the host side);
+ *   open:    map a peer's mailbox from its handle (same node; peer access is enabled lazily);  close / destroy. */
+int32_t nfa_mailbox_create(int32_t world, int32_t turns, void** box, unsigned char* handle64);
+int32_t nfa_mailbox_open(const unsigned char* handle64, void** peer_box);
+int32_t nfa_mailbox_close(void* peer_box);
+int32_t nfa_mailbox_destroy(void* box);
+
+/* post: store (value, tag) as one 8-byte word into slot [turn][rank] of every mailbox listed in `boxes` (device
+ *   array of `world` mailbox pointers, entry `rank` being the caller's own) -- st.global over NVLink, no handshake.
+ * sum:  out[0] = scale * sum of the `world` values of `turn` in the caller's own mailbox, in rank order, once all
+ *   carry `tag`; waits for stragglers with a bounded spin (then out = NaN and *status = 1).  `tag` must change from
+ *   one use of a turn to the next (the step number does). */
+int32_t nfa_mailbox_post(const float* value, const void* boxes, int32_t world, int32_t rank, int32_t turn, uint32_t tag,
+                         nfa_stream_t stream);
+int32_t nfa_mailbox_sum(const void* box, int32_t world, int32_t turn, uint32_t tag, float scale, float* out,
+                        int32_t* status, nfa_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -57,11 +57,17 @@ SIGNATURES = {
                                                                                           _c_ptr]),
     "nfa_searchsorted": (_c_i32, [_c_i64, _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_i64, _c_ptr, _c_ptr, _c_i64, _c_ptr,
                                   _c_ptr, _c_ptr]),
+    "nfa_mailbox_create": (_c_i32, [_c_i32, _c_i32, _c_ptr, _c_ptr]),
+    "nfa_mailbox_open": (_c_i32, [_c_ptr, _c_ptr]),
+    "nfa_mailbox_close": (_c_i32, [_c_ptr]),
+    "nfa_mailbox_destroy": (_c_i32, [_c_ptr]),
+    "nfa_mailbox_post": (_c_i32, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32, C.c_uint32, _c_ptr]),
+    "nfa_mailbox_sum": (_c_i32, [_c_ptr, _c_i32, _c_i32, C.c_uint32, _c_f32, _c_ptr, _c_ptr, _c_ptr]),
     "nfa_pack_info_workspace_bytes": (_c_i64, [_c_i32]),
     "nfa_pack_info": (_c_i32, [_c_i64, _c_ptr, _c_i32, _c_ptr, _c_ptr, _c_ptr]),
 }
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 _lib = None
 launches = 0  # number of native kernel-launching calls made through this module (bench.py reports it)

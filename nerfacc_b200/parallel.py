@@ -6,7 +6,7 @@ never mix rays -- so rank k of P takes a contiguous ray shard, all packed output
 stay rank-local (ray_indices are 0-based per shard), the occupancy grid is
 replicated, and the only exchange is one all-reduce of the scalar loss.
 """
-from typing import Tuple
+from typing import Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -26,18 +26,111 @@ def shard_rays(rays_o: torch.Tensor, rays_d: torch.Tensor, rank: int, world_size
     return rays_o[b:e], rays_d[b:e]
 
 
+class PeerMailbox:
+    """Sum of per-rank scalars over NVLink peer memory (csrc/peer.cu), for the ranks of ONE node.
+
+    Every rank owns a mailbox in its device memory, exported with CUDA IPC and mapped by its peers; ``post`` stores
+    this rank's value into every mailbox with one tiny kernel, ``collect`` sums a turn of the local mailbox with
+    another.  No NCCL / c10d call per step: on the host-bound step of this path the c10d route cost ~75 us per
+    step at N = 2, the two launches here ~10 us.  Built once (``PeerMailbox.get(device)``, collective: every rank
+    must call it), it falls back to ``None`` when the handles cannot be exchanged or mapped.
+    """
+
+    TURNS = 16  # ring of turns: a rank is never more than the consumer's lag (a few steps) ahead of the slowest
+    _instances: dict = {}
+
+    def __init__(self, device: torch.device):
+        import ctypes as C
+        self.device, self.world, self.rank = device, dist.get_world_size(), dist.get_rank()
+        self._C, self.step = C, 0
+        lib = _lib.load()
+        box, handle = C.c_void_p(), (C.c_ubyte * 64)()
+        with torch.cuda.device(device):
+            _lib.check(lib.nfa_mailbox_create(self.world, self.TURNS, C.byref(box), handle), "nfa_mailbox_create")
+        self.box = box.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle))
+        self.peers, ptrs = [], []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                ptrs.append(self.box)
+                continue
+            peer = C.c_void_p()
+            with torch.cuda.device(device):
+                _lib.check(lib.nfa_mailbox_open((C.c_ubyte * 64).from_buffer_copy(h), C.byref(peer)),
+                           "nfa_mailbox_open")
+            self.peers.append(peer.value)
+            ptrs.append(peer.value)
+        self.table = torch.tensor(ptrs, dtype=torch.int64, device=device)
+        self.status = torch.zeros(1, dtype=torch.int32, device=device)
+        dist.barrier()  # nobody posts before every mailbox is mapped everywhere
+
+    @classmethod
+    def get(cls, device: torch.device):
+        """The mailbox of this process for `device` (built on first use; collective).  None if unavailable."""
+        key = (device.type, device.index)
+        if key not in cls._instances:
+            ok = torch.ones(1, device=device)
+            try:
+                inst = cls(device)
+            except Exception:  # IPC not permitted, not all ranks on one node, ...
+                inst = None
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # all ranks take the same route
+            cls._instances[key] = inst if bool(ok.item()) else None
+        return cls._instances[key]
+
+    def check(self) -> None:
+        """Raise if a ``collect`` gave up waiting for a rank (synchronises the device)."""
+        if int(self.status.item()) != 0:
+            raise RuntimeError("PeerMailbox: a rank's value did not arrive (a process died or fell far behind)")
+
+    @classmethod
+    def shutdown(cls) -> None:
+        """Unmap the peers' mailboxes, then free the own one (collective; call before destroy_process_group)."""
+        for inst in cls._instances.values():
+            if inst is None:
+                continue
+            torch.cuda.synchronize(inst.device)
+            lib = _lib.load()
+            dist.barrier()
+            for peer in inst.peers:
+                lib.nfa_mailbox_close(inst._C.c_void_p(peer))
+            dist.barrier()
+            lib.nfa_mailbox_destroy(inst._C.c_void_p(inst.box))
+        cls._instances.clear()
+
+    def post(self, value: torch.Tensor):
+        """Send `value` (a float32 scalar on this device) to every rank.  Returns the ticket for ``collect``."""
+        self.step += 1
+        turn, tag = self.step % self.TURNS, self.step & 0xFFFFFFFF
+        _lib.call("nfa_mailbox_post", self.device, value.data_ptr(), self.table.data_ptr(), self.world, self.rank, turn,
+                  tag)
+        return turn, tag
+
+    def collect(self, ticket, scale: float = 1.0) -> torch.Tensor:
+        out = torch.empty((), dtype=torch.float32, device=self.device)
+        _lib.call("nfa_mailbox_sum", self.device, self.box, self.world, ticket[0], ticket[1], float(scale),
+                  out.data_ptr(), self.status.data_ptr())
+        return out
+
+
 class LossReduction:
     """Handle of a (possibly not yet started) all-reduce of the scalar loss; see :func:`all_reduce_loss_async`."""
 
-    def __init__(self, value: torch.Tensor, scale: float, reduce: bool):
+    def __init__(self, value: torch.Tensor, scale: float, reduce: bool, mailbox: Optional[PeerMailbox] = None):
         self._value, self._scale = value, scale
         self._work = None
         self._started = not reduce
+        self._mailbox, self._ticket = mailbox, None
 
     def _start(self) -> None:
         if not self._started:
             self._started = True
-            self._work = dist.all_reduce(self._value, op=dist.ReduceOp.SUM, async_op=True)
+            if self._mailbox is not None:
+                self._ticket = self._mailbox.post(self._value)
+            else:
+                self._work = dist.all_reduce(self._value, op=dist.ReduceOp.SUM, async_op=True)
 
     def result(self) -> torch.Tensor:
         """The reduced loss.  Orders the current stream after the collective (no host sync on CUDA)."""
@@ -51,6 +144,9 @@ class LossReduction:
                         break
             else:
                 self._start()
+        if self._ticket is not None:
+            self._value = self._mailbox.collect(self._ticket, self._scale)
+            self._ticket = None
         if self._work is not None:
             self._work.wait()
             self._work = None
@@ -59,19 +155,29 @@ class LossReduction:
         return self._value
 
 
-def all_reduce_loss_async(loss: torch.Tensor, average: bool = True, defer: bool = False) -> LossReduction:
+def all_reduce_loss_async(loss: torch.Tensor, average: bool = True, defer: bool = False,
+                          transport: str = "nccl") -> LossReduction:
     """Start the sum (or mean) of the per-rank scalar loss and return a handle.
 
     Call it as soon as the loss exists -- before ``backward()`` -- and read ``result()`` when the number is
-    needed (logging, usually a step later): the 4-byte exchange then runs on NCCL's stream next to the backward
-    kernels instead of stalling the compute stream until the slowest rank arrives.  With ``defer`` even the
-    host-side enqueue (tens of microseconds of c10d / NCCL launch work, on a step that is host-bound) is parked
-    until the next ``sampling()`` call waits for its march, where the host is idle anyway; ``result()`` starts
-    it if no sampling call came first.  The value is a detached copy; the local autograd graph is untouched.
+    needed (logging, usually a step later): the 4-byte exchange then runs next to the backward kernels instead of
+    stalling the compute stream until the slowest rank arrives.  With ``defer`` even the host-side enqueue is
+    parked until the next ``sampling()`` call waits for its march, where the host is idle anyway; ``result()``
+    starts it if no sampling call came first.  ``transport="peer"`` sends the scalar through :class:`PeerMailbox`
+    (NVLink peer stores, single node, CUDA float32 scalar) instead of ``dist.all_reduce``; it falls back to NCCL
+    when the mailbox cannot be set up.  The value is a detached copy; the local autograd graph is untouched.
     """
     if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
         return LossReduction(loss.detach(), 1.0, reduce=False)
-    handle = LossReduction(loss.detach().clone(), 1.0 / dist.get_world_size() if average else 1.0, reduce=True)
+    scale = 1.0 / dist.get_world_size() if average else 1.0
+    mailbox = None
+    if transport == "peer" and loss.is_cuda and loss.dtype == torch.float32 and loss.numel() == 1:
+        mailbox = PeerMailbox.get(loss.device)
+    elif transport not in ("nccl", "peer"):
+        raise ValueError(f"unknown transport: {transport}")
+    # the mailbox kernel reads the value when it runs: hand it the loss itself (kept alive by the handle)
+    value = loss.detach() if mailbox is not None else loss.detach().clone()
+    handle = LossReduction(value, scale, reduce=True, mailbox=mailbox)
     if defer:
         _lib.idle_tasks.append(handle._start)
     else:

