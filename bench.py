@@ -14,8 +14,16 @@ sampling -> rendering -> MSE loss on colours -> backward (d/dsigmas, d/drgbs).  
 rgbs stand in for the user's radiance field (seeded leaf tensors).
 
 `value`   samples/s with the ray batch already resident in HBM.
-`e2e`     same step through the public API with HOST inputs: rays copied from pinned
-          memory every step and the scalar loss read back, inside the timed region.
+`e2e`     same step through the public API with HOST inputs: every step copies its ray batch
+          from pinned host memory (double-buffered: the copy for step k+1 is started while step k
+          waits for its march) and one scalar loss goes back to the host (read one step late, as
+          a logger would), all inside the timed region.
+N > 1     ray-sharded weak scaling; the one exchange of the path, the sum of the scalar loss,
+          goes through nerfacc_b200.parallel (NVLink peer mailbox, NCCL fallback), started
+          before backward() and consumed a step later.
+clocks    `nvidia-smi -lms 200` runs from program start; the value arm puts CLOCK_LOAD_STEPS
+          extra untimed steps (on every rank) in front of its W warm-up steps so that samples
+          fall under load without leaving an idle gap in front of the timed region.
 `--impl reference`  the reference has no CPU implementation of the packed path
           (nerfacc/pack.py:47-48); the arm therefore times the CPU oracle port
           (oracle/oracle.c, OpenMP over rays) of exactly this path on the host cores.

@@ -722,8 +722,11 @@ def test_peer_mailbox_single_rank_roundtrip():
     if created:
         import tempfile
         store = os.path.join(tempfile.mkdtemp(), "store")
-        dist.init_process_group("nccl", init_method=f"file://{store}", world_size=1, rank=0,
-                                device_id=torch.device(dev))
+        try:
+            dist.init_process_group("nccl", init_method=f"file://{store}", world_size=1, rank=0,
+                                    device_id=torch.device(dev))
+        except Exception as exc:  # no usable NCCL in this environment: the mailbox needs a process group
+            pytest.skip(f"cannot create a single-rank NCCL group: {exc}")
     try:
         mb = parallel.PeerMailbox.get(torch.device(dev))
         assert mb is not None, "CUDA IPC mailbox could not be created"
