@@ -19,6 +19,10 @@ P("(`ncu --metrics gpu__time_duration.sum --clock-control none`; serialised, col
 P("| kernel | launches | mean us | share |"); P("|---|---:|---:|---:|")
 for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
     P(f"| `{k}` | {len(v)} | {sum(v)/len(v):.1f} | {100*sum(v)/tot:.1f}% |")
+P("\nNotes: the launch list covers the whole bench command -- 5 steps of the value arm (2 timed + 3 warm-up), 2+2 of")
+P("the e2e arm, and the per-kernel roofline timings (11 direct launches of each compositing kernel and 11 sampling calls,")
+P("each preceded by the 256 MB `FillFunctor<unsigned char>` L2 flush, which is not part of a step).  Per step: march,")
+P("offsets, expand, composite fwd, ATen's mse / mean / mse-backward / fill, composite bwd.")
 # 2. full profiles
 import glob
 rr = []
