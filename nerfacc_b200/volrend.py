@@ -45,35 +45,43 @@ def _segments(packed_info: Optional[Tensor], ray_indices: Optional[Tensor], n_ra
     return pi
 
 
+def _composite_forward(dens, rgbs, packed_info, t_starts, t_ends, prefix_trans, bkgd, from_alpha: bool,
+                       expected_depths: bool, want_rays: bool):
+    """One launch of nfa_composite_fwd.  Returns (weights, trans, alphas, colors, opac, depths, raw)."""
+    device = dens.device
+    n = dens.shape[0]
+    n_rays = packed_info.shape[0]
+    weights = torch.empty_like(dens)
+    trans = torch.empty_like(dens)
+    alphas = dens if from_alpha else torch.empty_like(dens)
+    if want_rays:
+        colors = torch.empty((n_rays, 3), dtype=torch.float32, device=device) if rgbs is not None else None
+        opac = torch.empty((n_rays, 1), dtype=torch.float32, device=device)
+        depths = torch.empty((n_rays, 1), dtype=torch.float32, device=device) if t_starts is not None else None
+        raw = torch.empty((n_rays, 5), dtype=torch.float32, device=device)
+    else:
+        colors = opac = depths = raw = None
+    _lib.call("nfa_composite_fwd", device, n_rays, n, _lib.ptr(packed_info), _lib.ptr(t_starts), _lib.ptr(t_ends),
+              _lib.ptr(dens), int(from_alpha), _lib.ptr(rgbs), _lib.ptr(prefix_trans), _lib.ptr(bkgd),
+              int(expected_depths), _lib.ptr(weights), _lib.ptr(trans),
+              None if from_alpha else _lib.ptr(alphas), _lib.ptr(colors), _lib.ptr(opac), _lib.ptr(depths),
+              _lib.ptr(raw))
+    if from_alpha:
+        alphas = dens.detach()  # an input, handed back for symmetry; carries no graph edge
+    return weights, trans, alphas, colors, opac, depths, raw
+
+
 class _Composite(torch.autograd.Function):
     """Fused weights (+ optional per-ray accumulation) with a recompute backward."""
 
     @staticmethod
     def forward(ctx, dens, rgbs, packed_info, t_starts, t_ends, prefix_trans, bkgd,
                 from_alpha: bool, expected_depths: bool, want_rays: bool):
-        device = dens.device
-        n = dens.shape[0]
-        n_rays = packed_info.shape[0]
-        weights = torch.empty_like(dens)
-        trans = torch.empty_like(dens)
-        alphas = dens if from_alpha else torch.empty_like(dens)
-        if want_rays:
-            colors = torch.empty((n_rays, 3), dtype=torch.float32, device=device) if rgbs is not None else None
-            opac = torch.empty((n_rays, 1), dtype=torch.float32, device=device)
-            depths = torch.empty((n_rays, 1), dtype=torch.float32, device=device) if t_starts is not None else None
-            raw = torch.empty((n_rays, 5), dtype=torch.float32, device=device)
-        else:
-            colors = opac = depths = raw = None
-        _lib.call("nfa_composite_fwd", device, n_rays, n, _lib.ptr(packed_info), _lib.ptr(t_starts), _lib.ptr(t_ends),
-                  _lib.ptr(dens), int(from_alpha), _lib.ptr(rgbs), _lib.ptr(prefix_trans), _lib.ptr(bkgd),
-                  int(expected_depths), _lib.ptr(weights), _lib.ptr(trans),
-                  None if from_alpha else _lib.ptr(alphas), _lib.ptr(colors), _lib.ptr(opac), _lib.ptr(depths),
-                  _lib.ptr(raw))
+        weights, trans, alphas, colors, opac, depths, raw = _composite_forward(
+            dens, rgbs, packed_info, t_starts, t_ends, prefix_trans, bkgd, from_alpha, expected_depths, want_rays)
         ctx.from_alpha, ctx.expected_depths = from_alpha, expected_depths
         ctx.save_for_backward(dens, rgbs, packed_info, t_starts, t_ends, prefix_trans, bkgd, raw)
         ctx.set_materialize_grads(False)
-        if from_alpha:
-            alphas = dens.detach()  # an input, handed back for symmetry; carries no graph edge
         return weights, trans, alphas, colors, opac, depths
 
     @staticmethod
@@ -167,8 +175,11 @@ def _composite_packed(dens: Tensor, rgbs: Optional[Tensor], t_starts: Optional[T
         if colors is not None and bkgd is not None:
             colors = colors + bkgd
         return dens, dens, dens, colors, zeros, zeros.clone() if t_starts is not None else None
-    return _Composite.apply(_f32c(dens), _f32c(rgbs), pi, _f32c(t_starts), _f32c(t_ends), _f32c(prefix_trans),
-                            _f32c(bkgd), from_alpha, expected_depths, want_rays)
+    args = (_f32c(dens), _f32c(rgbs), pi, _f32c(t_starts), _f32c(t_ends), _f32c(prefix_trans), _f32c(bkgd),
+            from_alpha, expected_depths, want_rays)
+    if not torch.is_grad_enabled() or not (dens.requires_grad or (rgbs is not None and rgbs.requires_grad)):
+        return _composite_forward(*args)[:6]  # inference: no graph node to build
+    return _Composite.apply(*args)
 
 
 # --------------------------------------------------------------------------
