@@ -160,9 +160,9 @@ __global__ void __launch_bounds__(kIsThreads) importance_sampling_kernel(IsParam
 // Warp per ray, kIsWarps rays in flight per CTA: the proposal-network shapes (tens of edges and samples per
 // ray, 10^5..10^6 rays), where a CTA per ray would leave most of its threads idle between two barriers.
 constexpr int kIsWarps = 8;
-// A warp takes up to 32 consecutive rays at a time (fewer when there are not enough rays to fill the machine): lane l draws the jitter of ray l (one Philox4x32-10 block is ~100
-// instructions; drawn per ray by all 32 lanes it was a quarter of the kernel), then the rays are resampled one
-// after the other with the jitter handed over by shuffle.
+// Stratified: a warp takes `chunk` consecutive rays per turn, lane l draws the jitter of ray l (one Philox4x32-10
+// block is ~100 instructions; drawn per ray by all 32 lanes it was a quarter of the kernel), then the rays are
+// resampled one after the other with the jitter handed over by shuffle.
 template <bool kStratified>
 __global__ void __launch_bounds__(kIsWarps * 32) importance_sampling_warp_kernel(IsParams p, int32_t floats_per_ray,
                                                                                  int32_t chunk /* rays per turn, <= 32 */)
@@ -170,15 +170,17 @@ __global__ void __launch_bounds__(kIsWarps * 32) importance_sampling_warp_kernel
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* stage = smem + (size_t)warp * floats_per_ray;
+    if constexpr (!kStratified) {  // one ray per turn, neighbouring rays on neighbouring warps
+        for (int64_t ray = (int64_t)blockIdx.x * kIsWarps + warp; ray < p.n_rays; ray += (int64_t)gridDim.x * kIsWarps)
+            resample_ray<true, 32, false>(p, (int32_t)ray, lane, stage, 0.5f);
+    } else
     for (int64_t ray0 = ((int64_t)blockIdx.x * kIsWarps + warp) * chunk; ray0 < p.n_rays;
          ray0 += (int64_t)gridDim.x * kIsWarps * chunk) {
         const int n = (int)min((int64_t)chunk, p.n_rays - ray0);
         float jitter = 0.5f;
-        if (kStratified && lane < n) jitter = philox_uniform(p.seed, (uint64_t)(ray0 + lane), p.offset);
-        for (int i = 0; i < n; ++i) {
-            const float bias = kStratified ? __shfl_sync(0xffffffffu, jitter, i) : 0.5f;
-            resample_ray<true, 32, false>(p, (int32_t)(ray0 + i), lane, stage, bias);
-        }
+        if (lane < n) jitter = philox_uniform(p.seed, (uint64_t)(ray0 + lane), p.offset);
+        for (int i = 0; i < n; ++i)
+            resample_ray<true, 32, false>(p, (int32_t)(ray0 + i), lane, stage, __shfl_sync(0xffffffffu, jitter, i));
     }
 }
 
