@@ -1,55 +1,32 @@
 """nerfacc_b200 -- Blackwell-native sampling + volume-rendering hot path with nerfacc's API.
 
-The public names below are the subset of /root/reference/nerfacc/__init__.py that
-lies on the hot path; `import nerfacc` resolves to this
-package through the alias package at the repository root.
+The public names are the subset of /root/reference/nerfacc/__init__.py that lies on the hot path
+ plus ``defer_until_wait``; ``import nerfacc`` resolves to this package through
+the alias package at the repository root.
 """
+from . import data_specs, grid, losses, pack, parallel, pdf, scan, volrend
 from ._lib import defer_until_wait
-from .data_specs import RayIntervals, RaySamples
-from .estimators.occ_grid import OccGridEstimator
-from .estimators.prop_net import PropNetEstimator
-from .grid import ray_aabb_intersect, traverse_grids
-from .losses import distortion
-from .pack import pack_info
-from .pdf import importance_sampling, searchsorted
-from .scan import exclusive_prod, exclusive_sum, inclusive_prod, inclusive_sum
+from .estimators import occ_grid as _occ_grid
+from .estimators import prop_net as _prop_net
 from .version import __version__
-from .volrend import (
-    accumulate_along_rays,
-    accumulate_along_rays_,
-    render_transmittance_from_alpha,
-    render_transmittance_from_density,
-    render_visibility_from_alpha,
-    render_visibility_from_density,
-    render_weight_from_alpha,
-    render_weight_from_density,
-    rendering,
-)
 
-__all__ = [
-    "__version__",
-    "inclusive_prod",
-    "exclusive_prod",
-    "inclusive_sum",
-    "exclusive_sum",
-    "pack_info",
-    "render_visibility_from_alpha",
-    "render_visibility_from_density",
-    "render_weight_from_alpha",
-    "render_weight_from_density",
-    "render_transmittance_from_alpha",
-    "render_transmittance_from_density",
-    "accumulate_along_rays",
-    "accumulate_along_rays_",
-    "rendering",
-    "RayIntervals",
-    "RaySamples",
-    "ray_aabb_intersect",
-    "traverse_grids",
-    "OccGridEstimator",
-    "PropNetEstimator",
-    "importance_sampling",
-    "searchsorted",
-    "distortion",
-    "defer_until_wait",
-]
+_EXPORTS = {
+    scan: ("inclusive_prod", "exclusive_prod", "inclusive_sum", "exclusive_sum"),
+    pack: ("pack_info",),
+    volrend: ("render_visibility_from_alpha", "render_visibility_from_density", "render_weight_from_alpha",
+              "render_weight_from_density", "render_transmittance_from_alpha", "render_transmittance_from_density",
+              "accumulate_along_rays", "accumulate_along_rays_", "rendering"),
+    data_specs: ("RayIntervals", "RaySamples"),
+    grid: ("ray_aabb_intersect", "traverse_grids"),
+    _occ_grid: ("OccGridEstimator",),
+    _prop_net: ("PropNetEstimator",),
+    pdf: ("importance_sampling", "searchsorted"),
+    losses: ("distortion",),
+}
+
+__all__ = ["__version__", "defer_until_wait"]
+for _module, _names in _EXPORTS.items():
+    for _name in _names:
+        globals()[_name] = getattr(_module, _name)
+        __all__.append(_name)
+del _module, _names, _name
