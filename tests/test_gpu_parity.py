@@ -94,6 +94,37 @@ def test_sampling_nested_levels_and_planes(orc):
     _check_sampling(orc, ro, rd, bins4[:1], a4[:1], render_step_size=5e-3, t_min=(rng.random(R) * 5e-3).astype(np.float32))
 
 
+@pytest.mark.parametrize("seed", range(10))
+def test_sampling_random_scenes(orc, seed):
+    """Randomised scenes: odd grid shapes, 1-3 levels, sparse to dense occupancy, rays from inside and outside,
+    random step sizes and clipping planes -- bit-exact against the oracle every time."""
+    rng = np.random.default_rng(1000 + seed)
+    R = int(rng.integers(130, 400))  # not a multiple of the 128-ray tile
+    levels = int(rng.integers(1, 4))
+    shape = tuple(int(v) for v in rng.integers(5, 41, 3))
+    density = float(rng.choice([0.02, 0.2, 0.5, 0.9]))
+    bins = rng.random((levels,) + shape) < density
+    if seed % 3 == 0:  # a compact blob, so the occupied-brick bounding box is much smaller than the grid
+        blob = np.zeros(shape, bool)
+        c = [s // 2 for s in shape]
+        blob[max(c[0] - 3, 0):c[0] + 3, max(c[1] - 2, 0):c[1] + 2, max(c[2] - 3, 0):c[2] + 4] = True
+        bins[0] = blob
+    aabbs = scenes.nested_aabbs(levels)
+    inside = rng.random(R) < 0.4
+    ro = np.where(inside[:, None], rng.uniform(-1, 1, (R, 3)), rng.standard_normal((R, 3)) * 3).astype(np.float32)
+    rd = rng.standard_normal((R, 3)).astype(np.float32)
+    rd /= np.linalg.norm(rd, axis=1, keepdims=True)
+    if seed % 4 == 1:
+        rd[::7] = np.array([0.0, 1.0, 0.0], np.float32)  # axis-aligned rays (infinite crossing times)
+    step = float(rng.choice([2e-3, 5e-3, 1.3e-2, 3e-2]))
+    kw = dict(render_step_size=step)
+    if seed % 2 == 0:
+        kw.update(near_plane=float(rng.uniform(0, 0.5)), far_plane=float(rng.uniform(2, 8)))
+    if seed % 5 == 3:
+        kw.update(t_min=rng.uniform(0, 1, R).astype(np.float32), t_max=rng.uniform(1, 6, R).astype(np.float32))
+    _check_sampling(orc, ro, rd, bins, aabbs, **kw)
+
+
 def test_sampling_edge_cases(orc):
     a1 = scenes.nested_aabbs(1)
     est = _estimator(np.zeros((1, 8, 8, 8), bool), a1)
