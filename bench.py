@@ -303,7 +303,9 @@ def main():
     def read_back(value):
         loss_host.copy_(value, non_blocking=True)  # the (reduced) loss goes back to the host
 
-    def step(host_inputs: bool):
+    ticket = [None]  # pipelined arm: the traversal of the NEXT step, already queued
+
+    def step(host_inputs, pipelined: bool = False):
         if host_inputs:
             if staged["event"] is None:
                 prefetch_rays()  # first step of the arm: nothing was prefetched yet
@@ -314,9 +316,16 @@ def main():
             nfa.defer_until_wait(prefetch_rays)
         else:
             o, d = ro_d, rd_d
-        ri_, ts_, te_ = est.sampling(o, d, render_step_size=step_size)
+        if pipelined:
+            if ticket[0] is None:
+                ticket[0] = est.sampling_begin(o, d, render_step_size=step_size)
+            ri_, ts_, te_ = est.sampling_end(ticket[0])
+        else:
+            ri_, ts_, te_ = est.sampling(o, d, render_step_size=step_size)
         colors, opac, depth, _ = nfa.rendering(ts_, te_, ri_, n_rays=R, rgb_sigma_fn=field)
         loss = torch.nn.functional.mse_loss(colors, target)
+        if pipelined:  # the next batch's traversal goes in front of this batch's backward kernels
+            ticket[0] = est.sampling_begin(o, d, render_step_size=step_size)
         # the only collective of the path: it overlaps the backward, and its host-side enqueue is parked until the
         # next sampling() waits for its march (the step is host-bound, that wait is the host's only idle time)
         red = parallel.all_reduce_loss_async(loss, defer=LOSS_DEFER and world > 1, transport=LOSS_TRANSPORT) \
@@ -335,11 +344,11 @@ def main():
                 done.result()
         return ri_.numel()
 
-    def timed(host_inputs: bool, steps: int, warmup: int, clocks=None, load_steps: int = 0):
+    def timed(host_inputs: bool, steps: int, warmup: int, clocks=None, load_steps: int = 0, pipelined: bool = False):
         if clocks:
             clocks.mark_load()
         for _ in range(warmup + load_steps):  # the same count on every rank: steps contain a collective
-            step(host_inputs)
+            step(host_inputs, pipelined)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -348,7 +357,7 @@ def main():
         e0.record()
         n = 0
         for _ in range(steps):
-            n += step(host_inputs)
+            n += step(host_inputs, pipelined)
         _lib.run_idle_tasks()  # deferred chores of the last step, then the trailing collectives / read-backs:
         while pending:         # everything completes inside the timed region
             done = pending.pop(0).result()
@@ -380,6 +389,12 @@ def main():
             f", deferred into the march wait, read {LOSS_LAG} step(s) late"
     value = n_samples / (ms * 1e-3)
     ms_e2e, n_e2e, _, _ = timed(True, args.steps, 2)
+    # extra, NOT the headline: the same step with sampling_begin / sampling_end (an extension of the drop-in API,
+    # see OccGridEstimator.sampling_begin), the next batch's traversal queued before this batch's backward
+    ms_pipe, n_pipe, _, _ = timed(False, args.steps, args.warmup, pipelined=True)
+    if ticket[0] is not None:
+        est.sampling_end(ticket[0])
+        ticket[0] = None
     e2e_value = n_e2e / (ms_e2e * 1e-3)
 
     # ---- per-kernel roofline: CUDA events on the launching stream, L2 flushed before each launch
@@ -476,6 +491,9 @@ def main():
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(R * 24),
                     "d2h_bytes_per_step": 4 + 32, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
+            "pipelined": {"value": n_pipe / (ms_pipe * 1e-3), "unit": "samples/s", "ms_per_step": ms_pipe / args.steps,
+                          "note": "extra: sampling_begin/sampling_end, next batch's traversal queued before backward(); "
+                                  "not the drop-in API, not the headline"},
             "clocks": ck,
             "roofline": roof,
             "cpu_baseline": cpu_base,

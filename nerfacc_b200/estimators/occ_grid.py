@@ -12,7 +12,7 @@ from typing import Callable, List, Optional, Tuple, Union
 import torch
 from torch import Tensor
 
-from ..grid import _enlarge_aabb, _march, traverse_grids
+from ..grid import _enlarge_aabb, _MarchJob, traverse_grids
 from .. import _lib
 from ..pack import _stash_packed_info
 from ..volrend import render_visibility_from_alpha, render_visibility_from_density
@@ -97,64 +97,109 @@ class OccGridEstimator(AbstractEstimator):
         (transmittance < early_stop_eps) or transparent (alpha < alpha_thre) are dropped.
         Not differentiable.  Semantics: reference occ_grid.py:85-221.
         """
-        n_rays = rays_o.shape[0]
         fast = cone_angle == 0.0 and render_step_size > 0.0 and rays_o.is_cuda
-        per_ray_planes = t_min is not None or t_max is not None or stratified or not fast
-        if per_ray_planes:
-            near_planes = torch.full_like(rays_o[..., 0], fill_value=near_plane)
-            far_planes = torch.full_like(rays_o[..., 0], fill_value=far_plane)
-            if t_min is not None:
-                near_planes = torch.clamp(near_planes, min=t_min)
-            if t_max is not None:
-                far_planes = torch.clamp(far_planes, max=t_max)
-            if stratified:
-                near_planes += torch.rand_like(near_planes) * render_step_size
-            near_planes, far_planes = near_planes.contiguous().float(), far_planes.contiguous().float()
-        else:
-            near_planes = far_planes = None  # the kernel takes the two scalars directly
-
         if fast:
-            res = _march(rays_o.contiguous().float(), rays_d.contiguous().float(), self.binaries,
+            ticket = self.sampling_begin(rays_o, rays_d, near_plane=near_plane, far_plane=far_plane, t_min=t_min,
+                                         t_max=t_max, render_step_size=render_step_size, stratified=stratified)
+            return self.sampling_end(ticket, sigma_fn=sigma_fn, alpha_fn=alpha_fn, early_stop_eps=early_stop_eps,
+                                     alpha_thre=alpha_thre)
+        near_planes, far_planes = self._ray_planes(rays_o, near_plane, far_plane, t_min, t_max, stratified,
+                                                   render_step_size, always=True)
+        intervals, samples, _ = traverse_grids(
+            rays_o, rays_d, self.binaries, self.aabbs, near_planes=near_planes, far_planes=far_planes,
+            step_size=render_step_size, cone_angle=cone_angle)
+        t_starts = intervals.vals[intervals.is_left]
+        t_ends = intervals.vals[intervals.is_right]
+        return self._drop_invisible(samples.ray_indices, t_starts, t_ends, samples.packed_info, sigma_fn, alpha_fn,
+                                    early_stop_eps, alpha_thre)
+
+    @torch.no_grad()
+    def sampling_begin(
+        self,
+        rays_o: Tensor,
+        rays_d: Tensor,
+        near_plane: float = 0.0,
+        far_plane: float = 1e10,
+        t_min: Optional[Tensor] = None,
+        t_max: Optional[Tensor] = None,
+        render_step_size: float = 1e-3,
+        stratified: bool = False,
+    ):
+        """First half of :meth:`sampling` (constant step, CUDA): queue the traversal and return a ticket at once.
+
+        The size of a batch is only known once the traversal has run, so ``sampling()`` has to wait for the GPU
+        once per call -- on a training step that is host-bound that wait (and the kernel itself) sits on the
+        critical path.  A loop that knows its next rays early can call ``sampling_begin`` for batch k+1 before
+        ``loss.backward()`` of batch k and ``sampling_end`` at the top of step k+1: the traversal then runs behind
+        the backward kernels while the host is busy, and ``sampling_end`` returns without waiting.  The occupancy
+        grid is read when the traversal runs; call ``sampling_end`` before changing it.  Not part of nerfacc's API.
+        """
+        if not (rays_o.is_cuda and render_step_size > 0.0):
+            raise ValueError("sampling_begin: only the constant-step CUDA path can be split; use sampling().")
+        near_planes, far_planes = self._ray_planes(rays_o, near_plane, far_plane, t_min, t_max, stratified,
+                                                   render_step_size, always=False)
+        return _MarchJob(rays_o.contiguous().float(), rays_d.contiguous().float(), self.binaries,
                          self.aabbs.contiguous().float(), near_planes, far_planes, float(render_step_size), None, None,
                          None, want_intervals=False, want_terminate=False, capacity_hint=self._capacity_hint,
-                         near_plane=float(near_plane), far_plane=float(far_plane))
-            ray_indices, t_starts, t_ends, packed_info = res.ray_indices, res.t_starts, res.t_ends, res.packed_info
-            # ~6% head-room over the last batch; re-measured every call
-            self._capacity_hint = res.n_samples + (res.n_samples >> 4) + 1024
-        else:
-            intervals, samples, _ = traverse_grids(
-                rays_o, rays_d, self.binaries, self.aabbs, near_planes=near_planes, far_planes=far_planes,
-                step_size=render_step_size, cone_angle=cone_angle)
-            t_starts = intervals.vals[intervals.is_left]
-            t_ends = intervals.vals[intervals.is_right]
-            ray_indices = samples.ray_indices
-            packed_info = samples.packed_info
+                         near_plane=float(near_plane), far_plane=float(far_plane)).begin()
 
-        # drop invisible samples (occ_grid.py:180-220)
-        if (alpha_thre > 0.0 or early_stop_eps > 0.0) and (sigma_fn is not None or alpha_fn is not None):
-            if alpha_thre > 0.0:  # min(0, mean) can never enable the alpha test, so the mean is only needed here
-                alpha_thre = min(alpha_thre, self._occs_mean())
-            use_sigma = sigma_fn is not None
-            if t_starts.shape[0] != 0:
-                dens = (sigma_fn if use_sigma else alpha_fn)(t_starts, t_ends, ray_indices)
-            else:
-                dens = torch.empty((0,), device=t_starts.device)
-            assert dens.shape == t_starts.shape, "{} must have shape of (N,)! Got {}".format(
-                "sigmas" if use_sigma else "alphas", dens.shape)
-            if t_starts.is_cuda and dens.dtype == torch.float32:
-                ray_indices, t_starts, t_ends = _visibility_compact(
-                    t_starts, t_ends, dens.detach(), packed_info, from_alpha=not use_sigma,
-                    early_stop_eps=float(early_stop_eps), alpha_thre=float(alpha_thre))
-            else:
-                if use_sigma:
-                    masks = render_visibility_from_density(t_starts=t_starts, t_ends=t_ends, sigmas=dens,
-                                                           packed_info=packed_info, early_stop_eps=early_stop_eps,
-                                                           alpha_thre=alpha_thre)
-                else:
-                    masks = render_visibility_from_alpha(alphas=dens, packed_info=packed_info,
-                                                         early_stop_eps=early_stop_eps, alpha_thre=alpha_thre)
-                ray_indices, t_starts, t_ends = ray_indices[masks], t_starts[masks], t_ends[masks]
-        return ray_indices, t_starts, t_ends
+    @torch.no_grad()
+    def sampling_end(
+        self,
+        ticket,
+        sigma_fn: Optional[Callable] = None,
+        alpha_fn: Optional[Callable] = None,
+        early_stop_eps: float = 1e-4,
+        alpha_thre: float = 0.0,
+    ) -> Tuple[Tensor, Tensor, Tensor]:
+        """Second half of :meth:`sampling`: wait for the traversal's sample count, return the samples (after the
+        optional visibility filter)."""
+        res = ticket.finish()
+        # ~6% head-room over the last batch; re-measured every call
+        self._capacity_hint = res.n_samples + (res.n_samples >> 4) + 1024
+        return self._drop_invisible(res.ray_indices, res.t_starts, res.t_ends, res.packed_info, sigma_fn, alpha_fn,
+                                    early_stop_eps, alpha_thre)
+
+    @staticmethod
+    def _ray_planes(rays_o, near_plane, far_plane, t_min, t_max, stratified, render_step_size, always: bool):
+        """Per-ray near / far planes (reference occ_grid.py:152-163), or (None, None) when the two scalars do."""
+        if not (always or t_min is not None or t_max is not None or stratified):
+            return None, None  # the kernel takes the two scalars directly
+        near_planes = torch.full_like(rays_o[..., 0], fill_value=near_plane)
+        far_planes = torch.full_like(rays_o[..., 0], fill_value=far_plane)
+        if t_min is not None:
+            near_planes = torch.clamp(near_planes, min=t_min)
+        if t_max is not None:
+            far_planes = torch.clamp(far_planes, max=t_max)
+        if stratified:
+            near_planes += torch.rand_like(near_planes) * render_step_size
+        return near_planes.contiguous().float(), far_planes.contiguous().float()
+
+    def _drop_invisible(self, ray_indices, t_starts, t_ends, packed_info, sigma_fn, alpha_fn, early_stop_eps,
+                        alpha_thre):
+        """The visibility filter of `sampling` (occ_grid.py:180-220)."""
+        if not ((alpha_thre > 0.0 or early_stop_eps > 0.0) and (sigma_fn is not None or alpha_fn is not None)):
+            return ray_indices, t_starts, t_ends
+        if alpha_thre > 0.0:  # min(0, mean) can never enable the alpha test, so the mean is only needed here
+            alpha_thre = min(alpha_thre, self._occs_mean())
+        use_sigma = sigma_fn is not None
+        if t_starts.shape[0] != 0:
+            dens = (sigma_fn if use_sigma else alpha_fn)(t_starts, t_ends, ray_indices)
+        else:
+            dens = torch.empty((0,), device=t_starts.device)
+        assert dens.shape == t_starts.shape, "{} must have shape of (N,)! Got {}".format(
+            "sigmas" if use_sigma else "alphas", dens.shape)
+        if t_starts.is_cuda and dens.dtype == torch.float32:
+            return _visibility_compact(t_starts, t_ends, dens.detach(), packed_info, from_alpha=not use_sigma,
+                                       early_stop_eps=float(early_stop_eps), alpha_thre=float(alpha_thre))
+        if use_sigma:
+            masks = render_visibility_from_density(t_starts=t_starts, t_ends=t_ends, sigmas=dens,
+                                                   packed_info=packed_info, early_stop_eps=early_stop_eps,
+                                                   alpha_thre=alpha_thre)
+        else:
+            masks = render_visibility_from_alpha(alphas=dens, packed_info=packed_info,
+                                                 early_stop_eps=early_stop_eps, alpha_thre=alpha_thre)
+        return ray_indices[masks], t_starts[masks], t_ends[masks]
 
     def _occs_mean(self) -> float:
         """`occs.mean()` (reference occ_grid.py:183), cached per version of the buffer: the reference pays a

@@ -119,6 +119,7 @@ class _MarchScratch:
         self.totals_dev = torch.zeros(4, dtype=torch.int64, device=device)
         self.totals_host = torch.zeros(4, dtype=torch.int64).pin_memory()
         self.event = torch.cuda.Event()
+        self.busy = False
         self.reserve(2 * n_rays + 1024)
 
     def reserve(self, run_capacity: int) -> None:
@@ -129,18 +130,26 @@ class _MarchScratch:
                                          dtype=torch.uint8, device=self.device)
 
 
-_scratch_cache: Dict[tuple, _MarchScratch] = {}
+_scratch_cache: Dict[tuple, list] = {}
 
 
-def _scratch(device, n_rays: int) -> _MarchScratch:
+def _scratch_acquire(device, n_rays: int) -> _MarchScratch:
+    """A workspace nobody is marching into.  One per (device, n_rays) in the usual one-call-at-a-time use; a
+    second one is made when a march is still in flight (sampling_begin without its sampling_end yet)."""
     key = (device, n_rays)
-    s = _scratch_cache.get(key)
-    if s is None:
+    pool = _scratch_cache.get(key)
+    if pool is None:
         if len(_scratch_cache) >= 8:
             _scratch_cache.clear()
-        s = _MarchScratch(device, n_rays)
-        _scratch_cache[key] = s
-    return s
+        pool = _scratch_cache[key] = []
+    for sc in pool:
+        if not sc.busy:
+            sc.busy = True
+            return sc
+    sc = _MarchScratch(device, n_rays)
+    sc.busy = True
+    pool.append(sc)
+    return sc
 
 
 class _MarchResult:
@@ -148,107 +157,133 @@ class _MarchResult:
                  "intervals", "samples", "terminate_planes")
 
 
-def _march(rays_o: Tensor, rays_d: Tensor, binaries: Tensor, aabbs: Tensor, near_planes: Optional[Tensor],
-           far_planes: Optional[Tensor], step_size: float, t_sorted: Optional[Tensor], t_indices: Optional[Tensor],
-           hits: Optional[Tensor], want_intervals: bool, want_terminate: bool,
-           capacity_hint: int = 0, near_plane: float = 0.0, far_plane: float = float("inf")) -> _MarchResult:
-    """Constant-step traversal: march -> expand, with ONE host synchronisation.
+class _MarchJob:
+    """Constant-step traversal: march -> expand, with ONE host synchronisation, in two halves.
 
-    `near_planes` / `far_planes` may both be None: every ray then uses the scalars.
-
-    With a `capacity_hint` (size of the previous batch plus head-room) the expand
-    kernels are queued behind the march before the host waits for the totals; only if
-    the batch outgrew the hint (or the run pool) is the cheap tail re-run.
+    `begin()` queues the march and, given a `capacity_hint` (size of the previous batch plus head-room), the
+    expand kernels behind it; `finish()` waits for the totals, re-runs the cheap tail only if the batch outgrew
+    the hint (or the run pool) and returns the result.  `near_planes` / `far_planes` may both be None: every ray
+    then uses the scalars.  The job keeps its inputs alive and owns its workspace until `finish()`.
     """
-    device = rays_o.device
-    n_rays = rays_o.shape[0]
-    n_grids, rx, ry, rz = (int(s) for s in binaries.shape)
-    occ = _packed_grid(binaries)
-    if n_grids > 1 and t_sorted is None:
-        t_sorted = torch.empty((n_rays, 2 * n_grids), dtype=torch.float32, device=device)
-        t_indices = torch.empty((n_rays, 2 * n_grids), dtype=torch.int64, device=device)
-        hits = torch.empty((n_rays, n_grids), dtype=torch.bool, device=device)
-        if n_rays > 0:
-            _lib.call("nfa_intersect_sorted", device, n_rays, _lib.ptr(rays_o), _lib.ptr(rays_d), n_grids,
-                      _lib.ptr(aabbs), _lib.ptr(t_sorted), _lib.ptr(t_indices), _lib.ptr(hits))
-    sc = _scratch(device, n_rays)
-    term = torch.empty(n_rays, dtype=torch.float32, device=device) if want_terminate else None
-    stream = torch.cuda.current_stream(device)
-    step_size = float(step_size)
 
-    def march():
-        _lib.call("nfa_march", device, n_rays, _lib.ptr(rays_o), _lib.ptr(rays_d), _lib.ptr(near_planes),
-                  _lib.ptr(far_planes), float(near_plane), float(far_plane), n_grids, rx, ry, rz, _lib.ptr(occ.words),
+    def __init__(self, rays_o: Tensor, rays_d: Tensor, binaries: Tensor, aabbs: Tensor, near_planes: Optional[Tensor],
+                 far_planes: Optional[Tensor], step_size: float, t_sorted: Optional[Tensor],
+                 t_indices: Optional[Tensor], hits: Optional[Tensor], want_intervals: bool, want_terminate: bool,
+                 capacity_hint: int = 0, near_plane: float = 0.0, far_plane: float = float("inf")):
+        self.device = device = rays_o.device
+        self.n_rays = n_rays = rays_o.shape[0]
+        self.shape = tuple(int(s) for s in binaries.shape)
+        n_grids = self.shape[0]
+        self.occ = _packed_grid(binaries)
+        if n_grids > 1 and t_sorted is None:
+            t_sorted = torch.empty((n_rays, 2 * n_grids), dtype=torch.float32, device=device)
+            t_indices = torch.empty((n_rays, 2 * n_grids), dtype=torch.int64, device=device)
+            hits = torch.empty((n_rays, n_grids), dtype=torch.bool, device=device)
+            if n_rays > 0:
+                _lib.call("nfa_intersect_sorted", device, n_rays, _lib.ptr(rays_o), _lib.ptr(rays_d), n_grids,
+                          _lib.ptr(aabbs), _lib.ptr(t_sorted), _lib.ptr(t_indices), _lib.ptr(hits))
+        self.inputs = (rays_o, rays_d, aabbs, near_planes, far_planes, t_sorted, t_indices, hits)
+        self.planes = (float(near_plane), float(far_plane))
+        self.step_size = float(step_size)
+        self.want_intervals, self.capacity_hint = want_intervals, int(capacity_hint)
+        self.term = torch.empty(n_rays, dtype=torch.float32, device=device) if want_terminate else None
+        self.packed_info = torch.empty((n_rays, 2), dtype=torch.int64, device=device)
+        self.sc = _scratch_acquire(device, n_rays)
+        self.bufs, self.cap = None, 0
+
+    def __del__(self):
+        sc = getattr(self, "sc", None)
+        if sc is not None:
+            sc.busy = False  # a ticket that was dropped without sampling_end()
+
+    def _launch_march(self) -> None:
+        rays_o, rays_d, aabbs, near_planes, far_planes, t_sorted, t_indices, hits = self.inputs
+        n_grids, rx, ry, rz = self.shape
+        sc, occ = self.sc, self.occ
+        _lib.call("nfa_march", self.device, self.n_rays, _lib.ptr(rays_o), _lib.ptr(rays_d), _lib.ptr(near_planes),
+                  _lib.ptr(far_planes), self.planes[0], self.planes[1], n_grids, rx, ry, rz, _lib.ptr(occ.words),
                   _lib.ptr(occ.coarse), _lib.ptr(occ.bounds), _lib.ptr(aabbs), _lib.ptr(t_sorted), _lib.ptr(t_indices),
-                  _lib.ptr(hits), step_size, sc.run_capacity, _lib.ptr(sc.workspace), _lib.ptr(sc.totals_dev),
-                  _lib.ptr(sc.totals_host), _lib.ptr(term))
-        sc.event.record(stream)
+                  _lib.ptr(hits), self.step_size, sc.run_capacity, _lib.ptr(sc.workspace), _lib.ptr(sc.totals_dev),
+                  _lib.ptr(sc.totals_host), _lib.ptr(self.term))
+        sc.event.record()
 
-    def read_totals():
-        # wait for the totals only: kernels queued behind the copy (the speculative expand)
-        # keep running while the host prepares the next launches
+    def _read_totals(self):
+        # wait for the totals only: kernels queued behind the march (the speculative expand) keep running while
+        # the host prepares the next launches
         if _lib.idle_tasks:
             _lib.run_idle_tasks()  # deferred host work fills the wait for the march
-        sc.event.synchronize()
-        n, runs, _, stuck = (int(v) for v in sc.totals_host.tolist())
+        self.sc.event.synchronize()
+        n, runs, _, stuck = (int(v) for v in self.sc.totals_host.tolist())
         if stuck:
             raise RuntimeError(
-                f"traverse_grids: step_size={step_size} is below the float32 resolution of the marching "
+                f"traverse_grids: step_size={self.step_size} is below the float32 resolution of the marching "
                 f"distance on {stuck} ray(s); the march cannot advance (the reference would not terminate).")
         return n, runs
 
-    packed_info = torch.empty((n_rays, 2), dtype=torch.int64, device=device)
-
-    def expand_samples(cap):
+    def _expand_samples(self, cap: int):
+        device, sc = self.device, self.sc
         ri = torch.empty(cap, dtype=torch.int64, device=device)
         ts = torch.empty(cap, dtype=torch.float32, device=device)
         te = torch.empty(cap, dtype=torch.float32, device=device)
-        _lib.call("nfa_expand_samples", device, n_rays, sc.run_capacity, _lib.ptr(sc.workspace),
-                  _lib.ptr(sc.totals_dev), step_size, cap, _lib.ptr(packed_info), _lib.ptr(ri), _lib.ptr(ts),
+        _lib.call("nfa_expand_samples", device, self.n_rays, sc.run_capacity, _lib.ptr(sc.workspace),
+                  _lib.ptr(sc.totals_dev), self.step_size, cap, _lib.ptr(self.packed_info), _lib.ptr(ri), _lib.ptr(ts),
                   _lib.ptr(te))
         return ri, ts, te
 
-    res = _MarchResult()
-    res.terminate_planes = term
-    res.intervals = res.samples = None
+    def begin(self) -> "_MarchJob":
+        self._launch_march()
+        if not self.want_intervals and self.capacity_hint > 0:
+            self.cap = self.capacity_hint
+            self.bufs = self._expand_samples(self.cap)  # speculative: queued before the sync
+        return self
 
-    march()
-    bufs, cap = None, 0
-    if not want_intervals and capacity_hint > 0:
-        cap = int(capacity_hint)
-        bufs = expand_samples(cap)  # speculative: queued before the sync
-    n, runs = read_totals()
-    if runs > sc.run_capacity:  # run pool overflow: rare (very fragmented grids); re-march with room
-        sc.reserve(runs + (runs >> 2) + 1024)
-        march()
-        n, runs = read_totals()
-        bufs = None
-    if not want_intervals:
-        if bufs is None or n > cap:
-            bufs = expand_samples(n)
-        ri, ts, te = bufs
-        res.ray_indices, res.t_starts, res.t_ends = ri[:n], ts[:n], te[:n]
-    else:
-        e = n + runs
-        iv_pi = torch.empty((n_rays, 2), dtype=torch.int64, device=device)
-        iv_vals = torch.empty(e, dtype=torch.float32, device=device)
-        iv_ray = torch.empty(e, dtype=torch.int64, device=device)
-        iv_left = torch.empty(e, dtype=torch.bool, device=device)
-        iv_right = torch.empty(e, dtype=torch.bool, device=device)
-        sm_vals = torch.empty(n, dtype=torch.float32, device=device)
-        sm_ray = torch.empty(n, dtype=torch.int64, device=device)
-        sm_valid = torch.empty(n, dtype=torch.bool, device=device)
-        _lib.call("nfa_expand_intervals", device, n_rays, sc.run_capacity, _lib.ptr(sc.workspace),
-                  _lib.ptr(sc.totals_dev), step_size, e, n, _lib.ptr(iv_pi), _lib.ptr(iv_vals), _lib.ptr(iv_ray),
-                  _lib.ptr(iv_left), _lib.ptr(iv_right), _lib.ptr(packed_info), _lib.ptr(sm_vals), _lib.ptr(sm_ray),
-                  _lib.ptr(sm_valid))
-        res.intervals = RayIntervals(vals=iv_vals, packed_info=iv_pi, ray_indices=iv_ray, is_left=iv_left,
-                                     is_right=iv_right)
-        res.samples = RaySamples(vals=sm_vals, packed_info=packed_info, ray_indices=sm_ray, is_valid=sm_valid)
-        res.ray_indices = sm_ray
-    res.n_samples, res.n_runs, res.packed_info = n, runs, packed_info
-    _stash_packed_info(res.ray_indices, packed_info, n_rays)
-    return res
+    def finish(self) -> _MarchResult:
+        device, n_rays, sc, packed_info = self.device, self.n_rays, self.sc, self.packed_info
+        res = _MarchResult()
+        res.terminate_planes = self.term
+        res.intervals = res.samples = None
+        try:
+            n, runs = self._read_totals()
+            if runs > sc.run_capacity:  # run pool overflow: rare (very fragmented grids); re-march with room
+                sc.reserve(runs + (runs >> 2) + 1024)
+                self._launch_march()
+                n, runs = self._read_totals()
+                self.bufs = None
+            if not self.want_intervals:
+                if self.bufs is None or n > self.cap:
+                    self.bufs = self._expand_samples(n)
+                ri, ts, te = self.bufs
+                res.ray_indices, res.t_starts, res.t_ends = ri[:n], ts[:n], te[:n]
+            else:
+                e = n + runs
+                iv_pi = torch.empty((n_rays, 2), dtype=torch.int64, device=device)
+                iv_vals = torch.empty(e, dtype=torch.float32, device=device)
+                iv_ray = torch.empty(e, dtype=torch.int64, device=device)
+                iv_left = torch.empty(e, dtype=torch.bool, device=device)
+                iv_right = torch.empty(e, dtype=torch.bool, device=device)
+                sm_vals = torch.empty(n, dtype=torch.float32, device=device)
+                sm_ray = torch.empty(n, dtype=torch.int64, device=device)
+                sm_valid = torch.empty(n, dtype=torch.bool, device=device)
+                _lib.call("nfa_expand_intervals", device, n_rays, sc.run_capacity, _lib.ptr(sc.workspace),
+                          _lib.ptr(sc.totals_dev), self.step_size, e, n, _lib.ptr(iv_pi), _lib.ptr(iv_vals),
+                          _lib.ptr(iv_ray), _lib.ptr(iv_left), _lib.ptr(iv_right), _lib.ptr(packed_info),
+                          _lib.ptr(sm_vals), _lib.ptr(sm_ray), _lib.ptr(sm_valid))
+                res.intervals = RayIntervals(vals=iv_vals, packed_info=iv_pi, ray_indices=iv_ray, is_left=iv_left,
+                                             is_right=iv_right)
+                res.samples = RaySamples(vals=sm_vals, packed_info=packed_info, ray_indices=sm_ray, is_valid=sm_valid)
+                res.ray_indices = sm_ray
+        finally:
+            # stream order protects the workspace: whatever marches into it next is queued behind this expand
+            sc.busy = False
+            self.sc = None
+        res.n_samples, res.n_runs, res.packed_info = n, runs, packed_info
+        _stash_packed_info(res.ray_indices, packed_info, n_rays)
+        return res
+
+
+def _march(*args, **kwargs) -> _MarchResult:
+    """One synchronous pass: see :class:`_MarchJob`."""
+    return _MarchJob(*args, **kwargs).begin().finish()
 
 
 @torch.no_grad()

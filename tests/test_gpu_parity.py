@@ -774,3 +774,30 @@ def test_peer_mailbox_single_rank_roundtrip():
         parallel.PeerMailbox.shutdown()
         if created:
             dist.destroy_process_group()
+
+
+def test_sampling_begin_end_matches_sampling():
+    """The split call returns what sampling() returns, also with two traversals in flight and a filter at the end."""
+    ro, rd = scenes.ball_rays(3000)
+    est = _estimator(scenes.ball_grid(128), scenes.nested_aabbs(1))
+    o, d = T(ro), T(rd)
+    want = est.sampling(o, d, render_step_size=scenes.BALL_STEP)
+    t1 = est.sampling_begin(o, d, render_step_size=scenes.BALL_STEP)
+    t2 = est.sampling_begin(o[:1000], d[:1000], render_step_size=scenes.BALL_STEP, near_plane=3.6)
+    t3 = est.sampling_begin(o, d, render_step_size=scenes.BALL_STEP)           # same shape as t1: second workspace
+    mid = est.sampling(o[:1000], d[:1000], render_step_size=scenes.BALL_STEP, near_plane=3.6)  # a plain call in between
+    got1, got3, got2 = est.sampling_end(t1), est.sampling_end(t3), est.sampling_end(t2)
+    for a, b in zip(want, got1):
+        assert torch.equal(a, b)
+    for a, b in zip(want, got3):
+        assert torch.equal(a, b)
+    for a, b in zip(mid, got2):
+        assert torch.equal(a, b)
+    sig = lambda ts, te, ri: 4.0 + 0.0 * ts
+    f_want = est.sampling(o, d, sigma_fn=sig, render_step_size=scenes.BALL_STEP, early_stop_eps=1e-2)
+    f_got = est.sampling_end(est.sampling_begin(o, d, render_step_size=scenes.BALL_STEP), sigma_fn=sig, early_stop_eps=1e-2)
+    for a, b in zip(f_want, f_got):
+        assert torch.equal(a, b)
+    assert f_got[0].numel() < want[0].numel()
+    with pytest.raises(ValueError):
+        est.sampling_begin(o.cpu(), d.cpu())
