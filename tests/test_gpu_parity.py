@@ -793,7 +793,7 @@ def test_sampling_begin_end_matches_sampling():
         assert torch.equal(a, b)
     for a, b in zip(mid, got2):
         assert torch.equal(a, b)
-    sig = lambda ts, te, ri: 4.0 + 0.0 * ts
+    sig = lambda ts, te, ri: 20.0 + 0.0 * ts  # opaque after ~0.23 units: most of every ray is dropped
     f_want = est.sampling(o, d, sigma_fn=sig, render_step_size=scenes.BALL_STEP, early_stop_eps=1e-2)
     f_got = est.sampling_end(est.sampling_begin(o, d, render_step_size=scenes.BALL_STEP), sigma_fn=sig, early_stop_eps=1e-2)
     for a, b in zip(f_want, f_got):
