@@ -15,9 +15,11 @@
  * -ffp-contract=off so the compiler adds no contractions of its own.
  *
  * Parity status: pinned.  tests/golden/ holds vectors produced by the
- * reference CUDA build on a B200 (oracle/gen_golden_gpu.py) and the
- * reference's own test / docstring known-answer vectors; tests/test_oracle_*.py
- * check this file against all of them.
+ * reference CUDA build on a B200 (oracle/gen_golden_gpu.py for traversal,
+ * compositing and scans, oracle/gen_golden_pdf_gpu.py for importance sampling,
+ * searchsorted and PropNetEstimator) and the reference's own test / docstring
+ * known-answer vectors; tests/test_oracle_*.py and tests/test_pdf_cpu.py check
+ * this file against all of them.
  */
 #include <math.h>
 #include <stdint.h>
