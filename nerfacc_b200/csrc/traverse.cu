@@ -6,16 +6,22 @@
 //
 //   occ_pack_kernel   bool grid -> 4x4x4 brick words + 1-bit/brick mip   (cached per grid version)
 //   march_kernel      1 thread / ray, 128 rays / CTA.  Ray tile and brick mip staged
-//                     into shared memory with cp.async.bulk (TMA 1-D) + mbarrier.
-//                     Phase 1: pure DDA walk recording occupied stretches (divergent
-//                     but cheap); phase 2: closed-form lattice seeks, all lanes in
-//                     step (march.cuh).  Runs go to a pool through a warp-aggregated
+//                     into shared memory with cp.async.bulk (TMA 1-D) + mbarrier; the
+//                     tile's rays are ordered by expected walk length so that the lanes
+//                     of a warp finish together.  Phase 1: pure DDA walk recording
+//                     occupied stretches (divergent but cheap); phase 2: closed-form
+//                     lattice seeks, all lanes in step (march.cuh).  Runs go to a pool through a warp-aggregated
 //                     atomic cursor; per-ray counts, per-tile sums and (last CTA) the
 //                     grand totals are written for the offsets pass.
 //   offsets_kernel    1 CTA / 128-ray tile: tile base from the tile sums + block scan
 //                     -> packed_info (ray-ordered offsets, so ray_indices stay sorted).
-//   expand_runs_kernel one warp per run: lanes compute their sample from the lattice
-//                     closed form and store coalesced (expand.cuh).
+//   expand_runs_vec_kernel / expand_runs_kernel
+//                     one warp per run: lanes compute their samples from the lattice
+//                     closed form (expand.cuh) and store them coalesced, 128-bit stores
+//                     when the outputs are 16-byte aligned; the <true> flavour writes the
+//                     interval-edge form traverse_grids() returns.
+//   generic_traverse_kernel  every other traverse_grids mode (march_generic.cuh).
+//   ray_aabb_kernel / intersect_sorted_kernel  slab tests (+ sorted crossings of nested boxes).
 //
 // No tensor cores: the path has no dense contraction; it is bound by dependent
 // f32 chains (march) and by HBM stores (expand).  See DESIGN.md.
