@@ -34,8 +34,23 @@ def test_public_signatures_match_reference():
     assert [n for n, _ in _params(nfa.traverse_grids)] == [
         "rays_o", "rays_d", "binaries", "aabbs", "near_planes", "far_planes", "step_size", "cone_angle",
         "traverse_steps_limit", "over_allocate", "rays_mask", "t_sorted", "t_indices", "hits"]
+    # pdf.py:12-15, :64-69; estimators/prop_net.py:37-52, :131, :156-161, :196-198; losses.py:7-13
+    assert _params(nfa.searchsorted) == [("sorted_sequence", "<req>"), ("values", "<req>")]
+    assert _params(nfa.importance_sampling) == [("intervals", "<req>"), ("cdfs", "<req>"),
+                                                ("n_intervals_per_ray", "<req>"), ("stratified", False)]
+    assert _params(nfa.PropNetEstimator.sampling)[1:] == [
+        ("prop_sigma_fns", "<req>"), ("prop_samples", "<req>"), ("num_samples", "<req>"), ("n_rays", "<req>"),
+        ("near_plane", "<req>"), ("far_plane", "<req>"), ("sampling_type", "lindisp"), ("stratified", False),
+        ("requires_grad", False)]
+    assert _params(nfa.PropNetEstimator.compute_loss)[1:] == [("trans", "<req>"), ("loss_scaler", 1.0)]
+    assert _params(nfa.PropNetEstimator.update_every_n_steps)[1:] == [("trans", "<req>"), ("requires_grad", False),
+                                                                      ("loss_scaler", 1.0)]
+    from nerfacc.estimators.prop_net import get_proposal_requires_grad_fn
+    assert _params(get_proposal_requires_grad_fn) == [("target", 5.0), ("num_steps", 1000)]
+    assert [n for n, _ in _params(nfa.distortion)] == ["weights", "t_starts", "t_ends", "ray_indices", "n_rays"]
     import nerfacc
     assert nerfacc.OccGridEstimator is nfa.OccGridEstimator and nerfacc.rendering is nfa.rendering
+    assert nerfacc.PropNetEstimator is nfa.PropNetEstimator and nerfacc.importance_sampling is nfa.importance_sampling
 
 
 def test_estimator_buffers_and_state_dict():
