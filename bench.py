@@ -46,9 +46,15 @@ METRIC = "ray-samples/sec (traverse+composite fwd+bwd)"
 RAYS_PER_GPU = 65536
 GRID_RES = 128
 
+def workload_name() -> str:
+    """The one workload both arms run (the driver compares the strings): config 2 of BASELINE.json."""
+    return (f"{GRID_RES}^3 occ-grid (ball, 6.5% occupied), {RAYS_PER_GPU} rays/GPU, ~130 samples/ray, "
+            "traverse + composite fwd+bwd")
+
+
 # algorithmic bytes (SURVEY.md 8d / DESIGN.md "Roofline")
 B_TRAVERSE, B_FWD, B_BWD, B_RAY = 16, 44, 48, 88
-LOSS_LAG = int(os.environ.get("NFA_BENCH_LOSS_LAG", "1"))  # steps between starting the loss all-reduce and consuming its result (N > 1)
+LOSS_LAG = int(os.environ.get("NFA_BENCH_LOSS_LAG", "2"))  # steps between starting the loss all-reduce and consuming its result (N > 1)
 CLOCK_LOAD_STEPS = int(os.environ.get("NFA_BENCH_CLOCK_LOAD_STEPS", "1500"))  # ~0.5 s of untimed steps in front of the value arm so nvidia-smi samples fall under load
 COLLECTIVE = os.environ.get("NFA_BENCH_NO_COLLECTIVE", "0") == "0"  # debugging aid: time N ranks without the all-reduce
 LOSS_TRANSPORT = os.environ.get("NFA_BENCH_LOSS_TRANSPORT", "peer")  # "peer": NVLink mailbox (csrc/peer.cu); "nccl": dist.all_reduce
@@ -57,9 +63,9 @@ LOSS_DEFER = os.environ.get("NFA_BENCH_LOSS_DEFER", "1") != "0"  # park its host
 
 
 def load_traffic(kernel, n_samples):
-    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/r1_traffic.json), or None when
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/r2_traffic.json), or None when
     the capture was taken on a different sample count."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r2_traffic.json")
     try:
         with open(path) as f:
             t = json.load(f)
@@ -188,6 +194,129 @@ def cpu_oracle_step(orc, ro, rd, bins, aabbs, step_size, sig_seed=43):
     return n, time.perf_counter() - t0 - t_gen
 
 
+def bench_config(n_samples: int, step_size: float, world: int) -> dict:
+    """`config` of the JSON line -- identical in both arms (the driver compares them)."""
+    return {"workload": workload_name(), "samples_per_ray": round(n_samples / RAYS_PER_GPU, 1),
+            "n_samples_per_gpu": int(n_samples), "render_step_size": step_size, "parallelism": f"ray-shard dp{world}"}
+
+
+def _import_reference():
+    """The UNMODIFIED reference package installed under baseline/_ref (pip --target), or None.
+    It shadows nothing of ours: bench.py imports `nerfacc_b200`, never the `nerfacc` alias."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "nerfacc")):
+        return None, "baseline/_ref is not installed"
+    if "nerfacc" in sys.modules and ref_dir not in (getattr(sys.modules["nerfacc"], "__file__", "") or ""):
+        return None, "another `nerfacc` module is already imported"
+    sys.path.insert(0, ref_dir)
+    try:
+        import nerfacc as ref
+        assert ref_dir in ref.__file__
+        return ref, None
+    except Exception as ex:  # missing dependency, ABI mismatch of the prebuilt csrc.so, ...
+        return None, f"{type(ex).__name__}: {ex}"
+    finally:
+        sys.path.remove(ref_dir)
+
+
+def time_reference_cuda(dev, ro_d, rd_d, step_size, R, N_ours, iters=10, warmup=3):
+    """the reference's own CUDA build, same scene, same step (sampling + rendering + MSE +
+    backward) through ITS public API, in this process right after our timed region; CUDA events."""
+    ref, why = _import_reference()
+    if ref is None:
+        return {"unavailable": why}
+    try:
+        from nerfacc_b200 import scenes
+        est = ref.OccGridEstimator(torch.from_numpy(scenes.ROI_AABB), resolution=GRID_RES).to(dev)
+        est.binaries = torch.from_numpy(scenes.ball_grid(GRID_RES)).to(dev)
+        ri, ts, te = est.sampling(ro_d, rd_d, render_step_size=step_size)
+        N = ri.numel()
+        g = torch.Generator(device="cpu").manual_seed(43)
+        sig = (5 * torch.rand(N, generator=g)).to(dev).requires_grad_(True)
+        rgb = torch.rand(N, 3, generator=g).to(dev).requires_grad_(True)
+        tgt = torch.rand(R, 3, generator=g).to(dev)
+
+        def sampling():
+            return est.sampling(ro_d, rd_d, render_step_size=step_size)
+
+        def render(ri_, ts_, te_):
+            col, _, _, _ = ref.rendering(ts_, te_, ri_, n_rays=R, rgb_sigma_fn=lambda a, b, c: (rgb, sig))
+            sig.grad = None
+            rgb.grad = None
+            torch.nn.functional.mse_loss(col, tgt).backward()
+
+        def timed(fn):
+            for _ in range(warmup):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / iters
+
+        ms_step = timed(lambda: render(*sampling()))
+        ms_samp = timed(sampling)
+        ms_rend = timed(lambda: render(ri, ts, te))
+        return {"impl": "reference CUDA build (baseline/_ref, unmodified, its own public API)", "n_samples": N,
+                "same_samples_as_ours": bool(N == N_ours), "ms_per_step": ms_step, "value": N / (ms_step * 1e-3),
+                "unit": "samples/s", "stages_us": {"sampling": round(ms_samp * 1e3, 1),
+                                                   "rendering_fwd_bwd": round(ms_rend * 1e3, 1)},
+                "steps": iters, "warmup": warmup}
+    except Exception as ex:
+        return {"unavailable": f"{type(ex).__name__}: {ex}"}
+
+
+def time_reference_cpu_torch(n_rays=4096, n_samples=128, iters=20, warmup=3):
+    """BASELINE.json config 1 / BASELINE.md B2: the reference's pure-PyTorch CPU path -- batched [4096,128]
+    `rendering` forward + backward on host tensors, uniform sigma = 5 -- on this box's host cores."""
+    ref, why = _import_reference()
+    if ref is None:
+        return {"unavailable": why}
+    try:
+        import nerfacc.volrend as rv
+        rv.is_cub_available = lambda: True  # reach the batched branch without touching the CUDA module (B2)
+        from nerfacc_b200 import scenes
+        threads_before = torch.get_num_threads()
+        cores = len(os.sched_getaffinity(0))
+        torch.set_num_threads(max(1, cores))
+        ro, rd = scenes.ball_rays(n_rays)
+        # uniform bins over each ray's chord through the ball of radius 0.5
+        o, d = torch.from_numpy(ro).double(), torch.from_numpy(rd).double()
+        bq = (o * d).sum(-1)
+        disc = (bq * bq - ((o * o).sum(-1) - 0.25)).clamp_min(0).sqrt()
+        t0, t1 = (-bq - disc), (-bq + disc)
+        edges = t0[:, None] + (t1 - t0)[:, None] * torch.linspace(0, 1, n_samples + 1, dtype=torch.float64)[None]
+        t_starts, t_ends = edges[:, :-1].float().contiguous(), edges[:, 1:].float().contiguous()
+        g = torch.Generator().manual_seed(44)
+        sig = torch.full((n_rays, n_samples), 5.0, requires_grad=True)
+        rgb = torch.rand(n_rays, n_samples, 3, generator=g).requires_grad_(True)
+
+        def step():
+            col, op, dep, _ = ref.rendering(t_starts, t_ends, rgb_sigma_fn=lambda a, b, c: (rgb, sig))
+            sig.grad = None
+            rgb.grad = None
+            (col.sum() + op.sum() + dep.sum()).backward()
+
+        for _ in range(warmup):
+            step()
+        t = time.perf_counter()
+        for _ in range(iters):
+            step()
+        sec = (time.perf_counter() - t) / iters
+        out = {"impl": "reference pure-PyTorch CPU path (baseline/_ref nerfacc.rendering, batched, config 1)",
+               "workload": f"{GRID_RES}^3-scene chords, {n_rays} rays x {n_samples} samples, uniform sigma, fwd+bwd",
+               "value": n_rays * n_samples / sec, "unit": "samples/s", "ms_per_step": sec * 1e3,
+               "cpu_count": os.cpu_count(), "cores_usable": cores, "torch_num_threads": torch.get_num_threads(),
+               "steps": iters, "warmup": warmup}
+        torch.set_num_threads(threads_before)
+        return out
+    except Exception as ex:
+        return {"unavailable": f"{type(ex).__name__}: {ex}"}
+
+
 def run_cpu_arm(args, rank, world):
     """`--impl reference`: CPU arm.  Rank 0 only."""
     if rank != 0:
@@ -212,9 +341,10 @@ def run_cpu_arm(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{GRID_RES}^3 occ-grid ball scene, {RAYS_PER_GPU} rays/GPU, ~128 samples/ray, traverse + "
-                               "composite fwd+bwd; CPU arm runs a bounded sample", "sample": sample},
+        "config": bench_config(tot_n // max(args.steps, 1) * (RAYS_PER_GPU // n_rays), scenes.BALL_STEP, args.gpus),
         "cpu_baseline": {"value": v, "unit": "samples/s", "cores": orc.num_threads(), "kind": "port", "sample": sample},
+        # config 1 of BASELINE.json: the one CPU implementation the reference itself has (batched rendering)
+        "cpu_baseline_torch": time_reference_cpu_torch(),
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -228,6 +358,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-cuda", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -344,6 +475,8 @@ def main():
                 done.result()
         return ri_.numel()
 
+    ranks_ms = []  # local ms/step of every rank in the most recent timed() call
+
     def timed(host_inputs: bool, steps: int, warmup: int, clocks=None, load_steps: int = 0, pipelined: bool = False):
         if clocks:
             clocks.mark_load()
@@ -372,14 +505,16 @@ def main():
         if world > 1:
             print(f"[rank {rank}] host_inputs={host_inputs} local ms/step={ms / steps:.4f}", file=sys.stderr, flush=True)
         t = torch.tensor([ms, float(n)], device=dev, dtype=torch.float64)
+        ranks_ms[:] = [ms / steps]
         if world > 1:
-            tm = t.clone()
-            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            ms, n = float(tm[0]), float(t[1])
+            every = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(every, t)
+            ranks_ms[:] = [float(x[0]) / steps for x in every]  # the limiter of an N-rank step is visible here
+            ms, n = max(float(x[0]) for x in every), sum(float(x[1]) for x in every)
         return ms, float(n), _lib.launches - l0, ck
 
     ms, n_samples, launches, ck = timed(False, args.steps, args.warmup, clocks, CLOCK_LOAD_STEPS)
+    per_rank = {"min": round(min(ranks_ms), 4), "max": round(max(ranks_ms), 4), "all": [round(x, 4) for x in ranks_ms]}
     loss_route = "none (1 GPU)"
     if world > 1:
         mb = parallel.PeerMailbox._instances.get((dev.type, dev.index))
@@ -400,6 +535,8 @@ def main():
     # ---- per-kernel roofline: CUDA events on the launching stream, L2 flushed before each launch
     roof = None
     cpu_base = None
+    ref_cuda = None
+    cpu_torch = None
     if rank == 0:
         peak, peak_kind = load_peaks()
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -420,8 +557,8 @@ def main():
                 tot += a.elapsed_time(c)
             return tot / reps * 1e-3
 
-        # The two compositing kernels are timed as KERNELS: launched straight through the C ABI with the argument
-        # lists nerfacc_b200.volrend uses, so the events bracket the launch alone and not ~80 us of autograd /
+        # The kernels are timed as KERNELS: launched straight through the C ABI with the argument lists
+        # nerfacc_b200.volrend / grid use, so the events bracket the launch alone and not ~80 us of autograd /
         # Python in front of it (the GPU would sit idle inside the bracket and the host would be billed to HBM).
         f32 = dict(dtype=torch.float32, device=dev)
         sg, cl = sigmas.detach(), rgbs.detach()
@@ -439,55 +576,87 @@ def main():
             _lib.call("nfa_composite_bwd", dev, R, N, P(pi), P(ts), P(te), P(sg), 0, P(cl), None, None, 1, P(raw),
                       P(gcol), None, None, None, None, None, P(g_sg), P(g_cl))
 
+        # the two traversal kernels, launched the way OccGridEstimator.sampling launches them
+        from nerfacc_b200.grid import _MarchJob
+        job = _MarchJob(ro_d, rd_d, est.binaries, est.aabbs, None, None, step_size, None, None, None,
+                        want_intervals=False, want_terminate=False, near_plane=0.0, far_plane=1e10)
+
+        def k_march(_):
+            job._launch_march()
+
+        def k_expand(_):  # offsets + expand
+            job._expand_samples(N)
+
         def k_trav(_):
             est.sampling(ro_d, rd_d, render_step_size=step_size)
 
+        t_march, t_expand = time_call(k_march), time_call(k_expand)
+        job.sc.busy = False
+        job.sc = None
         t_fwd, t_bwd, t_trav = time_call(k_fwd), time_call(k_bwd), time_call(k_trav)
         # parity of the direct launches with the public API (same kernels, same arguments)
         with torch.no_grad():
             chk = nfa.rendering(ts, te, ri, n_rays=R, rgb_sigma_fn=lambda a, b_, c: (cl, sg))
         assert torch.equal(chk[0], c_o) and torch.equal(chk[1], o_o), "direct kernel launch differs from rendering()"
+        # algorithmic bytes per launch (SURVEY 8d per-unit figures x units per launch):
+        #   march   reads rays 24 B/ray + writes counts 8 B/ray (+ ~32 B per run record, ~1 run/ray)
+        #   expand  16 B/sample written + packed_info 16 B/ray
+        #   fwd     44 B/sample + 36 B/ray,  bwd 48 B/sample + 40 B/ray
+        # and the bytes the kernels must really move (they never read the 8 B/sample of ray_indices: the
+        # packed_info stashed by sampling() replaces it) -- `frac_dram` uses those.
         stages = {
-            "composite_bwd": (B_BWD * N + 40 * R, t_bwd),
-            "composite_fwd": (B_FWD * N + 36 * R, t_fwd),
-            "traverse(march+expand+sync)": (B_TRAVERSE * N + 48 * R, t_trav),
+            "march": (64 * R, 64 * R, t_march),
+            "expand": (B_TRAVERSE * N + 16 * R, B_TRAVERSE * N + 48 * R, t_expand),
+            "composite_fwd": (B_FWD * N + 36 * R, (B_FWD - 8) * N + 36 * R, t_fwd),
+            "composite_bwd": (B_BWD * N + 40 * R, (B_BWD - 8) * N + 40 * R, t_bwd),
         }
-        dom = max(["composite_bwd", "composite_fwd"], key=lambda k: stages[k][1])
-        by, tt = stages[dom]
+        dom = max(stages, key=lambda k: stages[k][2])  # the kernel that takes longest, whatever it is
+        by, by_real, tt = stages[dom]
+        traffic = load_traffic(dom, N)
         roof = {"bound": "hbm", "kernel": dom, "achieved": by / tt / 1e9, "peak": peak, "peak_kind": peak_kind,
                 "unit": "GB/s", "frac": by / tt / 1e9 / peak, "algorithmic_bytes": by,
-                "traffic": load_traffic(dom, N),
-                "stages_us": {k: round(v[1] * 1e6, 1) for k, v in stages.items()},
-                "stages_gbs": {k: round(v[0] / v[1] / 1e9, 1) for k, v in stages.items()},
+                "traffic": traffic,
+                "frac_algorithmic": by / tt / 1e9 / peak,
+                "frac_dram": (traffic if traffic else by_real) / tt / 1e9 / peak,
+                "frac_dram_source": "ncu dram bytes (profiles/r2_traffic.json)" if traffic else
+                                    "bytes the kernel must move (no ray_indices read)",
+                "stages_us": {k: round(v[2] * 1e6, 1) for k, v in stages.items()},
+                "stages_frac_algorithmic": {k: round(v[0] / v[2] / 1e9 / peak, 3) for k, v in stages.items()},
+                "stages_frac_dram": {k: round((load_traffic(k, N) or v[1]) / v[2] / 1e9 / peak, 3)
+                                     for k, v in stages.items()},
+                "sampling_call_us": round(t_trav * 1e6, 1),
                 "step_frac_of_roofline": ((B_TRAVERSE + B_FWD + B_BWD) * N + B_RAY * R) / (ms / args.steps * 1e-3) / 1e9 / peak}
+        del flush
+        if world == 1 and not args.no_reference_cuda:
+            ref_cuda = time_reference_cuda(dev, ro_d, rd_d, step_size, R, N)
         if not args.no_cpu_baseline:
             from oracle import oracle as orc
             orc.build()
-            os.sched_setaffinity(0, all_cpus)  # the CPU baseline may use every host core again
+            os.sched_setaffinity(0, all_cpus)  # the CPU baselines may use every host core again
             orc.set_num_threads(physical_cores(orc))
-            n_cpu = 16384
             bins, aabbs = scenes.ball_grid(GRID_RES), scenes.nested_aabbs(1)
-            cpu_oracle_step(orc, ro_all[:n_cpu], rd_all[:n_cpu], bins, aabbs, step_size)
+            ro_c, rd_c = ro_all[b:e], rd_all[b:e]  # the whole 65 536-ray batch, as the reference arm runs it
+            cpu_oracle_step(orc, ro_c, rd_c, bins, aabbs, step_size)
             tn, tsec = 0, 0.0
             t_begin = time.perf_counter()
             while tsec < 3.0 and time.perf_counter() - t_begin < 30.0:
-                n_, t_ = cpu_oracle_step(orc, ro_all[:n_cpu], rd_all[:n_cpu], bins, aabbs, step_size)
+                n_, t_ = cpu_oracle_step(orc, ro_c, rd_c, bins, aabbs, step_size)
                 tn += n_
                 tsec += t_
             cpu_base = {"value": tn / tsec, "unit": "samples/s", "cores": orc.num_threads(), "kind": "port",
-                        "sample": f"{n_cpu} rays of the same scene, repeated for ~3 s (oracle port, OpenMP over rays)"}
+                        "sample": f"all {R} rays of the same scene, repeated for ~3 s (oracle port, OpenMP over rays)"}
+            cpu_torch = time_reference_cpu_torch()
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{GRID_RES}^3 occ-grid (ball, 6.5% occupied), {RAYS_PER_GPU} rays/GPU, "
-                                   f"{N / R:.1f} samples/ray, traverse + composite fwd+bwd",
-                       "n_samples_per_gpu": N, "render_step_size": step_size, "parallelism": f"ray-shard dp{world}",
-                       "loss_all_reduce": loss_route,
-                       "l2": "per-step working set ~0.9 GB > 126 MB L2 (inputs larger than L2); per-kernel "
-                             "roofline timings flush L2 before each launch"},
+            "config": bench_config(N, step_size, world),
+            "details": {"loss_all_reduce": loss_route,
+                        "l2": "per-step working set ~0.9 GB > 126 MB L2 (inputs larger than L2); per-kernel "
+                              "roofline timings flush L2 before each launch",
+                        "per_rank_ms_per_step": per_rank},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(R * 24),
                     "d2h_bytes_per_step": 4 + 32, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
@@ -497,6 +666,8 @@ def main():
             "clocks": ck,
             "roofline": roof,
             "cpu_baseline": cpu_base,
+            "reference_cuda": ref_cuda,
+            "cpu_baseline_torch": cpu_torch,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -397,7 +397,31 @@ __global__ void __launch_bounds__(kPackTile) pack_scan_kernel(int32_t n_rays,
 // synchronising boolean mask-selects; here: mask + per-ray counts, the two-level scan of
 // pack_info, and a ballot compaction that writes the kept samples and their packed_info.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ float vis_exp_neg(float x) { return __expf(-x); }
+// exp as the reference evaluates it: ATen's exp kernel calls the CUDA math library's expf (not the ex2.approx
+// shortcut): the keep / drop decision compares T and alpha with thresholds, so the last bit matters.
+__device__ __forceinline__ float vis_exp_neg(float x) { return expf(-x); }
+
+// Inclusive scan of one 32-element block in the summation ORDER of the reference's packed scan kernel
+// (include/utils_scan.cuh:146-263, launched 16 x 32 => blocks of 2 x 16 = 32 elements): the running total of the
+// previous blocks is folded into element 0, then a Brent-Kung up-sweep / down-sweep.  Float addition is not
+// associative, and `sampling(sigma_fn=...)` thresholds the result, so the tree is reproduced step by step
+// (9 shuffles instead of the 5 of a Kogge-Stone scan; the filter is memory-bound).
+template <bool kProd>
+__device__ __forceinline__ float ref_block_scan(float x, float carry, int lane)
+{
+    if (lane == 0) x = kProd ? x * carry : x + carry;  // utils_scan.cuh:196-198
+#pragma unroll
+    for (int d = 1; d <= 16; d <<= 1) {  // up-sweep, :203-209
+        const float y = __shfl_up_sync(kFullMask, x, d);
+        if (((lane + 1) & (2 * d - 1)) == 0) x = kProd ? y * x : y + x;
+    }
+#pragma unroll
+    for (int d = 8; d >= 1; d >>= 1) {  // down-sweep, :212-218
+        const float y = __shfl_up_sync(kFullMask, x, d);
+        if (((lane + 1) & (2 * d - 1)) == d && lane + 1 > d) x = kProd ? y * x : y + x;
+    }
+    return x;
+}
 
 template <bool kAlpha>
 __global__ void __launch_bounds__(kScanWarps * 32) vis_mask_kernel(int32_t n_rays,
@@ -412,35 +436,30 @@ __global__ void __launch_bounds__(kScanWarps * 32) vis_mask_kernel(int32_t n_ray
     for (int r = blockIdx.x * kScanWarps + (threadIdx.x >> 5); r < n_rays; r += gridDim.x * kScanWarps) {
         const longlong2 pi = *reinterpret_cast<const longlong2*>(packed_info + 2 * (int64_t)r);
         const int64_t start = pi.x, n = pi.y;
-        float carry = kAlpha ? 1.0f : 0.0f;
+        float carry = kAlpha ? 1.0f : 0.0f;  // `init` of the reference kernel; then the previous blocks' total
         unsigned kept = 0;
         for (int64_t base = 0; base < n; base += 32) {
             const int64_t i = start + base + lane;
             const bool valid = base + lane < n;
             float T, a;
             if (!kAlpha) {
-                const float sd = valid ? __ldg(dens + i) * (__ldg(t_ends + i) - __ldg(t_starts + i)) : 0.f;
-                float incl = sd;
-#pragma unroll
-                for (int s = 1; s < 32; s <<= 1) {
-                    const float y = __shfl_up_sync(kFullMask, incl, s);
-                    if (lane >= s) incl += y;
-                }
-                T = vis_exp_neg(carry + (incl - sd));
-                a = 1.0f - vis_exp_neg(sd);
-                carry += __shfl_sync(kFullMask, incl, 31);
-            } else {
-                a = valid ? __ldg(dens + i) : 0.f;
-                float incl = 1.0f - a;
-#pragma unroll
-                for (int s = 1; s < 32; s <<= 1) {
-                    const float y = __shfl_up_sync(kFullMask, incl, s);
-                    if (lane >= s) incl *= y;
-                }
+                // volrend.py:271-275: sigmas_dt = sigmas * (t_ends - t_starts); alphas = 1 - exp(-sigmas_dt);
+                // trans = exp(-exclusive_sum(sigmas_dt))
+                const float sd = valid ? __fmul_rn(__ldg(dens + i), __fsub_rn(__ldg(t_ends + i), __ldg(t_starts + i))) : 0.f;
+                const float incl = ref_block_scan<false>(sd, carry, lane);
                 float excl = __shfl_up_sync(kFullMask, incl, 1);
-                if (lane == 0) excl = 1.0f;
-                T = carry * excl;
-                carry *= __shfl_sync(kFullMask, incl, 31);
+                if (lane == 0) excl = carry;
+                T = vis_exp_neg(excl);
+                a = __fsub_rn(1.0f, vis_exp_neg(sd));
+                carry = __shfl_sync(kFullMask, incl, 31);
+            } else {
+                // volrend.py:208-210: trans = exclusive_prod(1 - alphas)
+                a = valid ? __ldg(dens + i) : 0.f;
+                const float incl = ref_block_scan<true>(valid ? __fsub_rn(1.0f, a) : 1.0f, carry, lane);
+                float excl = __shfl_up_sync(kFullMask, incl, 1);
+                if (lane == 0) excl = carry;
+                T = excl;
+                carry = __shfl_sync(kFullMask, incl, 31);
             }
             const bool keep = valid && (T >= early_stop_eps) && (!(alpha_thre > 0.0f) || a >= alpha_thre);
             if (valid) mask[i] = keep ? 1 : 0;

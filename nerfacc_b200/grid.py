@@ -205,7 +205,9 @@ class _MarchJob:
                   _lib.ptr(occ.coarse), _lib.ptr(occ.bounds), _lib.ptr(aabbs), _lib.ptr(t_sorted), _lib.ptr(t_indices),
                   _lib.ptr(hits), self.step_size, sc.run_capacity, _lib.ptr(sc.workspace), _lib.ptr(sc.totals_dev),
                   _lib.ptr(sc.totals_host), _lib.ptr(self.term))
-        sc.event.record()
+        # on the stream (of THIS device) the march was launched on: the default `record()` would use the current
+        # device's stream and the totals could be read before they are written
+        sc.event.record(torch.cuda.current_stream(self.device))
 
     def _read_totals(self):
         # wait for the totals only: kernels queued behind the march (the speculative expand) keep running while

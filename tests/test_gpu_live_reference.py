@@ -1,0 +1,88 @@
+"""Live parity against the UNMODIFIED reference CUDA build (baseline/_ref) at the BASELINE.json sizes.
+
+The reference runs in a subprocess (tests/ref_runner.py) on exactly the inputs the product gets here; both
+go through the same public API.  Bars (north_star): bit-exact `ray_indices` / `packed_info` / `t_starts` /
+`t_ends` / PDF samples; 1e-5 abs on weights / colours / opacities / depths, 1e-5 abs + 1e-4 rel on gradients.
+Skipped (with the reason) where baseline/_ref cannot be imported -- it is git-ignored but travels to the GPU box.
+"""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+import nerfacc_b200 as nfa
+import ref_runner as rr
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+dev = torch.device("cuda:0")
+_cache = {}
+
+
+def reference(case):
+    if case in _cache:
+        return _cache[case]
+    if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "nerfacc")):
+        pytest.skip("baseline/_ref (the reference install) is not present")
+    path = os.path.join(tempfile.mkdtemp(prefix="nfa_ref_"), case + ".npz")
+    env = {k: v for k, v in os.environ.items() if k != "PYTHONPATH"}
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ref_runner.py"), case, path], capture_output=True,
+                       text=True, timeout=900, env=env, cwd="/tmp")
+    if r.returncode != 0:
+        pytest.skip("reference CUDA build unavailable: " + r.stderr.strip().splitlines()[-1][:300])
+    _cache[case] = dict(np.load(path))
+    os.remove(path)
+    return _cache[case]
+
+
+def test_config2_full_size_bit_exact_sampling_and_rendering():
+    ref = reference("config2")
+    got = rr.run_case(nfa, "config2", dev)
+    assert int(got["n"]) == int(ref["n"]) == 8513610
+    for k in ("packed_info", "ri", "ts", "te"):              # bit-exact
+        np.testing.assert_array_equal(got[k], ref[k], err_msg=k)
+    for k in ("colors", "opacities", "depths", "weights", "trans", "alphas"):
+        assert np.abs(got[k] - ref[k]).max() < 1e-5, k       # 1e-5 abs
+    for k in ("g_sig", "g_rgb"):
+        np.testing.assert_allclose(got[k], ref[k], atol=1e-5, rtol=1e-4, err_msg=k)
+
+
+def test_config3_256_grid_inference_bit_exact():
+    ref = reference("config3")
+    got = rr.run_case(nfa, "config3", dev)
+    assert int(got["n"]) == int(ref["n"]) and int(ref["n"]) > 200 * 262144
+    np.testing.assert_array_equal(got["packed_info"], ref["packed_info"])
+    for k in ("sha_ri", "sha_ts", "sha_te"):                  # bit-exact over all ~68 M samples
+        assert str(got[k]) == str(ref[k]), k
+    for k in ("colors", "opacities", "depths"):
+        assert np.abs(got[k] - ref[k]).max() < 1e-5, k
+
+
+def test_config4_importance_sampling_full_size_bit_exact():
+    ref = reference("config4")
+    got = rr.run_case(nfa, "config4", dev)
+    for k in ("iv_0", "sm_0", "iv_1", "sm_1"):                # plain and stratified (same generator seed)
+        assert got[k].shape == ref[k].shape
+        np.testing.assert_array_equal(got[k], ref[k], err_msg=k)
+
+
+@pytest.mark.parametrize("case", ["vis_ball", "vis_lvl4", "vis_alpha"])
+def test_visibility_filter_keeps_exactly_the_reference_samples(case):
+    """sampling(sigma_fn | alpha_fn, early_stop_eps, alpha_thre) (reference occ_grid.py:180-220): the kept set must be
+    the reference's, sample for sample -- flips are counted and must be zero."""
+    ref = reference(case)
+    got = rr.run_case(nfa, case, dev)
+    assert int(got["n_before"]) == int(ref["n_before"])
+    key = lambda d: set(zip(d["ri"].tolist(), d["ts"].view(np.uint32).tolist()))
+    a, b = key(got), key(ref)
+    flips = len(a ^ b)
+    print(f"{case}: kept {len(b)} of {int(ref['n_before'])} (reference), flipped samples: {flips}")
+    assert 0 < len(b) < int(ref["n_before"])
+    assert flips == 0
+    np.testing.assert_array_equal(got["ri"], ref["ri"])
+    np.testing.assert_array_equal(got["ts"], ref["ts"])
+    np.testing.assert_array_equal(got["te"], ref["te"])
