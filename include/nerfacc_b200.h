@@ -28,7 +28,7 @@ extern "C" {
 #define NFA_ERR_ARG (-1)         /* null pointer / negative size / inconsistent sizes */
 #define NFA_ERR_UNSUPPORTED (-2) /* valid request outside what this build implements */
 
-#define NFA_ABI_VERSION 8
+#define NFA_ABI_VERSION 9
 
 typedef void* nfa_stream_t; /* cudaStream_t */
 
@@ -61,7 +61,8 @@ int32_t nfa_intersect_sorted(int32_t n_rays, const float* rays_o, const float* r
 
 /* Derived cache of OccGridEstimator.binaries (nerfacc/estimators/occ_grid.py:73-76):
  * words  [nfa_occ_words()]        uint64, one per 4x4x4-cell brick,
- * coarse [nfa_occ_coarse_words()] uint32, one bit per brick ("any cell set"),
+ * coarse [nfa_occ_coarse_words()] uint32, two bits per brick, 16 bricks per word: bit 0 "some cell set",
+ *                                 bit 1 "all 64 cells set" (0 empty, 1 mixed, 3 full),
  * bounds [n_grids * 6]            int32, per level min xyz / max xyz (inclusive, brick units) of the
  *                                 non-empty bricks; min > max when the level is empty. */
 int64_t nfa_occ_words(int32_t n_grids, int32_t rx, int32_t ry, int32_t rz);

@@ -67,7 +67,7 @@ SIGNATURES = {
     "nfa_pack_info": (_c_i32, [_c_i64, _c_ptr, _c_i32, _c_ptr, _c_ptr, _c_ptr]),
 }
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 _lib = None
 launches = 0  # number of native kernel-launching calls made through this module (bench.py reports it)

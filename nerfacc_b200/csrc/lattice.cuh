@@ -53,13 +53,29 @@ struct LatPiece {
     bool stuck;      // dt < ulp(t)/2: the reference would never advance
 };
 
-// floor(a / b) for 0 <= a < 2^24, 1 <= b < 2^24.  On the device a round-toward-zero float division is
-// exact here (both operands are exact floats, and below 2^24 the float grid is at least as fine as the
-// integers, so RZ(a/b) lies in [floor(a/b), a/b]) and costs a third of the emulated integer division.
+// floor(a / b) for 0 <= a < 2^24, 1 <= b < 2^24.  On the device: one approximate reciprocal (MUFU.RCP), a
+// truncated product and an exact integer remainder that settles the last units -- a dozen instructions
+// instead of the emulated integer division (or the out-of-line round-toward-zero float division).
 NFA_HD uint32_t div_u24(uint32_t a, uint32_t b)
 {
 #ifdef __CUDA_ARCH__
-    return (uint32_t)__fdiv_rz((float)a, (float)b);
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((float)b));
+    uint32_t q = (uint32_t)__fmul_rz((float)a, r);   // off by a few units at most (both casts are exact)
+    int32_t rem = (int32_t)(a - q * b);
+    while (rem < 0) { --q; rem += (int32_t)b; }
+    while (rem >= (int32_t)b) { ++q; rem -= (int32_t)b; }
+    return q;
+#else
+    return a / b;
+#endif
+}
+
+// quotient used only as a starting guess (the caller settles it with the exact predicate)
+NFA_HD float div_estimate(float a, float b)
+{
+#ifdef __CUDA_ARCH__
+    return __fdividef(a, b);
 #else
     return a / b;
 #endif
@@ -123,26 +139,28 @@ NFA_HD bool lat_seek(const Lattice& L, float& t, float target, uint32_t& k)
         if (f_add(t, L.half) >= target) return true;
         const LatPiece p = lat_piece(L, t);
         if (p.stuck) return false;
-        if (!p.regular) {
-            const float tn = f_add(t, L.dt);
-            if (!(tn > t)) return false;
-            t = tn;
-            ++k;
-            continue;
+        if (p.regular) {
+            // estimate the step count inside this binade, then settle it with the
+            // exact predicate (monotone in j), so the estimate only affects speed.
+            const float inc_f = f_sub(lat_point(p, 1u), t);
+            const float x = div_estimate(f_sub(f_sub(target, L.half), t), inc_f);
+            uint32_t j;
+            if (!(x >= 1.0f)) j = 1u;
+            else if (x >= (float)p.jmax) j = p.jmax;
+            else j = (uint32_t)x;
+            while (j > 1u && f_add(lat_point(p, j - 1u), L.half) >= target) --j;
+            while (j < p.jmax && !(f_add(lat_point(p, j), L.half) >= target)) ++j;
+            t = lat_point(p, j);
+            k += j;
+            // not the last point of the binade: the target is reached.  At the last point the next step leaves
+            // the binade and is a real add (what the next pass of the loop would find out for itself).
+            if (j < p.jmax) return true;
+            if (f_add(t, L.half) >= target) return true;
         }
-        // estimate the step count inside this binade, then settle it with the
-        // exact predicate (monotone in j), so the estimate only affects speed.
-        const float inc_f = f_sub(lat_point(p, 1u), t);
-        const float x = f_div(f_sub(f_sub(target, L.half), t), inc_f);
-        uint32_t j;
-        if (!(x >= 1.0f)) j = 1u;
-        else if (x >= (float)p.jmax) j = p.jmax;
-        else j = (uint32_t)x;
-        if (j < 1u) j = 1u;
-        while (j > 1u && f_add(lat_point(p, j - 1u), L.half) >= target) --j;
-        while (j < p.jmax && !(f_add(lat_point(p, j), L.half) >= target)) ++j;
-        t = lat_point(p, j);
-        k += j;
+        const float tn = f_add(t, L.dt);
+        if (!(tn > t)) return false;
+        t = tn;
+        ++k;
     }
     return false;
 }

@@ -28,7 +28,8 @@ namespace nfa {
 
 // ---------------------------------------------------------------------------
 // Bit-packed occupancy: 4x4x4-cell bricks, one uint64 per brick, plus a
-// 1-bit-per-brick "any cell occupied" mip.  Derived cache of the estimator's
+// 2-bit-per-brick class mip (bit 0: some cell occupied, bit 1: all 64 cells
+// occupied; so 0 = empty, 1 = mixed, 3 = full).  Derived cache of the estimator's
 // bool `binaries` (reference estimators/occ_grid.py:73-76).
 // ---------------------------------------------------------------------------
 struct OccGeom {
@@ -50,11 +51,25 @@ NFA_HD OccGeom occ_geom(int n_grids, int rx, int ry, int rz)
 
 struct OccView {
     const uint64_t* words;   // [n_grids * wpl]
-    const uint32_t* coarse;  // [(n_grids * wpl + 31) / 32]; may live in shared memory
+    const uint32_t* coarse;  // class mip, 16 bricks per word: [(n_grids * wpl + 15) / 16]; may live in shared memory
     const int32_t* bounds;   // [n_grids][6] bounding box of the non-empty bricks (brick units,
                              // min xyz then max xyz, inclusive; min > max: level empty), or null
     OccGeom g;
 };
+
+enum : uint32_t { kBrickEmpty = 0u, kBrickMixed = 1u, kBrickFull = 3u };
+
+NFA_HD uint32_t occ_class(const uint32_t* mip, int brick)
+{
+    return (mip[brick >> 4] >> ((brick & 15) << 1)) & 3u;
+}
+
+// the 64 cell bits of a brick: only mixed bricks are read from memory
+NFA_HD uint64_t occ_brick_bits(const OccView& occ, int brick)
+{
+    const uint32_t c = occ_class(occ.coarse, brick);
+    return c == kBrickMixed ? occ.words[brick] : (c == kBrickFull ? ~0ull : 0ull);
+}
 
 // ---------------------------------------------------------------------------
 // Ray / box slab test: reference utils_grid.cuh:10-55.
@@ -152,15 +167,16 @@ struct Walk {
     float tdx, tdy, tdz;   // next crossing time per axis
     float dlx, dly, dlz;   // crossing-time increment per axis
     int remx, remy, remz;  // steps left on the axis before the walk ends (overflow index or grid edge)
-    int sgx, sgy, sgz;     // step direction per axis (-1, 0, +1)
-    // incremental occupancy cursor: current brick word + bit of the current cell inside it
+    // occupancy cursor: current brick word + bit of the current cell inside it, and what one step along an
+    // axis adds to them (0 for an axis the ray does not move along)
+    int dbx, dby, dbz;     // to `bit`: +-16, +-4, +-1
+    int sbx, sby, sbz;     // to `brick` when the step leaves the brick: +-nb[1]*nb[2], +-nb[2], +-1
     int brick;
     int bit;               // (x&3)<<4 | (y&3)<<2 | (z&3)
     uint64_t word;
     // state flags (ints, not bools: the compiler would byte-pack bools and shuffle them around)
     int in_seg;
     int open;        // inside a stretch (no EMPTY since it began)
-    int has_occ;     // the current descriptor has seen an occupied cell
     int joined;      // the current descriptor continues the previous one (SEG inside a stretch)
     int done;
     // empty-space acceleration (single level, no terminate plane wanted): see walk_open_segment
@@ -168,7 +184,8 @@ struct Walk {
     float t_stop;
     // stretch under construction.  `pend` is the skip target: while no stretch is open it
     // accumulates (max) the exits of empty cells / segment starts; once a stretch opens it is
-    // frozen and becomes that stretch's pend.
+    // frozen and becomes that stretch's pend.  `d_open` is the exit of the stretch's last occupied
+    // cell, -inf while the current descriptor has not seen one.
     float pend, d_open;
 };
 
@@ -188,26 +205,22 @@ NFA_HD void walk_init(Walk& w, const float o[3], const float d[3], float near, f
     w.tdx = w.tdy = w.tdz = 0.f;
     w.dlx = w.dly = w.dlz = 0.f;
     w.remx = w.remy = w.remz = 0;
-    w.sgx = w.sgy = w.sgz = 0;
+    w.dbx = w.dby = w.dbz = 0;
+    w.sbx = w.sby = w.sbz = 0;
     w.brick = 0;
     w.bit = 0;
     w.word = 0;
     w.in_seg = 0;
     w.open = 0;
-    w.has_occ = 0;
     w.joined = 0;
     w.done = 0;
     w.accel = 0;
     w.t_stop = INFINITY;
     w.pend = -INFINITY;
-    w.d_open = 0.f;
+    w.d_open = -INFINITY;
 }
 
-NFA_HD void walk_load_brick(Walk& w, const OccView& occ)
-{
-    const uint32_t c = occ.coarse[w.brick >> 5];
-    w.word = ((c >> (w.brick & 31)) & 1u) ? occ.words[w.brick] : 0ull;
-}
+NFA_HD void walk_load_brick(Walk& w, const OccView& occ) { w.word = occ_brick_bits(occ, w.brick); }
 
 // Steps left on one axis: until the index reaches the overflow index (reference
 // utils_grid.cuh:121-139, `current == overflow` ends the walk) or leaves the grid
@@ -292,7 +305,8 @@ NFA_HD void walk_open_segment(Walk& w, const OccView& occ, int level, float lo, 
     }
     w.tdx = s.td[0]; w.tdy = s.td[1]; w.tdz = s.td[2];
     w.dlx = s.dl[0]; w.dly = s.dl[1]; w.dlz = s.dl[2];
-    w.sgx = s.st[0]; w.sgy = s.st[1]; w.sgz = s.st[2];
+    w.dbx = s.st[0] * 16; w.dby = s.st[1] * 4; w.dbz = s.st[2];
+    w.sbx = s.st[0] * occ.g.nb[1] * occ.g.nb[2]; w.sby = s.st[1] * occ.g.nb[2]; w.sbz = s.st[2];
     w.remx = remx; w.remy = remy; w.remz = remz;
     w.brick = ((s.cur[0] >> 2) * occ.g.nb[1] + (s.cur[1] >> 2)) * occ.g.nb[2] + (s.cur[2] >> 2) + level * occ.g.wpl;
     w.bit = ((s.cur[0] & 3) << 4) | ((s.cur[1] & 3) << 2) | (s.cur[2] & 3);
@@ -362,78 +376,79 @@ NFA_HD void walk_run(Walk& w, const Boxes& boxes, const OccView& occ, Buf& buf, 
             int level;
             float lo, hi;
             if (!boxes.next(w, w.seg_i, level, lo, hi)) {
-                if (w.open) buf.put(n_desc++, w.pend, w.has_occ ? w.d_open : -INFINITY, w.joined != 0);
+                if (w.open) buf.put(n_desc++, w.pend, w.d_open, w.joined != 0);
                 w.done = 1;
                 return;
             }
             // SEG(lo)
             if (w.open) {
-                buf.put(n_desc++, w.pend, w.has_occ ? w.d_open : -INFINITY, w.joined != 0);
+                buf.put(n_desc++, w.pend, w.d_open, w.joined != 0);
                 w.pend = lo;
                 w.joined = 1;
-                w.has_occ = 0;
+                w.d_open = -INFINITY;
             } else {
                 w.pend = f_max(w.pend, lo);
             }
             walk_open_segment(w, occ, level, lo, hi, boxes.aabb(level));
             continue;
         }
-        // Cells of the current segment: the hot loop, on local scalars.  The body uses
-        // selects instead of branches -- the lanes of a warp follow unrelated rays, so every
-        // branch that depends on the ray (axis choice, occupied / empty) would be serialised.
+        // Cells of the current segment: the hot loop, on local scalars.  One pass = one cell of the reference's
+        // loop (grid.cu:184-271).  The lanes of a warp follow unrelated rays, so everything that depends on the
+        // ray (axis choice, occupied / empty, leaving the brick) is a select or a predicated instruction; the
+        // only real branches are the rare stretch boundaries and the end of the segment.
         float tdx = w.tdx, tdy = w.tdy, tdz = w.tdz;
         int remx = w.remx, remy = w.remy, remz = w.remz;
         int bit = w.bit, brick = w.brick;
         uint64_t word = w.word;
-        int open = w.open, has_occ = w.has_occ, joined = w.joined;
+        int open = w.open, joined = w.joined;
         float pend = w.pend, d_open = w.d_open;
         const float dlx = w.dlx, dly = w.dly, dlz = w.dlz, seg_hi = w.seg_hi, t_stop = w.t_stop;
-        const int sgx = w.sgx, sgy = w.sgy, sgz = w.sgz;
-        const int bx = occ.g.nb[1] * occ.g.nb[2], by = occ.g.nb[2];
+        const int dbx = w.dbx, dby = w.dby, dbz = w.dbz, sbx = w.sbx, sby = w.sby, sbz = w.sbz;
         int in_seg = 1;
         do {
             const float tt = f_min(f_min(tdx, f_min(tdy, tdz)), seg_hi);  // grid.cu:185-186
-            const int occd = (int)((word >> bit) & 1ull);
-            if (!occd && open) {  // EMPTY(tt) closes the stretch (rare)
-                buf.put(n_desc++, pend, has_occ ? d_open : -INFINITY, joined != 0);
-                pend = -INFINITY;
+            const int occd = (int)((uint32_t)(word >> bit) & 1u);
+            if (occd != open) {  // a stretch opens (its pend is frozen from here on) or closes
+                if (open) {      // EMPTY(tt) closes the stretch
+                    buf.put(n_desc++, pend, d_open, joined != 0);
+                    pend = -INFINITY;
+                } else {
+                    joined = 0;
+                }
+                open = occd;
             }
-            // OCC(tt): a stretch opens (pend frozen) or grows; EMPTY(tt): skip target moves on
-            joined = (occd && !open) ? 0 : joined;
-            pend = occd ? pend : f_max(pend, tt);
+            // OCC(tt): the stretch grows; EMPTY(tt): the skip target moves on
             d_open = occd ? tt : d_open;
-            open = occd;
-            has_occ = occd;
+            pend = occd ? pend : f_max(pend, tt);
             // utils_grid.cuh:116-142: x only if strictly smallest, else y if strictly below z, else z
             const bool mx = tdx < tdy && tdx < tdz;
             const bool my = !mx && (tdy < tdz);
             const bool mz = !mx && !my;
-            const float nx = f_add(tdx, dlx), ny = f_add(tdy, dly), nz = f_add(tdz, dlz);
-            tdx = mx ? nx : tdx;
-            tdy = my ? ny : tdy;
-            tdz = mz ? nz : tdz;
+            tdx = mx ? f_add(tdx, dlx) : tdx;
+            tdy = my ? f_add(tdy, dly) : tdy;
+            tdz = mz ? f_add(tdz, dlz) : tdz;
             remx -= mx ? 1 : 0;
             remy -= my ? 1 : 0;
             remz -= mz ? 1 : 0;
-            if ((mx ? remx : (my ? remy : remz)) == 0 || tt >= t_stop) {
+            const int rem = mx ? remx : (my ? remy : remz);
+            // move the occupancy cursor along the stepped axis: add inside the axis' 2-bit field of `bit`;
+            // a carry / borrow out of the field means the step left the brick
+            const int db = mx ? dbx : (my ? dby : dbz);
+            const int mk = mx ? 0x30 : (my ? 0x0c : 0x03);
+            const int nb = bit + db;
+            const bool crossed = ((nb ^ bit) & ~mk) != 0;
+            bit = (bit & ~mk) | (nb & mk);
+            if (rem == 0 || tt >= t_stop) {
                 in_seg = 0;  // overflow index / grid edge reached, or (accelerated) past the occupied box
-            } else {
-                // move the occupancy cursor along the stepped axis
-                const int sh = mx ? 4 : (my ? 2 : 0);
-                const int sg = mx ? sgx : (my ? sgy : sgz);
-                const int t = ((bit >> sh) & 3) + sg;
-                bit = (bit & ~(3 << sh)) | ((t & 3) << sh);
-                if ((unsigned)t > 3u) {  // crossed into the neighbouring brick
-                    brick += sg * (mx ? bx : (my ? by : 1));
-                    const uint32_t c = occ.coarse[brick >> 5];
-                    word = ((c >> (brick & 31)) & 1u) ? occ.words[brick] : 0ull;
-                }
+            } else if (crossed) {
+                brick += mx ? sbx : (my ? sby : sbz);
+                word = occ_brick_bits(occ, brick);
             }
         } while (in_seg && n_desc < cap);
         w.tdx = tdx; w.tdy = tdy; w.tdz = tdz;
         w.remx = remx; w.remy = remy; w.remz = remz;
         w.bit = bit; w.brick = brick; w.word = word;
-        w.open = open; w.has_occ = has_occ; w.joined = joined;
+        w.open = open; w.joined = joined;
         w.pend = pend; w.d_open = d_open;
         w.in_seg = in_seg;
     }

@@ -16,8 +16,7 @@ namespace nfa {
 NFA_HD bool occ_test(const OccView& v, int level, int ix, int iy, int iz)
 {
     const int b = ((ix >> 2) * v.g.nb[1] + (iy >> 2)) * v.g.nb[2] + (iz >> 2) + level * v.g.wpl;
-    if (!((v.coarse[b >> 5] >> (b & 31)) & 1u)) return false;
-    return (v.words[b] >> (((ix & 3) << 4) | ((iy & 3) << 2) | (iz & 3))) & 1ull;
+    return (occ_brick_bits(v, b) >> (((ix & 3) << 4) | ((iy & 3) << 2) | (iz & 3))) & 1ull;
 }
 
 // reference grid.cu:23-28

@@ -38,8 +38,9 @@ constexpr int32_t kBoundsMaxInit = (int32_t)0x80808080;
 
 NFA_HD int64_t occ_coarse_words(const OccGeom& g)
 {
-    // padded to a multiple of 4 words (16 bytes) so it can be moved with one bulk copy
-    const int64_t n = ((int64_t)g.n_grids * g.wpl + 31) / 32;
+    // class mip: 2 bits per brick, 16 bricks per word; padded to a multiple of 4 words (16 bytes) so it can
+    // be moved with one bulk copy
+    const int64_t n = ((int64_t)g.n_grids * g.wpl + 15) / 16;
     return (n + 3) & ~(int64_t)3;
 }
 

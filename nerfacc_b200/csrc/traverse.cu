@@ -4,7 +4,7 @@
 // nerfacc/estimators/occ_grid.py:154-177 -> nerfacc/grid.py:93-192 ->
 // nerfacc/cuda/csrc/grid.cu:320-474):
 //
-//   occ_pack_kernel   bool grid -> 4x4x4 brick words + 1-bit/brick mip   (cached per grid version)
+//   occ_pack_kernel   bool grid -> 4x4x4 brick words + 2-bit/brick class mip (cached per grid version)
 //   march_kernel      1 thread / ray, 128 rays / CTA.  Ray tile and brick mip staged
 //                     into shared memory with cp.async.bulk (TMA 1-D) + mbarrier; the
 //                     tile's rays are ordered by expected walk length so that the lanes
@@ -36,8 +36,34 @@
 
 namespace nfa {
 
-constexpr int kTileRays = 128;      // rays per CTA in the march / offsets kernels
+constexpr int kMaxTileRays = 512;   // rays per CTA in the march / offsets kernels: march_tile_rays(), <= this
 constexpr int kDescSlots = 8;       // stretch descriptors buffered per ray between the two march phases
+constexpr int kSortBuckets = 256;   // counting sort of a tile's rays by expected walk length
+
+// Rays per march CTA (= threads).  All CTAs of a batch this size are resident at once, so the kernel takes as
+// long as the SM with the most rays: pick the tile that spreads the rays most evenly over the 148 SMs
+// (65 536 rays: 147 tiles of 448 rays, one per SM, instead of 512 tiles of 128 = 4 on some SMs and 3 on
+// others); ties go to the larger tile, whose rays sort into more uniform warps.  Large batches (several
+// waves) use 256.
+__host__ __device__ inline int march_tile_rays(int32_t n_rays)
+{
+    const int kSMs = 148;
+    if (n_rays <= 32) return 32;
+    if ((int64_t)n_rays > (int64_t)kSMs * 2048) return 256;
+    int best = 128;
+    int64_t best_cost = INT64_MAX;
+    for (int t = 64; t <= kMaxTileRays; t += 32) {
+        const int64_t tiles = (n_rays + t - 1) / t;
+        const int64_t per_sm = (tiles + kSMs - 1) / kSMs;
+        if (per_sm * t > 2048) continue;  // would not be resident together
+        const int64_t cost = per_sm * t;
+        if (cost <= best_cost) {
+            best_cost = cost;
+            best = t;
+        }
+    }
+    return best;
+}
 constexpr int kExpandThreads = 256;
 
 // One run of consecutive lattice samples, as written by the march kernel (32 bytes, two 16-byte stores).
@@ -69,6 +95,7 @@ struct Workspace {
     uint32_t* cnt_runs;
     RunRec* pool;
     int n_tiles;
+    int tile_rays;
     int64_t run_capacity;
 };
 
@@ -76,7 +103,8 @@ __host__ __device__ inline int64_t align16(int64_t x) { return (x + 15) & ~(int6
 
 __host__ __device__ inline int64_t ws_bytes(int32_t n_rays, int64_t run_capacity)
 {
-    const int64_t nt = (n_rays + kTileRays - 1) / kTileRays;
+    const int tile = march_tile_rays(n_rays);
+    const int64_t nt = (n_rays + tile - 1) / tile;
     return 64 + align16(nt * (int64_t)sizeof(TileSum)) + align16((int64_t)n_rays * 4) * 2 +
            run_capacity * (int64_t)sizeof(RunRec);
 }
@@ -85,7 +113,8 @@ __host__ __device__ inline Workspace ws_view(void* base, int32_t n_rays, int64_t
 {
     Workspace w;
     char* p = (char*)base;
-    w.n_tiles = (n_rays + kTileRays - 1) / kTileRays;
+    w.tile_rays = march_tile_rays(n_rays);
+    w.n_tiles = (n_rays + w.tile_rays - 1) / w.tile_rays;
     w.run_capacity = run_capacity;
     w.done = (uint32_t*)p;
     w.cursor = (uint32_t*)(p + 4);
@@ -148,8 +177,8 @@ __global__ void __launch_bounds__(256) occ_pack_kernel(OccGeom g, const uint8_t*
                                                        int32_t* __restrict__ bounds, int64_t n_words, int64_t n_coarse)
 {
     const int64_t cells = (int64_t)g.res[0] * g.res[1] * g.res[2];
-    // one thread per brick; a warp's 32 bricks share one coarse word
-    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_coarse * 32;
+    // one thread per brick; a half-warp's 16 bricks share one word of the class mip
+    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_coarse * 16;
          b += (int64_t)gridDim.x * blockDim.x) {
         uint64_t w = 0;
         if (b < n_words) {
@@ -167,8 +196,11 @@ __global__ void __launch_bounds__(256) occ_pack_kernel(OccGeom g, const uint8_t*
                 atomicMax(bb + 3, bx); atomicMax(bb + 4, by); atomicMax(bb + 5, bz);
             }
         }
-        const uint32_t any = __ballot_sync(0xffffffffu, w != 0);
-        if ((threadIdx.x & 31) == 0) coarse[b >> 5] = any;
+        // bit 0: some cell set, bit 1: all 64 set (march.cuh occ_class)
+        uint32_t v = (w == 0 ? kBrickEmpty : (w == ~0ull ? kBrickFull : kBrickMixed)) << ((threadIdx.x & 15) << 1);
+#pragma unroll
+        for (int s = 8; s > 0; s >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, s);
+        if ((threadIdx.x & 15) == 0) coarse[b >> 4] = v;
     }
 }
 
@@ -206,14 +238,14 @@ struct MarchParams {
 
 // descriptor buffer: one shared-memory column per thread, joined flags in a register
 struct SmemBuf {
-    float* pend;   // [kDescSlots][kTileRays]
+    float* pend;   // [kDescSlots][tile]
     float* open;
     uint32_t joined_mask;
-    int tid;
+    int tid, tile;
     __device__ __forceinline__ void put(int j, float p, float o, bool jn)
     {
-        pend[j * kTileRays + tid] = p;
-        open[j * kTileRays + tid] = o;
+        pend[j * tile + tid] = p;
+        open[j * tile + tid] = o;
         joined_mask |= (jn ? 1u : 0u) << j;
     }
 };
@@ -237,33 +269,46 @@ __device__ __forceinline__ void emit_runs(const RunOut& out, uint32_t ray, const
     }
 }
 
-template <bool kSingle, bool kSmemCoarse>
-__global__ void __launch_bounds__(kTileRays) march_kernel(const MarchParams p)
+// dynamic shared memory of the march kernel (tile = blockDim.x rays):
+//   [class mip (kSmemCoarse)] [o: 3 tile f32] [d: 3 tile f32] [pend: 8 tile] [open: 8 tile] [order: tile u32]
+__host__ __device__ inline size_t march_smem_bytes(int tile, size_t coarse_bytes)
 {
-    extern __shared__ __align__(16) uint32_t s_coarse[];
-    __shared__ __align__(16) float s_o[kTileRays * 3];
-    __shared__ __align__(16) float s_d[kTileRays * 3];
-    __shared__ float s_pend[kDescSlots * kTileRays];
-    __shared__ float s_open[kDescSlots * kTileRays];
-    __shared__ __align__(8) uint64_t s_bar;
-    __shared__ unsigned long long s_red_samples[kTileRays / 32];
-    __shared__ uint32_t s_red_runs[kTileRays / 32], s_red_flags[kTileRays / 32];
-    __shared__ bool s_last;
-    __shared__ uint32_t s_sort[kTileRays];
-    static_assert(kTileRays <= 128, "the sort key packs the thread id in 7 bits");
+    return coarse_bytes + (size_t)tile * 4 * (3 + 3 + 2 * kDescSlots + 1);
+}
 
+template <bool kSingle, bool kSmemCoarse>
+__global__ void __launch_bounds__(kMaxTileRays) march_kernel(const MarchParams p)
+{
+    extern __shared__ __align__(16) uint32_t s_dyn[];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ unsigned long long s_red_samples[kMaxTileRays / 32];
+    __shared__ uint32_t s_red_runs[kMaxTileRays / 32], s_red_flags[kMaxTileRays / 32];
+    __shared__ bool s_last;
+    __shared__ uint32_t s_hist[kSortBuckets];
+
+    const int T = blockDim.x;
     const int tid = threadIdx.x, lane = tid & 31;
     const int tile = blockIdx.x;
-    const int r0 = tile * kTileRays;
-    const int nr = min(kTileRays, p.n_rays - r0);
+    const int r0 = tile * T;
+    const int nr = min(T, p.n_rays - r0);
+    uint32_t* s_coarse = s_dyn;
+    float* s_o = reinterpret_cast<float*>(s_dyn + (kSmemCoarse ? p.coarse_words : 0));
+    float* s_d = s_o + 3 * T;
+    float* s_pend = s_d + 3 * T;
+    float* s_open = s_pend + kDescSlots * T;
+    uint32_t* s_sort = reinterpret_cast<uint32_t*>(s_open + kDescSlots * T);
 
-    // ---- stage the ray tile (and the brick mip) into shared memory: TMA bulk copies + mbarrier
+    // ---- stage the ray tile (and the class mip) into shared memory: TMA bulk copies + mbarrier
     const float* g_o = p.rays_o + (int64_t)r0 * 3;
     const float* g_d = p.rays_d + (int64_t)r0 * 3;
     const uint32_t ray_bytes = (uint32_t)nr * 12u;
     const bool bulk_rays = ((ray_bytes & 15u) == 0u) && ((((uintptr_t)g_o) | ((uintptr_t)g_d)) & 15u) == 0u;
     const bool bulk_coarse = kSmemCoarse && ((((uintptr_t)p.coarse) & 15u) == 0u);
     if (tid == 0) mbar_init(&s_bar, 1);
+    if (kSingle && tid < kSortBuckets) s_hist[tid] = 0u;
+    if (kSingle && T < kSortBuckets) {
+        for (int i = tid + T; i < kSortBuckets; i += T) s_hist[i] = 0u;
+    }
     __syncthreads();
     if (tid == 0) {
         uint32_t bytes = 0;
@@ -277,53 +322,71 @@ __global__ void __launch_bounds__(kTileRays) march_kernel(const MarchParams p)
         if (bulk_coarse) bulk_g2s(s_coarse, p.coarse, (uint32_t)p.coarse_words * 4u, &s_bar);
     }
     if (!bulk_rays) {
-        for (int i = tid; i < nr * 3; i += kTileRays) {
+        for (int i = tid; i < nr * 3; i += T) {
             s_o[i] = g_o[i];
             s_d[i] = g_d[i];
         }
     }
     if (kSmemCoarse && !bulk_coarse) {
-        for (int i = tid; i < p.coarse_words; i += kTileRays) s_coarse[i] = p.coarse[i];
+        for (int i = tid; i < p.coarse_words; i += T) s_coarse[i] = p.coarse[i];
     }
     mbar_wait(&s_bar, 0);
     __syncthreads();
 
     // ---- order the tile's rays by expected walk length, so the 32 lanes of a warp finish together.
-    // A warp runs as long as its longest ray; with rays in input order 34 % of the lanes of the cell loop idle
-    // (ncu: 21 of 32 threads per instruction).  The estimate (cells crossed between the slab hits of the box
-    // the walk is confined to) only decides which thread takes which ray -- every output is indexed by ray id.
+    // A warp runs as long as its longest ray; with rays in input order a third of the lanes of the cell loop idle.
+    // The estimate (cells crossed between the slab hits of the box the walk is confined to) only decides which
+    // thread takes which ray -- every output is indexed by ray id.  Counting sort: bucket histogram with shared
+    // atomics (the order inside a bucket is arbitrary and irrelevant), one warp scans the buckets.
     int rt = tid;
     if (kSingle) {
-        uint32_t key = 0;
+        uint32_t bucket = 0;
         if (tid < nr) {
             const float* box = p.aabbs;
             const bool have_bb = p.bounds != nullptr && p.terminate == nullptr && p.bounds[0] <= p.bounds[3];
             float tn = p.near_planes ? p.near_planes[r0 + tid] : p.near_plane;
             float tf = p.far_planes ? p.far_planes[r0 + tid] : p.far_plane;
-            float cells = 0.f;
+            float cells = 0.f, span = 0.f;
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
                 const float voxel = (box[3 + a] - box[a]) / (float)p.g.res[a];
                 const float lo = have_bb ? box[a] + (float)(4 * p.bounds[a] - 1) * voxel : box[a];
                 const float hi = have_bb ? box[a] + (float)(4 * p.bounds[3 + a] + 5) * voxel : box[3 + a];
                 const float oa = s_o[tid * 3 + a], da = s_d[tid * 3 + a];
-                const float inv = 1.0f / da;
+                const float inv = __fdividef(1.0f, da);
                 const float t0 = (lo - oa) * inv, t1 = (hi - oa) * inv;
                 tn = fmaxf(tn, fminf(t0, t1));
                 tf = fminf(tf, fmaxf(t0, t1));
-                cells += fabsf(da) / voxel;
+                cells += __fdividef(fabsf(da), voxel);
+                span += __fdividef(hi - lo, voxel);  // a walk crosses at most this many cells (all three axes)
             }
-            const float est = cells * (tf - tn);
-            if (est > 0.f) key = est < 16777215.f ? (uint32_t)est : 16777215u;  // NaN / miss -> 0
+            const float est = cells * (tf - tn) * __fdividef((float)(kSortBuckets - 1), span);
+            if (est > 0.f) bucket = est < (float)(kSortBuckets - 1) ? (uint32_t)est : (uint32_t)(kSortBuckets - 1);  // NaN / miss -> 0
         }
-        const uint32_t mine = (key << 7) | (uint32_t)tid;  // unique, ties in input order
-        s_sort[tid] = mine;
+        const uint32_t pos = atomicAdd(&s_hist[bucket], 1u);
         __syncthreads();
-        int rank = 0;
-#pragma unroll 8
-        for (int j = 0; j < kTileRays; ++j) rank += s_sort[j] < mine ? 1 : 0;
+        if (tid < 32) {  // exclusive scan of the 256 bucket counts: 8 per lane + a shuffle scan
+            uint32_t c[kSortBuckets / 32], sum = 0;
+#pragma unroll
+            for (int i = 0; i < kSortBuckets / 32; ++i) {
+                c[i] = s_hist[tid * (kSortBuckets / 32) + i];
+                sum += c[i];
+            }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int sft = 1; sft < 32; sft <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, sft);
+                if (lane >= sft) incl += y;
+            }
+            uint32_t run = incl - sum;
+#pragma unroll
+            for (int i = 0; i < kSortBuckets / 32; ++i) {
+                s_hist[tid * (kSortBuckets / 32) + i] = run;
+                run += c[i];
+            }
+        }
         __syncthreads();
-        s_sort[rank] = (uint32_t)tid;
+        s_sort[s_hist[bucket] + pos] = (uint32_t)tid;
         __syncthreads();
         rt = (int)s_sort[tid];
     }
@@ -356,6 +419,7 @@ __global__ void __launch_bounds__(kTileRays) march_kernel(const MarchParams p)
     buf.open = s_open;
     buf.joined_mask = 0u;
     buf.tid = tid;
+    buf.tile = T;
     int n_desc = 0;
     const int G = p.g.n_grids;
     const int64_t rr = active ? r : 0;
@@ -372,7 +436,7 @@ __global__ void __launch_bounds__(kTileRays) march_kernel(const MarchParams p)
             RunOut out;
             out.valid = false;
             if (j < n_desc)
-                lat_consume(m, s_pend[j * kTileRays + tid], s_open[j * kTileRays + tid], (buf.joined_mask >> j) & 1u, out);
+                lat_consume(m, s_pend[j * T + tid], s_open[j * T + tid], (buf.joined_mask >> j) & 1u, out);
             emit_runs(out, (uint32_t)r, p.ws, lane);
         }
         n_desc = 0;
@@ -393,13 +457,14 @@ __global__ void __launch_bounds__(kTileRays) march_kernel(const MarchParams p)
     }
 
     // ---- tile sums, and grand totals by the last CTA to finish ------------
+    const int n_warps = T >> 5;
     unsigned long long vs = active ? m.n_samples : 0u;
     uint32_t vr = active ? m.n_runs : 0u, vf = (active && !m.ok) ? 1u : 0u;
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) {
-        vs += __shfl_xor_sync(0xffffffffu, vs, s);
-        vr += __shfl_xor_sync(0xffffffffu, vr, s);
-        vf += __shfl_xor_sync(0xffffffffu, vf, s);
+    for (int sft = 16; sft > 0; sft >>= 1) {
+        vs += __shfl_xor_sync(0xffffffffu, vs, sft);
+        vr += __shfl_xor_sync(0xffffffffu, vr, sft);
+        vf += __shfl_xor_sync(0xffffffffu, vf, sft);
     }
     if (lane == 0) {
         s_red_samples[tid >> 5] = vs;
@@ -412,7 +477,7 @@ __global__ void __launch_bounds__(kTileRays) march_kernel(const MarchParams p)
         ts.samples = 0;
         ts.runs = 0;
         ts.stuck = 0;
-        for (int k = 0; k < kTileRays / 32; ++k) {
+        for (int k = 0; k < n_warps; ++k) {
             ts.samples += s_red_samples[k];
             ts.runs += s_red_runs[k];
             ts.stuck += s_red_flags[k];
@@ -426,7 +491,7 @@ __global__ void __launch_bounds__(kTileRays) march_kernel(const MarchParams p)
     if (s_last) {
         __threadfence();
         unsigned long long a = 0, b = 0, c = 0;
-        for (int i = tid; i < p.ws.n_tiles; i += kTileRays) {
+        for (int i = tid; i < p.ws.n_tiles; i += T) {
             const volatile unsigned long long* q = (const volatile unsigned long long*)&p.ws.tiles[i];
             const unsigned long long w0 = q[0], w1 = q[1];  // {samples}, {runs | stuck << 32}
             a += w0;
@@ -434,12 +499,12 @@ __global__ void __launch_bounds__(kTileRays) march_kernel(const MarchParams p)
             c += w1 >> 32;
         }
 #pragma unroll
-        for (int s = 16; s > 0; s >>= 1) {
-            a += __shfl_xor_sync(0xffffffffu, a, s);
-            b += __shfl_xor_sync(0xffffffffu, b, s);
-            c += __shfl_xor_sync(0xffffffffu, c, s);
+        for (int sft = 16; sft > 0; sft >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, sft);
+            b += __shfl_xor_sync(0xffffffffu, b, sft);
+            c += __shfl_xor_sync(0xffffffffu, c, sft);
         }
-        __shared__ unsigned long long s_tot[3][kTileRays / 32];
+        __shared__ unsigned long long s_tot[3][kMaxTileRays / 32];
         if (lane == 0) {
             s_tot[0][tid >> 5] = a;
             s_tot[1][tid >> 5] = b;
@@ -448,7 +513,7 @@ __global__ void __launch_bounds__(kTileRays) march_kernel(const MarchParams p)
         __syncthreads();
         if (tid < 3) {
             unsigned long long v = 0;
-            for (int k = 0; k < kTileRays / 32; ++k) v += s_tot[tid][k];
+            for (int k = 0; k < n_warps; ++k) v += s_tot[tid][k];
             // totals: [0] samples, [1] runs, [2] run-pool capacity used for this call, [3] stuck rays
             p.totals[tid == 2 ? 3 : tid] = (int64_t)v;
             if (p.totals_host) p.totals_host[tid == 2 ? 3 : tid] = (int64_t)v;
@@ -469,19 +534,20 @@ __global__ void __launch_bounds__(kTileRays) march_kernel(const MarchParams p)
 // offsets: per-ray packed_info from the counts (tile base from the tile sums + block scan)
 // ---------------------------------------------------------------------------
 template <bool kIntervals>
-__global__ void __launch_bounds__(kTileRays) offsets_kernel(int32_t n_rays, Workspace ws, int64_t* sm_packed_info,
-                                                           int64_t* iv_packed_info)
+__global__ void __launch_bounds__(kMaxTileRays) offsets_kernel(int32_t n_rays, Workspace ws, int64_t* sm_packed_info,
+                                                              int64_t* iv_packed_info)
 {
-    __shared__ unsigned long long s_red[2][kTileRays / 32];
+    __shared__ unsigned long long s_red[2][kMaxTileRays / 32];
     __shared__ unsigned long long s_base[2];
-    __shared__ uint32_t s_wsum[2][kTileRays / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ uint32_t s_wsum[2][kMaxTileRays / 32];
+    const int T = blockDim.x;  // == ws.tile_rays
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = T >> 5;
     const int tile = blockIdx.x;
-    const int r0 = tile * kTileRays;
-    const int nr = min(kTileRays, n_rays - r0);
+    const int r0 = tile * T;
+    const int nr = min(T, n_rays - r0);
 
     unsigned long long a = 0, b = 0;
-    for (int i = tid; i < tile; i += kTileRays) {
+    for (int i = tid; i < tile; i += T) {
         const TileSum ts = ws.tiles[i];
         a += ts.samples;
         b += ts.runs;
@@ -517,7 +583,7 @@ __global__ void __launch_bounds__(kTileRays) offsets_kernel(int32_t n_rays, Work
     __syncthreads();
     if (tid == 0) {
         unsigned long long ta = 0, tb = 0;
-        for (int k = 0; k < kTileRays / 32; ++k) {
+        for (int k = 0; k < n_warps; ++k) {
             ta += s_red[0][k];
             tb += s_red[1][k];
         }
@@ -896,7 +962,7 @@ int32_t nfa_occ_pack(int32_t n_grids, int32_t rx, int32_t ry, int32_t rz, const 
     const int64_t n_words = (int64_t)n_grids * g.wpl;
     if (n_words > (int64_t)INT32_MAX) return NFA_ERR_UNSUPPORTED;
     const int64_t n_coarse = occ_coarse_words(g);
-    const int64_t threads = n_coarse * 32;
+    const int64_t threads = n_coarse * 16;
     const int blocks = (int)((threads + 255) / 256 < 148 * 16 ? (threads + 255) / 256 : 148 * 16);
     occ_bounds_init_kernel<<<(6 * n_grids + 127) / 128, 128, 0, (cudaStream_t)stream>>>(bounds, n_grids);
     occ_pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(g, binaries, words, coarse, bounds, n_words, n_coarse);
@@ -952,16 +1018,21 @@ int32_t nfa_march(int32_t n_rays, const float* rays_o, const float* rays_d, cons
     p.totals = totals;
     p.totals_host = totals_host;
     p.terminate = terminate_planes;
-    const int tiles = p.ws.n_tiles;
+    const int tiles = p.ws.n_tiles, tile_rays = p.ws.tile_rays;
     const size_t coarse_bytes = (size_t)p.coarse_words * 4;
-    // keep the brick mip in shared memory while it leaves room for >= 2 CTAs / SM
-    const bool smem_coarse = coarse_bytes <= 96 * 1024;
-    const size_t dyn = smem_coarse ? coarse_bytes : 0;
+    // keep the class mip in shared memory while it leaves room for the tile's own buffers (256^3: 64 KiB)
+    const bool smem_coarse = coarse_bytes <= 128 * 1024;
+    const size_t dyn = march_smem_bytes(tile_rays, smem_coarse ? coarse_bytes : 0);
 #define NFA_LAUNCH_MARCH(S, C)                                                                          \
     do {                                                                                                \
-        if (dyn > 32 * 1024)                                                                            \
-            cudaFuncSetAttribute(march_kernel<S, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); \
-        march_kernel<S, C><<<tiles, kTileRays, dyn, s>>>(p);                                            \
+        static bool raised[64] = {}; /* once per instantiation and device: above the 48 KiB default */  \
+        int dev_ = 0;                                                                                   \
+        cudaGetDevice(&dev_);                                                                           \
+        if (dyn > 40 * 1024 && !raised[dev_ & 63]) {                                                    \
+            cudaFuncSetAttribute(march_kernel<S, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+            raised[dev_ & 63] = true;                                                                   \
+        }                                                                                               \
+        march_kernel<S, C><<<tiles, tile_rays, dyn, s>>>(p);                                            \
     } while (0)
     if (!have_sorted) {
         if (smem_coarse) NFA_LAUNCH_MARCH(true, true); else NFA_LAUNCH_MARCH(true, false);
@@ -990,7 +1061,7 @@ int32_t nfa_expand_samples(int32_t n_rays, int64_t run_capacity, const void* wor
     if ((((uintptr_t)packed_info) & 15u) != 0) return NFA_ERR_ARG;
     const Workspace ws = ws_view(const_cast<void*>(workspace), n_rays, run_capacity);
     cudaStream_t s = (cudaStream_t)stream;
-    offsets_kernel<false><<<ws.n_tiles, kTileRays, 0, s>>>(n_rays, ws, packed_info, nullptr);
+    offsets_kernel<false><<<ws.n_tiles, ws.tile_rays, 0, s>>>(n_rays, ws, packed_info, nullptr);
     if (capacity > 0 && run_capacity > 0) {
         ExpandParams p = {};
         p.ws = ws;
@@ -1022,7 +1093,7 @@ int32_t nfa_expand_intervals(int32_t n_rays, int64_t run_capacity, const void* w
     if (((((uintptr_t)iv_packed_info) | ((uintptr_t)sm_packed_info)) & 15u) != 0) return NFA_ERR_ARG;
     const Workspace ws = ws_view(const_cast<void*>(workspace), n_rays, run_capacity);
     cudaStream_t s = (cudaStream_t)stream;
-    offsets_kernel<true><<<ws.n_tiles, kTileRays, 0, s>>>(n_rays, ws, sm_packed_info, iv_packed_info);
+    offsets_kernel<true><<<ws.n_tiles, ws.tile_rays, 0, s>>>(n_rays, ws, sm_packed_info, iv_packed_info);
     if (edge_capacity > 0 && run_capacity > 0) {
         ExpandParams p = {};
         p.ws = ws;

@@ -74,7 +74,7 @@ void sim_occ_pack(int n_grids, int rx, int ry, int rz, const uint8_t* binaries, 
                     const uint64_t w = occ_brick_word(binaries + l * cells, g, bx, by, bz);
                     words[b] = w;
                     if (w) {
-                        coarse[b >> 5] |= 1u << (b & 31);
+                        coarse[b >> 4] |= (w == ~0ull ? kBrickFull : kBrickMixed) << ((b & 15) << 1);
                         const int bc[3] = {bx, by, bz};
                         for (int a = 0; a < 3; ++a) {
                             if (bc[a] < bounds[6 * l + a]) bounds[6 * l + a] = bc[a];

@@ -38,7 +38,7 @@ def test_version_and_error_strings_without_gpu():
     assert b"argument" in lib.nfa_error_string(-1)
     # pure host helpers
     assert lib.nfa_occ_words(1, 128, 128, 128) == 32 ** 3
-    assert lib.nfa_occ_coarse_words(1, 128, 128, 128) == 1024
+    assert lib.nfa_occ_coarse_words(1, 128, 128, 128) == 2048
     assert lib.nfa_occ_words(2, 30, 17, 5) == 2 * 8 * 5 * 2
     assert lib.nfa_march_workspace_bytes(65536, 1000) > 65536 * 8 + 1000 * 32
     assert lib.nfa_pack_info_workspace_bytes(10) >= 80
