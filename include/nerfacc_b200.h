@@ -70,6 +70,20 @@ int64_t nfa_occ_coarse_words(int32_t n_grids, int32_t rx, int32_t ry, int32_t rz
 int32_t nfa_occ_pack(int32_t n_grids, int32_t rx, int32_t ry, int32_t rz, const uint8_t* binaries,
                      uint64_t* words, uint32_t* coarse, int32_t* bounds, nfa_stream_t stream);
 
+/* Grid maintenance (OccGridEstimator._update, nerfacc/estimators/occ_grid.py:367-404).
+ * nfa_occ_ema_update: occs[cell_ids[i]] = max(occs[cell_ids[i]] * ema_decay, occ[i]) (:395-398); a cell named more
+ *   than once gets the largest of its results.  scratch: n floats.
+ * nfa_occ_threshold_pack: thre = min(mean(occs[occs >= 0]), occ_thre) (:400-402), binaries = occs > thre (:403-404)
+ *   written as bool bytes AND as the derived cache nfa_occ_pack would build from them (words / coarse / bounds),
+ *   one pass, no host synchronisation.  workspace: nfa_occ_threshold_workspace_bytes(n_cells) bytes, 16-byte
+ *   aligned, n_cells = n_grids*rx*ry*rz. */
+int32_t nfa_occ_ema_update(int64_t n, const int64_t* cell_ids, const float* occ, float ema_decay, float* occs,
+                           float* scratch, nfa_stream_t stream);
+int64_t nfa_occ_threshold_workspace_bytes(int64_t n_cells);
+int32_t nfa_occ_threshold_pack(int32_t n_grids, int32_t rx, int32_t ry, int32_t rz, const float* occs, float occ_thre,
+                               uint8_t* binaries, uint64_t* words, uint32_t* coarse, int32_t* bounds, void* workspace,
+                               nfa_stream_t stream);
+
 /* ----------------------------------------------------------------------- */
 /* Grid traversal, constant step (cone_angle == 0, step_size > 0)           */
 /* ----------------------------------------------------------------------- */

@@ -72,6 +72,9 @@ class OccGridEstimator(AbstractEstimator):
         # size of the previous sample batch: lets `sampling` launch the expand kernel
         # before the (single) host sync instead of after it
         self._capacity_hint = 0
+        # ray-sharded data parallelism: all-reduce(max) `occs` in `_update` so that every replica thresholds the
+        # same grid (the ranks evaluate `occ_eval_fn` at different random points).  Off by default.
+        self.sync_across_ranks = False
 
     @torch.no_grad()
     def sampling(
@@ -306,21 +309,55 @@ class OccGridEstimator(AbstractEstimator):
         ema_decay: float = 0.95,
         warmup_steps: int = 256,
     ) -> None:
-        """EMA-max update of `occs` at sampled cells, then re-threshold into `binaries`."""
+        """EMA-max update of `occs` at sampled cells, then re-threshold into `binaries` (reference :367-404).
+
+        On the GPU the arithmetic runs in csrc/occ_update.cu: the EMA-max at the sampled cells, then ONE pass that
+        takes the mean of the visible cells, thresholds, and writes both the bool grid and the traversal's packed
+        form of it -- no host synchronisation, and the next `sampling()` finds its derived cache ready.  Cell
+        sampling and the user's `occ_eval_fn` stay in torch (same random streams as the reference)."""
         if step < warmup_steps:
             per_level = self._get_all_cells()
         else:
             per_level = self._sample_uniform_and_occupied_cells(self.cells_per_lvl // 4)
 
+        native = self.occs.is_cuda and self.occs.dtype == torch.float32 and self.occs.is_contiguous()
         for lvl, indices in enumerate(per_level):
             coords = self.grid_coords[indices]
             unit = (coords + torch.rand_like(coords, dtype=torch.float32)) / self.resolution
             pts = self.aabbs[lvl, :3] + unit * (self.aabbs[lvl, 3:] - self.aabbs[lvl, :3])
             occ = occ_eval_fn(pts).squeeze(-1)
             cell_ids = lvl * self.cells_per_lvl + indices
-            self.occs[cell_ids] = torch.maximum(self.occs[cell_ids] * ema_decay, occ)
-        thre = torch.clamp(self.occs[self.occs >= 0].mean(), max=occ_thre)
-        self.binaries = (self.occs > thre).view(self.binaries.shape)
+            if native and occ.is_cuda:
+                n = cell_ids.shape[0]
+                if n:
+                    ids, val = cell_ids.contiguous(), occ.detach().to(torch.float32).contiguous()
+                    scratch = torch.empty(n, dtype=torch.float32, device=self.occs.device)
+                    _lib.call("nfa_occ_ema_update", self.occs.device, n, _lib.ptr(ids), _lib.ptr(val), float(ema_decay),
+                              _lib.ptr(self.occs), _lib.ptr(scratch))
+            else:
+                self.occs[cell_ids] = torch.maximum(self.occs[cell_ids] * ema_decay, occ)
+        if self.sync_across_ranks:  # keep the replicas of a ray-sharded job on one grid (SURVEY 8e)
+            from ..parallel import all_reduce_max_
+            all_reduce_max_(self.occs)
+        if native:
+            self._threshold_native(float(occ_thre))
+        else:
+            thre = torch.clamp(self.occs[self.occs >= 0].mean(), max=occ_thre)
+            self.binaries = (self.occs > thre).view(self.binaries.shape)
+
+    def _threshold_native(self, occ_thre: float) -> None:
+        """binaries = occs > min(mean(occs[occs >= 0]), occ_thre), written together with its packed form."""
+        from ..grid import _OccPack
+        lib = _lib.load()
+        device, shape = self.occs.device, tuple(int(v) for v in self.binaries.shape)
+        binaries = torch.empty(shape, dtype=torch.bool, device=device)
+        pack = _OccPack(None, shape=shape, device=device)
+        ws = torch.empty(lib.nfa_occ_threshold_workspace_bytes(self.occs.numel()), dtype=torch.uint8, device=device)
+        _lib.call("nfa_occ_threshold_pack", device, shape[0], shape[1], shape[2], shape[3], _lib.ptr(self.occs), occ_thre,
+                  _lib.ptr(binaries), _lib.ptr(pack.words), _lib.ptr(pack.coarse), _lib.ptr(pack.bounds), _lib.ptr(ws))
+        self.binaries = binaries
+        binaries._nfa_occ = (binaries._version, pack)  # grid._packed_grid: the derived cache is already there
+        self._occs_mean_key = None  # occs changed behind torch's version counter
 
 
 _vis_scratch = {}
@@ -336,9 +373,12 @@ def _visibility_compact(t_starts: Tensor, t_ends: Tensor, dens: Tensor, packed_i
     pi = packed_info.contiguous()
     if pi.dtype != torch.int64:
         pi = pi.to(torch.int64)
-    sc = _vis_scratch.get(device)
+    key = (device, _lib.stream_ptr(device))  # per stream: the pinned count slot is protected by stream order only
+    sc = _vis_scratch.get(key)
     if sc is None:
-        sc = _vis_scratch[device] = (torch.zeros(1, dtype=torch.int64).pin_memory(), torch.cuda.Event())
+        if len(_vis_scratch) >= 16:
+            _vis_scratch.clear()
+        sc = _vis_scratch[key] = (torch.zeros(1, dtype=torch.int64).pin_memory(), torch.cuda.Event())
     total_host, event = sc
     ws = torch.empty(lib.nfa_visibility_workspace_bytes(n_rays, n), dtype=torch.uint8, device=device)
     new_pi = torch.empty((n_rays, 2), dtype=torch.int64, device=device)

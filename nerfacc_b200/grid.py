@@ -79,19 +79,23 @@ class _OccPack:
 
     __slots__ = ("words", "coarse", "bounds", "shape")
 
-    def __init__(self, binaries: Tensor):
+    def __init__(self, binaries: Optional[Tensor], shape=None, device=None):
+        """Pack `binaries`; or, with `binaries=None`, only allocate for `shape` on `device` (the grid-update
+        kernel then fills bool grid and pack in one pass, estimators/occ_grid.py `_update`)."""
         lib = _lib.load()
-        g, rx, ry, rz = (int(s) for s in binaries.shape)
-        device = binaries.device
-        b = binaries.contiguous()
-        if b.dtype != torch.bool:
-            b = b != 0
+        if binaries is not None:
+            shape, device = binaries.shape, binaries.device
+        g, rx, ry, rz = (int(s) for s in shape)
         self.shape = (g, rx, ry, rz)
         self.words = torch.empty(lib.nfa_occ_words(g, rx, ry, rz), dtype=torch.int64, device=device)
         self.coarse = torch.empty(lib.nfa_occ_coarse_words(g, rx, ry, rz), dtype=torch.int32, device=device)
         self.bounds = torch.empty(6 * g, dtype=torch.int32, device=device)
-        _lib.call("nfa_occ_pack", device, g, rx, ry, rz, _lib.ptr(b), _lib.ptr(self.words), _lib.ptr(self.coarse),
-                  _lib.ptr(self.bounds))
+        if binaries is not None:
+            b = binaries.contiguous()
+            if b.dtype != torch.bool:
+                b = b != 0
+            _lib.call("nfa_occ_pack", device, g, rx, ry, rz, _lib.ptr(b), _lib.ptr(self.words), _lib.ptr(self.coarse),
+                      _lib.ptr(self.bounds))
 
 
 def _packed_grid(binaries: Tensor) -> _OccPack:
@@ -110,45 +114,54 @@ def _packed_grid(binaries: Tensor) -> _OccPack:
 
 
 class _MarchScratch:
-    """Per-(device, n_rays) reusable workspace (counts, tile sums, run pool) + pinned read-back slot."""
+    """Reusable march workspace (counts, tile sums, run pool) + pinned read-back slot of one (device, stream).
 
-    def __init__(self, device, n_rays: int):
-        self.device, self.n_rays = device, n_rays
+    It is sized for the largest batch seen and only ever grows: training loops that resize their ray batch every
+    step (the reference's own NGP loop does, to hit a target sample count) would otherwise allocate a new pinned
+    buffer -- a synchronising cudaHostAlloc -- on nearly every call."""
+
+    def __init__(self, device):
+        self.device = device
         self.run_capacity = 0
         self.workspace = None
         self.totals_dev = torch.zeros(4, dtype=torch.int64, device=device)
         self.totals_host = torch.zeros(4, dtype=torch.int64).pin_memory()
         self.event = torch.cuda.Event()
         self.busy = False
-        self.reserve(2 * n_rays + 1024)
 
-    def reserve(self, run_capacity: int) -> None:
-        if run_capacity > self.run_capacity:
-            lib = _lib.load()
-            self.run_capacity = int(run_capacity)
-            self.workspace = torch.zeros(lib.nfa_march_workspace_bytes(self.n_rays, self.run_capacity),
-                                         dtype=torch.uint8, device=self.device)
+    def reserve(self, n_rays: int, run_capacity: int = 0) -> None:
+        """Room for `n_rays` rays and max(run_capacity, what was seen so far, 2 n_rays + 1024) runs.  The layout inside
+        the buffer is recomputed per call by the library; a fresh buffer is zeroed because the kernel expects (and
+        leaves behind) a zero header."""
+        lib = _lib.load()
+        self.run_capacity = max(self.run_capacity, int(run_capacity), 2 * n_rays + 1024)
+        need = lib.nfa_march_workspace_bytes(n_rays, self.run_capacity)
+        if self.workspace is None or self.workspace.numel() < need:
+            self.workspace = torch.zeros(need + (need >> 2), dtype=torch.uint8, device=self.device)
 
 
 _scratch_cache: Dict[tuple, list] = {}
 
 
 def _scratch_acquire(device, n_rays: int) -> _MarchScratch:
-    """A workspace nobody is marching into.  One per (device, n_rays) in the usual one-call-at-a-time use; a
-    second one is made when a march is still in flight (sampling_begin without its sampling_end yet)."""
-    key = (device, n_rays)
+    """A workspace nobody is marching into, for the CURRENT stream of `device`: two streams sampling at the same
+    time must not share a run pool or a pinned totals slot (stream order is what protects them).  One scratch per
+    (device, stream) in the usual one-call-at-a-time use; a second one is made when a march is still in flight
+    (sampling_begin without its sampling_end yet)."""
+    key = (device, _lib.stream_ptr(device))
     pool = _scratch_cache.get(key)
     if pool is None:
-        if len(_scratch_cache) >= 8:
+        if len(_scratch_cache) >= 16:
             _scratch_cache.clear()
         pool = _scratch_cache[key] = []
     for sc in pool:
         if not sc.busy:
-            sc.busy = True
-            return sc
-    sc = _MarchScratch(device, n_rays)
+            break
+    else:
+        sc = _MarchScratch(device)
+        pool.append(sc)
     sc.busy = True
-    pool.append(sc)
+    sc.reserve(n_rays)
     return sc
 
 
@@ -247,7 +260,7 @@ class _MarchJob:
         try:
             n, runs = self._read_totals()
             if runs > sc.run_capacity:  # run pool overflow: rare (very fragmented grids); re-march with room
-                sc.reserve(runs + (runs >> 2) + 1024)
+                sc.reserve(n_rays, runs + (runs >> 2) + 1024)
                 self._launch_march()
                 n, runs = self._read_totals()
                 self.bufs = None

@@ -140,6 +140,14 @@ def _packed_mode(x: Tensor, packed_info: Optional[Tensor], ray_indices: Optional
     return packed_info is not None or ray_indices is not None
 
 
+def _grad_through(*tensors: Optional[Tensor]) -> bool:
+    """Does the caller differentiate through any of these?  The fused kernels treat t_starts / t_ends /
+    prefix_trans as constants (their backward returns None for them); the reference's op sequence
+    (volrend.py:271-277) is differentiable in them, so such calls take the ATen formulation over the native
+    scans instead of silently dropping the gradient."""
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
 _uniform_segments = {}
 
 
@@ -215,7 +223,8 @@ def rendering(
     name = "sigmas" if use_sigma else "alphas"
     assert dens.shape == t_starts.shape, "{} must have shape of (N,)! Got {}".format(name, dens.shape)
 
-    if ray_indices is not None and dens.is_cuda:
+    t_grad = _grad_through(t_starts, t_ends)
+    if ray_indices is not None and dens.is_cuda and not t_grad:
         assert n_rays is not None, "n_rays must be provided"
         bk = render_bkgd
         fuse_bkgd = bk is not None and not bk.requires_grad and bk.numel() == 3 and bk.is_cuda
@@ -230,7 +239,7 @@ def rendering(
             extras["sigmas"] = dens
         return colors, opacities, depths, extras
 
-    seg = _batched_segments(dens, None) if ray_indices is None and rgbs.dtype == torch.float32 else None
+    seg = _batched_segments(dens, None) if ray_indices is None and rgbs.dtype == torch.float32 and not t_grad else None
     if seg is not None and t_starts.shape == dens.shape == t_ends.shape:
         # batched (n_rays, S) on the GPU: the same fused kernels, addressed through uniform segments
         bk = render_bkgd
@@ -248,7 +257,7 @@ def rendering(
             extras["sigmas"] = dens
         return colors, opacities, depths, extras
 
-    # batched CPU inputs: the reference's own op sequence
+    # batched CPU inputs, or gradients wanted w.r.t. t_starts / t_ends: the reference's own op sequence
     if use_sigma:
         weights, trans, alphas = render_weight_from_density(t_starts, t_ends, dens, ray_indices=ray_indices,
                                                             n_rays=n_rays)
@@ -275,11 +284,11 @@ def render_transmittance_from_alpha(
     prefix_trans: Optional[Tensor] = None,
 ) -> Tensor:
     """T_i = prod_{j<i} (1 - alpha_j) per ray (reference volrend.py:167-216)."""
-    if _packed_mode(alphas, packed_info, ray_indices) and alphas.is_cuda:
+    if _packed_mode(alphas, packed_info, ray_indices) and alphas.is_cuda and not _grad_through(prefix_trans):
         _, trans, _, _, _, _ = _composite_packed(alphas, None, None, None, packed_info, ray_indices, n_rays,
                                                  prefix_trans, None, True, False, False)
         return trans
-    seg = _batched_segments(alphas, prefix_trans)
+    seg = None if _packed_mode(alphas, packed_info, ray_indices) else _batched_segments(alphas, prefix_trans)
     if seg is not None:
         return render_transmittance_from_alpha(alphas.reshape(-1), packed_info=seg).view_as(alphas)
     trans = exclusive_prod(1 - alphas, packed_info=packed_info, indices=ray_indices)
@@ -298,11 +307,12 @@ def render_transmittance_from_density(
     prefix_trans: Optional[Tensor] = None,
 ) -> Tuple[Tensor, Tensor]:
     """T_i = exp(-sum_{j<i} sigma_j dt_j) and alpha_i = 1 - exp(-sigma_i dt_i) (reference volrend.py:219-278)."""
-    if _packed_mode(sigmas, packed_info, ray_indices) and sigmas.is_cuda:
+    t_grad = _grad_through(t_starts, t_ends, prefix_trans)
+    if _packed_mode(sigmas, packed_info, ray_indices) and sigmas.is_cuda and not t_grad:
         _, trans, alphas, _, _, _ = _composite_packed(sigmas, None, t_starts, t_ends, packed_info, ray_indices,
                                                       n_rays, prefix_trans, None, False, False, False)
         return trans, alphas
-    seg = _batched_segments(sigmas, prefix_trans)
+    seg = None if (t_grad or _packed_mode(sigmas, packed_info, ray_indices)) else _batched_segments(sigmas, prefix_trans)
     if seg is not None and t_starts.shape == sigmas.shape == t_ends.shape:
         trans, alphas = render_transmittance_from_density(t_starts.reshape(-1), t_ends.reshape(-1),
                                                           sigmas.reshape(-1), packed_info=seg)
@@ -323,11 +333,11 @@ def render_weight_from_alpha(
     prefix_trans: Optional[Tensor] = None,
 ) -> Tuple[Tensor, Tensor]:
     """w_i = T_i alpha_i (reference volrend.py:281-323).  Returns (weights, trans)."""
-    if _packed_mode(alphas, packed_info, ray_indices) and alphas.is_cuda:
+    if _packed_mode(alphas, packed_info, ray_indices) and alphas.is_cuda and not _grad_through(prefix_trans):
         weights, trans, _, _, _, _ = _composite_packed(alphas, None, None, None, packed_info, ray_indices, n_rays,
                                                        prefix_trans, None, True, False, False)
         return weights, trans
-    seg = _batched_segments(alphas, prefix_trans)
+    seg = None if _packed_mode(alphas, packed_info, ray_indices) else _batched_segments(alphas, prefix_trans)
     if seg is not None:
         weights, trans = render_weight_from_alpha(alphas.reshape(-1), packed_info=seg)
         return weights.view_as(alphas), trans.view_as(alphas)
@@ -345,12 +355,13 @@ def render_weight_from_density(
     prefix_trans: Optional[Tensor] = None,
 ) -> Tuple[Tensor, Tensor, Tensor]:
     """w_i = T_i (1 - exp(-sigma_i dt_i)) (reference volrend.py:326-376).  Returns (weights, trans, alphas)."""
-    if _packed_mode(sigmas, packed_info, ray_indices) and sigmas.is_cuda:
+    t_grad = _grad_through(t_starts, t_ends, prefix_trans)
+    if _packed_mode(sigmas, packed_info, ray_indices) and sigmas.is_cuda and not t_grad:
         weights, trans, alphas, _, _, _ = _composite_packed(sigmas, None, t_starts, t_ends, packed_info,
                                                             ray_indices, n_rays, prefix_trans, None, False, False,
                                                             False)
         return weights, trans, alphas
-    seg = _batched_segments(sigmas, prefix_trans)
+    seg = None if (t_grad or _packed_mode(sigmas, packed_info, ray_indices)) else _batched_segments(sigmas, prefix_trans)
     if seg is not None and t_starts.shape == sigmas.shape == t_ends.shape:
         weights, trans, alphas = render_weight_from_density(t_starts.reshape(-1), t_ends.reshape(-1),
                                                             sigmas.reshape(-1), packed_info=seg)

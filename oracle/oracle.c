@@ -703,3 +703,42 @@ ORC_API void orc_searchsorted(
         ids_right[tid] = clamp_i64(p, base, last) - rel;
     }
 }
+
+/* ------------------------------------------------------------------------- */
+/* grid maintenance: OccGridEstimator._update                                 */
+/* (nerfacc/estimators/occ_grid.py:367-404); pinned by tests/golden/ref_occ_update.npz */
+/* ------------------------------------------------------------------------- */
+
+/* occ_grid.py:395-398  occs[ids] = maximum(occs[ids] * ema_decay, occ).  The right-hand side is evaluated on the
+ * OLD values for every draw before anything is written (index_put_); when `ids` names a cell more than once
+ * torch keeps one of the candidates (the last one on the CPU, an arbitrary one on CUDA) -- this restatement
+ * keeps the largest, the only rule that does not depend on the order of the writes.  `fresh`: n floats. */
+ORC_API void orc_occ_ema_update(int64_t n, const int64_t* ids, const float* occ, float ema_decay, float* occs,
+                                float* fresh)
+{
+    for (int64_t i = 0; i < n; ++i) {
+        const float a = occs[ids[i]] * ema_decay, b = occ[i];
+        fresh[i] = (a != a || b != b) ? NAN : (a > b ? a : b); /* torch.maximum propagates NaN */
+    }
+    for (int64_t i = 0; i < n; ++i) occs[ids[i]] = -INFINITY;
+    for (int64_t i = 0; i < n; ++i) {
+        float* dst = occs + ids[i];
+        if (fresh[i] != fresh[i] || *dst != *dst) *dst = NAN;
+        else if (fresh[i] > *dst) *dst = fresh[i];
+    }
+}
+
+/* occ_grid.py:400-404  thre = clamp(occs[occs >= 0].mean(), max=occ_thre); binaries = occs > thre.
+ * The mean is accumulated in double (torch reduces in float32 in an order of its own; the two agree to the last
+ * bit or two of the mean, which only matters for a cell whose occupancy sits on the threshold).  Returns thre. */
+ORC_API float orc_occ_threshold(int64_t n_cells, const float* occs, float occ_thre, uint8_t* binaries)
+{
+    double sum = 0.0;
+    int64_t cnt = 0;
+    for (int64_t i = 0; i < n_cells; ++i)
+        if (occs[i] >= 0.0f) { sum += occs[i]; ++cnt; }
+    const float mean = cnt ? (float)(sum / (double)cnt) : NAN;
+    const float thre = (mean != mean) ? mean : (mean < occ_thre ? mean : occ_thre);
+    for (int64_t i = 0; i < n_cells; ++i) binaries[i] = occs[i] > thre ? 1 : 0;
+    return thre;
+}

@@ -449,3 +449,26 @@ def searchsorted(key_vals, query_vals, key_packed_info=None, query_packed_info=N
                            C.c_int64(qv.shape[-1] if qp is None else 0), _p(kv, _F), _p(kp, _I64),
                            C.c_int64(kv.shape[-1] if kp is None else 0), _p(left, _I64), _p(right, _I64))
     return left, right
+
+
+# --------------------------------------------------------------------------
+# estimators/occ_grid.py: grid maintenance
+# --------------------------------------------------------------------------
+
+def occ_ema_update(occs, cell_ids, occ, ema_decay=0.95):
+    """occs[cell_ids] = maximum(occs[cell_ids] * ema_decay, occ) (occ_grid.py:395-398); returns the new array."""
+    out = _f32(occs).copy()
+    ids, val = _i64(cell_ids), _f32(occ)
+    fresh = np.empty(len(ids), np.float32)
+    lib().orc_occ_ema_update(C.c_int64(len(ids)), _p(ids, _I64), _p(val, _F), C.c_float(ema_decay), _p(out, _F), _p(fresh, _F))
+    return out
+
+
+def occ_threshold(occs, occ_thre=0.01):
+    """(binaries, thre) with thre = min(mean(occs[occs >= 0]), occ_thre), binaries = occs > thre (occ_grid.py:400-404)."""
+    o = _f32(occs)
+    b = np.empty(o.size, np.uint8)
+    fn = lib().orc_occ_threshold
+    fn.restype = C.c_float
+    thre = fn(C.c_int64(o.size), _p(o, _F), C.c_float(occ_thre), _p(b, _U8))
+    return b.astype(bool).reshape(o.shape), float(thre)

@@ -10,6 +10,8 @@
 #include <cstring>
 #include <vector>
 
+static long g_walk_counts[3];
+#define NFA_COUNT(i) (++g_walk_counts[i])
 #include "../../nerfacc_b200/csrc/occ_pack.cuh"
 #include "../../nerfacc_b200/csrc/expand.cuh"
 #include "../../nerfacc_b200/csrc/march_generic.cuh"
@@ -18,6 +20,12 @@
 using namespace nfa;
 
 extern "C" {
+
+// loop passes of the walk since the last reset: cell steps, whole-brick steps, brick-loop entries
+void sim_walk_counts(long* out, int reset)
+{
+    for (int i = 0; i < 3; ++i) { out[i] = g_walk_counts[i]; if (reset) g_walk_counts[i] = 0; }
+}
 
 // serial reference chain: k steps of t += dt
 float sim_chain(float t, float dt, uint32_t k)

@@ -801,3 +801,168 @@ def test_sampling_begin_end_matches_sampling():
     assert f_got[0].numel() < want[0].numel()
     with pytest.raises(ValueError):
         est.sampling_begin(o.cpu(), d.cpu())
+
+
+# ---------------------------------------------------------------- round 2: advisor findings
+
+def test_gradients_flow_through_t_and_prefix_trans():
+    """render_*_from_density are differentiable in t_starts / t_ends / prefix_trans in the reference
+    (volrend.py:271-277); the fused kernels treat them as constants, so such calls must take the ATen route."""
+    torch.manual_seed(3)
+    cnts = torch.tensor([7, 0, 33, 1, 64], device=dev)
+    ri = torch.repeat_interleave(torch.arange(5, device=dev), cnts)
+    n = int(cnts.sum())
+    pi = nfa.pack_info(ri, 5)
+    ts0 = torch.rand(n, device=dev)
+    te0 = ts0 + 0.01 + 0.05 * torch.rand(n, device=dev)
+    sig0 = 3 * torch.rand(n, device=dev)
+    pre0 = 0.5 + 0.5 * torch.rand(n, device=dev)
+
+    def plain(ts, te, sig, pre):  # per-ray loops, plain torch, float64
+        w = []
+        for r in range(5):
+            s, c = int(pi[r, 0]), int(pi[r, 1])
+            sd = (sig[s:s + c] * (te[s:s + c] - ts[s:s + c])).double()
+            T = torch.exp(-(torch.cumsum(sd, 0) - sd)) * pre[s:s + c].double()
+            w.append(T * (1 - torch.exp(-sd)))
+        return torch.cat(w)
+
+    for kw in (dict(packed_info=pi), dict(ray_indices=ri, n_rays=5)):
+        leaves = [x.clone().requires_grad_(True) for x in (ts0, te0, sig0, pre0)]
+        w, T, a = nfa.render_weight_from_density(leaves[0], leaves[1], leaves[2], prefix_trans=leaves[3], **kw)
+        (w * torch.arange(n, device=dev)).sum().backward()
+        ref_leaves = [x.clone().requires_grad_(True) for x in (ts0, te0, sig0, pre0)]
+        (plain(*ref_leaves) * torch.arange(n, device=dev)).sum().backward()
+        for got, want, name in zip(leaves, ref_leaves, ("t_starts", "t_ends", "sigmas", "prefix_trans")):
+            assert got.grad is not None, name
+            torch.testing.assert_close(got.grad, want.grad, atol=2e-4, rtol=2e-4, msg=name)
+    # only t requires grad: the result must still carry a graph (the fused early-out must not swallow it)
+    ts = ts0.clone().requires_grad_(True)
+    T, a = nfa.render_transmittance_from_density(ts, te0, sig0, packed_info=pi)
+    assert T.requires_grad and a.requires_grad
+    col, op, dep, _ = nfa.rendering(ts, te0, ri, n_rays=5, rgb_sigma_fn=lambda a_, b_, c_: (torch.ones(n, 3, device=dev), sig0))
+    assert col.requires_grad
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_sampling_on_a_device_that_is_not_current():
+    """The totals event must be recorded on the stream of the tensors' device (advisor finding, grid.py)."""
+    other = torch.device("cuda:1")
+    ro, rd = scenes.ball_rays(2048)
+    bins = scenes.ball_grid(64)
+    with torch.cuda.device(0):
+        est = nfa.OccGridEstimator(torch.from_numpy(scenes.ROI_AABB), resolution=64).to(other)
+        est.binaries = torch.from_numpy(bins).to(other)
+        a = est.sampling(torch.from_numpy(ro).to(other), torch.from_numpy(rd).to(other), render_step_size=1e-2)
+        b = est.sampling(torch.from_numpy(ro[:1000]).to(other), torch.from_numpy(rd[:1000]).to(other), render_step_size=1e-2)
+    with torch.cuda.device(1):
+        c = est.sampling(torch.from_numpy(ro).to(other), torch.from_numpy(rd).to(other), render_step_size=1e-2)
+    assert a[0].numel() > 0 and torch.equal(a[0], c[0]) and torch.equal(a[1], c[1])
+    assert b[0].numel() > 0 and int(b[0].max()) < 1000
+
+
+def test_two_streams_sampling_concurrently_do_not_share_scratch():
+    """Workspaces and pinned count slots are per (device, stream): two streams sampling at once stay correct."""
+    from nerfacc_b200 import grid as _grid
+    bins = scenes.ball_grid(128)
+    est = _estimator(bins, scenes.nested_aabbs(1))
+    ro_a, rd_a = scenes.ball_rays(20000, seed=1)
+    ro_b, rd_b = scenes.ball_rays(31000, seed=2)
+    A, B = (T(ro_a), T(rd_a)), (T(ro_b), T(rd_b))
+    want_a = est.sampling(*A, render_step_size=scenes.BALL_STEP)
+    want_b = est.sampling(*B, render_step_size=scenes.BALL_STEP)
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            ta = est.sampling_begin(*A, render_step_size=scenes.BALL_STEP)
+        with torch.cuda.stream(s2):
+            tb = est.sampling_begin(*B, render_step_size=scenes.BALL_STEP)
+        with torch.cuda.stream(s1):
+            got_a = est.sampling_end(ta)
+        with torch.cuda.stream(s2):
+            got_b = est.sampling_end(tb)
+        torch.cuda.synchronize()
+        for g, w in zip(got_a + got_b, want_a + want_b):
+            assert torch.equal(g, w)
+    keys = {k for k in _grid._scratch_cache if k[0] == torch.device(dev)}
+    assert len({k[1] for k in keys}) >= 3  # default stream + the two side streams each own a scratch
+
+
+# ---------------------------------------------------------------- f4: grid maintenance kernels (csrc/occ_update.cu)
+
+@pytest.mark.parametrize("case", ["warm", "sampled", "sampled_hi"])
+def test_grid_update_kernels_match_oracle_and_reference_golden(orc, case):
+    from nerfacc_b200.grid import _OccPack
+    z = load_golden("ref_occ_update")
+    before, ids, occ = z[case + "_occs_before"], z[case + "_ids"], z[case + "_occ"]
+    occ_thre, decay = (float(v) for v in z[case + "_args"])
+    lib = _lib.load()
+    occs = T(before).clone()
+    scratch = torch.empty(len(ids), dtype=torch.float32, device=dev)
+    t_ids, t_occ = T(ids), T(occ)
+    _lib.call("nfa_occ_ema_update", occs.device, len(ids), _lib.ptr(t_ids), _lib.ptr(t_occ), decay, _lib.ptr(occs),
+              _lib.ptr(scratch))
+    want = orc.occ_ema_update(before, ids, occ, decay)
+    np.testing.assert_array_equal(N(occs), want)                     # bit-exact, duplicates included (largest wins)
+    shape = z[case + "_binaries"].shape
+    bins = torch.empty(shape, dtype=torch.bool, device=dev)
+    pack = _OccPack(None, shape=shape, device=torch.device(dev))
+    ws = torch.empty(lib.nfa_occ_threshold_workspace_bytes(occs.numel()), dtype=torch.uint8, device=dev)
+    for _ in range(2):  # the workspace is reusable
+        _lib.call("nfa_occ_threshold_pack", occs.device, *shape, _lib.ptr(occs), occ_thre, _lib.ptr(bins),
+                  _lib.ptr(pack.words), _lib.ptr(pack.coarse), _lib.ptr(pack.bounds), _lib.ptr(ws))
+    o_bins, o_thre = orc.occ_threshold(want, occ_thre)
+    np.testing.assert_array_equal(N(bins).reshape(-1), o_bins.reshape(-1))
+    assert np.float32(N(ws[16:20].view(torch.float32))[0]) == np.float32(o_thre)
+    fresh = _OccPack(bins)                                            # what nfa_occ_pack builds from the bool grid
+    assert torch.equal(pack.words, fresh.words) and torch.equal(pack.coarse, fresh.coarse)
+    assert torch.equal(pack.bounds, fresh.bounds)
+    # and on the reference's own `occs` the bool grid is the reference's
+    occs2 = T(z[case + "_occs_after"])
+    _lib.call("nfa_occ_threshold_pack", occs2.device, *shape, _lib.ptr(occs2), occ_thre, _lib.ptr(bins),
+              _lib.ptr(pack.words), _lib.ptr(pack.coarse), _lib.ptr(pack.bounds), _lib.ptr(ws))
+    np.testing.assert_array_equal(N(bins), z[case + "_binaries"])
+
+
+def test_estimator_update_native_path_feeds_sampling():
+    """_update on the GPU: same result as the reference's torch formulation on the same draws, and the packed grid
+    it leaves behind is what sampling() would have built."""
+    torch.manual_seed(11)
+    est = nfa.OccGridEstimator(torch.from_numpy(scenes.ROI_AABB), resolution=32, levels=2).to(dev)
+    est.train()
+
+    def occ_eval_fn(x):
+        return torch.exp(-6.0 * (x * x).sum(-1, keepdim=True)) * 0.05
+
+    for step in (0, 300):
+        before = est.occs.clone()
+        state = torch.cuda.get_rng_state()
+        est._update(step=step, occ_eval_fn=occ_eval_fn, occ_thre=0.01, ema_decay=0.95, warmup_steps=256)
+        got_occs, got_bins = est.occs.clone(), est.binaries.clone()
+        assert getattr(est.binaries, "_nfa_occ", None) is not None    # derived cache attached by the kernel
+        # replay with the reference's op sequence (occ_grid.py:367-404) on the same random draws
+        torch.cuda.set_rng_state(state)
+        est.occs.copy_(before)
+        per_level = est._get_all_cells() if step < 256 else est._sample_uniform_and_occupied_cells(est.cells_per_lvl // 4)
+        for lvl, indices in enumerate(per_level):
+            coords = est.grid_coords[indices]
+            x = (coords + torch.rand_like(coords, dtype=torch.float32)) / est.resolution
+            x = est.aabbs[lvl, :3] + x * (est.aabbs[lvl, 3:] - est.aabbs[lvl, :3])
+            occ = occ_eval_fn(x).squeeze(-1)
+            cell_ids = lvl * est.cells_per_lvl + indices
+            new = torch.maximum(est.occs[cell_ids] * 0.95, occ)
+            ref_occs = est.occs.clone()
+            ref_occs.scatter_reduce_(0, cell_ids, torch.full_like(new, -float("inf")), "amin", include_self=True)
+            ref_occs.scatter_reduce_(0, cell_ids, new, "amax", include_self=True)
+            est.occs.copy_(ref_occs)
+        assert torch.equal(est.occs, got_occs)
+        thre = torch.clamp(est.occs[est.occs >= 0].double().mean().float(), max=0.01)
+        assert torch.equal((est.occs > thre).view(got_bins.shape), got_bins)
+    assert getattr(est.binaries, "_nfa_occ", None) is not None        # still the kernel-made pack
+    ro, rd = scenes.ball_rays(4096)
+    a = est.sampling(T(ro), T(rd), render_step_size=1e-2)
+    est2 = nfa.OccGridEstimator(torch.from_numpy(scenes.ROI_AABB), resolution=32, levels=2).to(dev)
+    est2.binaries = got_bins.clone()
+    b = est2.sampling(T(ro), T(rd), render_step_size=1e-2)
+    assert a[0].numel() > 0 and all(torch.equal(x, y) for x, y in zip(a, b))
