@@ -140,22 +140,27 @@ NFA_HD bool lat_seek(const Lattice& L, float& t, float target, uint32_t& k)
         const LatPiece p = lat_piece(L, t);
         if (p.stuck) return false;
         if (p.regular) {
-            // estimate the step count inside this binade, then settle it with the
-            // exact predicate (monotone in j), so the estimate only affects speed.
-            const float inc_f = f_sub(lat_point(p, 1u), t);
-            const float x = div_estimate(f_sub(f_sub(target, L.half), t), inc_f);
-            uint32_t j;
-            if (!(x >= 1.0f)) j = 1u;
-            else if (x >= (float)p.jmax) j = p.jmax;
-            else j = (uint32_t)x;
-            while (j > 1u && f_add(lat_point(p, j - 1u), L.half) >= target) --j;
-            while (j < p.jmax && !(f_add(lat_point(p, j), L.half) >= target)) ++j;
-            t = lat_point(p, j);
-            k += j;
-            // not the last point of the binade: the target is reached.  At the last point the next step leaves
-            // the binade and is a real add (what the next pass of the loop would find out for itself).
-            if (j < p.jmax) return true;
-            if (f_add(t, L.half) >= target) return true;
+            // The whole binade lies before the target (the usual case while the lattice climbs from `near` to the
+            // first occupied cell): go to its last point; the step that leaves the binade is the real add below.
+            const float t_last = lat_point(p, p.jmax);
+            if (!(f_add(t_last, L.half) >= target)) {
+                t = t_last;
+                k += p.jmax;
+            } else {
+                // the target is reached inside this binade: estimate the step count, then settle it with the
+                // exact predicate (monotone in j), so the estimate only affects speed.
+                const float inc_f = f_sub(lat_point(p, 1u), t);
+                const float x = div_estimate(f_sub(f_sub(target, L.half), t), inc_f);
+                uint32_t j;
+                if (!(x >= 1.0f)) j = 1u;
+                else if (x >= (float)p.jmax) j = p.jmax;
+                else j = (uint32_t)x;
+                while (j > 1u && f_add(lat_point(p, j - 1u), L.half) >= target) --j;
+                while (j < p.jmax && !(f_add(lat_point(p, j), L.half) >= target)) ++j;
+                t = lat_point(p, j);
+                k += j;
+                return true;  // point j satisfies the predicate (at the latest j == jmax does, checked above)
+            }
         }
         const float tn = f_add(t, L.dt);
         if (!(tn > t)) return false;

@@ -24,6 +24,17 @@
 
 #include "lattice.cuh"
 
+// NFA_BRICK_STEPS == 0 (the shipped setting, see DESIGN.md "march"): the walk never takes whole bricks and the
+// cell loop reads every brick word straight from memory (L1-resident) without consulting the class mip.
+#ifndef NFA_BRICK_STEPS
+#define NFA_BRICK_STEPS 0
+#endif
+#if NFA_BRICK_STEPS
+#define NFA_IF_CLASSES(yes, no) yes
+#else
+#define NFA_IF_CLASSES(yes, no) no
+#endif
+
 // test hook: tests/host_sim counts loop passes (cell steps, brick steps, brick-loop entries); a no-op in the product
 #ifndef NFA_COUNT
 #define NFA_COUNT(i)
@@ -181,6 +192,7 @@ struct Walk {
     uint64_t word;
     uint32_t cls;          // class of the current brick (kBrickEmpty / kBrickMixed / kBrickFull)
     int a_off;             // whole-brick steps are off for the rest of the segment (its end is near)
+    int brick_steps;       // 0: never take whole bricks (measurement aid)
     // state flags (ints, not bools: the compiler would byte-pack bools and shuffle them around)
     int in_seg;
     int open;        // inside a stretch (no EMPTY since it began)
@@ -219,6 +231,7 @@ NFA_HD void walk_init(Walk& w, const float o[3], const float d[3], float near, f
     w.word = 0;
     w.cls = kBrickMixed;
     w.a_off = 0;
+    w.brick_steps = 1;
     w.in_seg = 0;
     w.open = 0;
     w.joined = 0;
@@ -231,8 +244,11 @@ NFA_HD void walk_init(Walk& w, const float o[3], const float d[3], float near, f
 
 NFA_HD void walk_load_brick(Walk& w, const OccView& occ)
 {
-    w.cls = occ_class(occ.coarse, w.brick);
-    w.word = w.cls == kBrickMixed ? occ.words[w.brick] : (w.cls == kBrickFull ? ~0ull : 0ull);
+    NFA_IF_CLASSES(
+        w.cls = occ_class(occ.coarse, w.brick);
+        w.word = w.cls == kBrickMixed ? occ.words[w.brick] : (w.cls == kBrickFull ? ~0ull : 0ull);,
+        w.cls = kBrickMixed;
+        w.word = occ.words[w.brick];)
 }
 
 // Steps left on one axis: until the index reaches the overflow index (reference
@@ -324,7 +340,7 @@ NFA_HD void walk_open_segment(Walk& w, const OccView& occ, int level, float lo, 
     w.brick = ((s.cur[0] >> 2) * occ.g.nb[1] + (s.cur[1] >> 2)) * occ.g.nb[2] + (s.cur[2] >> 2) + level * occ.g.wpl;
     w.bit = ((s.cur[0] & 3) << 4) | ((s.cur[1] & 3) << 2) | (s.cur[2] & 3);
     walk_load_brick(w, occ);
-    w.a_off = 0;
+    w.a_off = (NFA_BRICK_STEPS && w.brick_steps) ? 0 : 1;
     w.in_seg = 1;
 }
 
@@ -425,7 +441,6 @@ NFA_HD void walk_run(Walk& w, const Boxes& boxes, const OccView& occ, Buf& buf, 
         while (in_seg && n_desc < cap) {
             // ---------------- cell loop: while the brick is mixed (or brick steps are off)
             while (in_seg && n_desc < cap && (cls == kBrickMixed || a_off)) {
-                NFA_COUNT(0);
                 const float tt = f_min(f_min(tdx, f_min(tdy, tdz)), seg_hi);  // grid.cu:185-186
                 const int occd = (int)((uint32_t)(word >> bit) & 1u);
                 if (occd != open) {  // a stretch opens (its pend is frozen from here on) or closes
@@ -438,35 +453,33 @@ NFA_HD void walk_run(Walk& w, const Boxes& boxes, const OccView& occ, Buf& buf, 
                     open = occd;
                 }
                 // OCC(tt): the stretch grows; EMPTY(tt): the skip target moves on
-                d_open = occd ? tt : d_open;
-                pend = occd ? pend : f_max(pend, tt);
-                // utils_grid.cuh:116-142: x only if strictly smallest, else y if strictly below z, else z
+                if (occd) d_open = tt;
+                else pend = f_max(pend, tt);
+                // utils_grid.cuh:116-142: x only if strictly smallest, else y if strictly below z, else z.
+                // The occupancy cursor moves along the stepped axis: add inside the axis' 2-bit field of `bit`; a
+                // carry / borrow out of the field means the step left the brick.
                 const bool mx = tdx < tdy && tdx < tdz;
                 const bool my = !mx && (tdy < tdz);
-                const bool mz = !mx && !my;
-                tdx = mx ? f_add(tdx, dlx) : tdx;
-                tdy = my ? f_add(tdy, dly) : tdy;
-                tdz = mz ? f_add(tdz, dlz) : tdz;
-                remx -= mx ? 1 : 0;
-                remy -= my ? 1 : 0;
-                remz -= mz ? 1 : 0;
-                const int rem = mx ? remx : (my ? remy : remz);
-                // move the occupancy cursor along the stepped axis: add inside the axis' 2-bit field of `bit`;
-                // a carry / borrow out of the field means the step left the brick
-                const int db = mx ? dbx : (my ? dby : dbz);
-                const int mk = mx ? 0x30 : (my ? 0x0c : 0x03);
+                int db, mk, sb;
+                if (mx) { tdx = f_add(tdx, dlx); --remx; db = dbx; mk = 0x30; sb = sbx; }
+                else if (my) { tdy = f_add(tdy, dly); --remy; db = dby; mk = 0x0c; sb = sby; }
+                else { tdz = f_add(tdz, dlz); --remz; db = dbz; mk = 0x03; sb = sbz; }
                 const int nb = bit + db;
                 const bool crossed = ((nb ^ bit) & ~mk) != 0;
                 bit = (bit & ~mk) | (nb & mk);
-                if (rem == 0 || tt >= t_stop) {
+                // only the stepped counter changed and all three were positive: one of them is 0 <=> that one is
+                const int rem_min = remx < remy ? (remx < remz ? remx : remz) : (remy < remz ? remy : remz);
+                if (rem_min == 0 || tt >= t_stop) {
                     in_seg = 0;  // overflow index / grid edge reached, or (accelerated) past the occupied box
                 } else if (crossed) {
-                    brick += mx ? sbx : (my ? sby : sbz);
-                    cls = occ_class(occ.coarse, brick);
-                    word = cls == kBrickMixed ? occ.words[brick] : (cls == kBrickFull ? ~0ull : 0ull);
+                    brick += sb;
+                    NFA_IF_CLASSES(
+                        cls = occ_class(occ.coarse, brick);
+                        word = cls == kBrickMixed ? occ.words[brick] : (cls == kBrickFull ? ~0ull : 0ull);,
+                        word = occ.words[brick];)
                 }
             }
-            if (!in_seg || n_desc >= cap) break;
+            if (!NFA_BRICK_STEPS || !in_seg || n_desc >= cap) break;
 
             // ---------------- brick loop.  Per axis: q = crossings left inside the brick, B = time of the crossing
             // that leaves it (q more chain adds), cnt = bricks that may still be taken whole along this axis

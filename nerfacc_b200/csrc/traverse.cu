@@ -27,6 +27,7 @@
 // f32 chains (march) and by HBM stores (expand).  See DESIGN.md.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/nerfacc_b200.h"
 #include "expand.cuh"
@@ -45,8 +46,14 @@ constexpr int kSortBuckets = 256;   // counting sort of a tile's rays by expecte
 // (65 536 rays: 147 tiles of 448 rays, one per SM, instead of 512 tiles of 128 = 4 on some SMs and 3 on
 // others); ties go to the larger tile, whose rays sort into more uniform warps.  Large batches (several
 // waves) use 256.
-__host__ __device__ inline int march_tile_rays(int32_t n_rays)
+inline int march_tile_rays(int32_t n_rays)
 {
+    static const int forced = [] {  // measurement aid: NFA_MARCH_TILE=<multiple of 32> pins the tile size
+        const char* e = getenv("NFA_MARCH_TILE");
+        const int v = e ? atoi(e) : 0;
+        return (v >= 32 && v <= kMaxTileRays && v % 32 == 0) ? v : 0;
+    }();
+    if (forced) return forced;
     const int kSMs = 148;
     if (n_rays <= 32) return 32;
     if ((int64_t)n_rays > (int64_t)kSMs * 2048) return 256;
@@ -101,7 +108,7 @@ struct Workspace {
 
 __host__ __device__ inline int64_t align16(int64_t x) { return (x + 15) & ~(int64_t)15; }
 
-__host__ __device__ inline int64_t ws_bytes(int32_t n_rays, int64_t run_capacity)
+inline int64_t ws_bytes(int32_t n_rays, int64_t run_capacity)
 {
     const int tile = march_tile_rays(n_rays);
     const int64_t nt = (n_rays + tile - 1) / tile;
@@ -109,7 +116,7 @@ __host__ __device__ inline int64_t ws_bytes(int32_t n_rays, int64_t run_capacity
            run_capacity * (int64_t)sizeof(RunRec);
 }
 
-__host__ __device__ inline Workspace ws_view(void* base, int32_t n_rays, int64_t run_capacity)
+inline Workspace ws_view(void* base, int32_t n_rays, int64_t run_capacity)
 {
     Workspace w;
     char* p = (char*)base;
@@ -230,6 +237,7 @@ struct MarchParams {
     const int64_t* t_indices;
     const uint8_t* hits;
     float step_size;
+    int32_t brick_steps;  // 0: cell loop only (NFA_MARCH_BRICK_STEPS=0 in the environment; measurement aid)
     Workspace ws;
     int64_t* totals;
     int64_t* totals_host;  // optional host-visible mirror (pinned memory), saves a D2H copy node
@@ -414,6 +422,7 @@ __global__ void __launch_bounds__(kMaxTileRays) march_kernel(const MarchParams p
     w.done = active ? 0 : 1;
     // nothing after the last occupied cell is observable without a terminate plane on one level
     w.accel = (kSingle && p.terminate == nullptr) ? 1 : 0;
+    w.brick_steps = p.brick_steps;
     SmemBuf buf;
     buf.pend = s_pend;
     buf.open = s_open;
@@ -1014,6 +1023,11 @@ int32_t nfa_march(int32_t n_rays, const float* rays_o, const float* rays_d, cons
     p.t_indices = have_sorted ? t_indices : nullptr;
     p.hits = have_sorted ? hits : nullptr;
     p.step_size = step_size;
+    static const int brick_steps = [] {
+        const char* e = getenv("NFA_MARCH_BRICK_STEPS");
+        return (e && e[0] == '0') ? 0 : 1;
+    }();
+    p.brick_steps = brick_steps;
     p.ws = ws_view(workspace, n_rays, run_capacity);
     p.totals = totals;
     p.totals_host = totals_host;
@@ -1021,7 +1035,7 @@ int32_t nfa_march(int32_t n_rays, const float* rays_o, const float* rays_d, cons
     const int tiles = p.ws.n_tiles, tile_rays = p.ws.tile_rays;
     const size_t coarse_bytes = (size_t)p.coarse_words * 4;
     // keep the class mip in shared memory while it leaves room for the tile's own buffers (256^3: 64 KiB)
-    const bool smem_coarse = coarse_bytes <= 128 * 1024;
+    const bool smem_coarse = NFA_BRICK_STEPS && coarse_bytes <= 128 * 1024;  // only the brick loop reads the mip
     const size_t dyn = march_smem_bytes(tile_rays, smem_coarse ? coarse_bytes : 0);
 #define NFA_LAUNCH_MARCH(S, C)                                                                          \
     do {                                                                                                \

@@ -37,19 +37,17 @@ def orc():
     return oracle
 
 
-@pytest.fixture(scope="session")
-def host_sim():
-    """CPU build of the product's host+device traversal headers (tests/host_sim)."""
+def _build_host_sim(brick_steps: int):
     import ctypes as C
     d = os.path.join(ROOT, "tests", "host_sim")
-    so = os.path.join(d, "libhost_sim.so")
+    so = os.path.join(d, "libhost_sim_brick.so" if brick_steps else "libhost_sim.so")
     src = os.path.join(d, "host_sim.cpp")
     hdrs = [os.path.join(ROOT, "nerfacc_b200", "csrc", h) for h in ("lattice.cuh", "march.cuh", "march_generic.cuh", "expand.cuh", "occ_pack.cuh", "nfa_math.cuh",
                                                                      "pdf.cuh")]
     newest = max(os.path.getmtime(p) for p in [src] + hdrs)
     if not os.path.exists(so) or os.path.getmtime(so) < newest:
         subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
-                               "-Wno-unknown-pragmas", "-o", so, src])
+                               "-Wno-unknown-pragmas", f"-DNFA_BRICK_STEPS={brick_steps}", "-o", so, src])
     lib = C.CDLL(so)
     lib.sim_chain.restype = C.c_float
     lib.sim_chain.argtypes = [C.c_float, C.c_float, C.c_uint32]
@@ -61,6 +59,19 @@ def host_sim():
     lib.sim_philox_uniform.restype = C.c_float
     lib.sim_philox_uniform.argtypes = [C.c_uint64] * 3
     return lib
+
+
+@pytest.fixture(scope="session")
+def host_sim():
+    """CPU build of the product's host+device traversal headers (tests/host_sim), as shipped."""
+    return _build_host_sim(0)
+
+
+@pytest.fixture(scope="session")
+def host_sim_brick():
+    """The same headers with the whole-brick loop of the walk compiled in (NFA_BRICK_STEPS=1, march.cuh): exact, but
+    slower on the GPU under SIMT divergence, so not shipped; kept tested."""
+    return _build_host_sim(1)
 
 
 def load_golden(name):

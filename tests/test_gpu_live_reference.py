@@ -54,9 +54,9 @@ def test_config2_full_size_bit_exact_sampling_and_rendering():
 def test_config3_256_grid_inference_bit_exact():
     ref = reference("config3")
     got = rr.run_case(nfa, "config3", dev)
-    assert int(got["n"]) == int(ref["n"]) and int(ref["n"]) > 200 * 262144
+    assert int(got["n"]) == int(ref["n"]) and int(ref["n"]) > 100 * 262144
     np.testing.assert_array_equal(got["packed_info"], ref["packed_info"])
-    for k in ("sha_ri", "sha_ts", "sha_te"):                  # bit-exact over all ~68 M samples
+    for k in ("sha_ri", "sha_ts", "sha_te"):                  # bit-exact over all ~34 M samples
         assert str(got[k]) == str(ref[k]), k
     for k in ("colors", "opacities", "depths"):
         assert np.abs(got[k] - ref[k]).max() < 1e-5, k

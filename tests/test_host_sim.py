@@ -280,3 +280,40 @@ def test_generic_marcher_modes(host_sim, orc):
     assert _check_generic(host_sim, orc, ro, rd, bins4, a4, zero, inf, 1e-2, 0.003, limit=5, over_allocate=True) > 0
     # a limit without over-allocation (two-pass; the mask is ignored there, reference grid.cu:418,450)
     assert _check_generic(host_sim, orc, ro, rd, bins4, a4, zero, inf, 1e-2, 0.0, limit=50, mask=mask) > 0
+
+
+# ---------------------------------------------------------------- the whole-brick loop (compiled out of the product)
+
+def test_brick_loop_variant_is_bit_exact_and_actually_skips(host_sim_brick, orc):
+    """march.cuh with NFA_BRICK_STEPS=1: uniform 4x4x4 bricks are crossed in one step.  Same outputs as the oracle
+    on every scene class; on the ball scene it replaces most cell steps."""
+    import ctypes as C
+    sim = host_sim_brick
+    R = 1024
+    ro, rd = scenes.ball_rays(R)
+    bins, aabbs = scenes.ball_grid(128), scenes.nested_aabbs(1)
+    near, far = np.zeros(R, np.float32), np.full(R, 1e10, np.float32)
+    counts = (C.c_long * 3)()
+    sim.sim_walk_counts(counts, 1)
+    _compare(sim, orc, ro, rd, bins, aabbs, near, far, scenes.BALL_STEP, accel=1)
+    sim.sim_walk_counts(counts, 1)
+    cells, bricks, entries = counts[0] / R, counts[1] / R, counts[2] / R
+    assert bricks > 10 and cells < 40 and entries < 5          # ~98 cell steps per ray without the brick loop
+    rng = np.random.default_rng(7)
+    _compare(sim, orc, ro, rd, bins, aabbs, near, far, scenes.BALL_STEP)
+    frag = bins & (rng.random(bins.shape) > 0.5)
+    _compare(sim, orc, ro[:512], rd[:512], frag, aabbs, near[:512], far[:512], scenes.BALL_STEP, accel=1)
+    ro2 = rng.standard_normal((200, 3)).astype(np.float32)
+    rd2 = rng.standard_normal((200, 3)).astype(np.float32)
+    rd2 /= np.linalg.norm(rd2, axis=1, keepdims=True)
+    bins4 = rng.random((4, 32, 32, 32)) > 0.5
+    blocks = np.kron(rng.random((4, 8, 8, 8)) > 0.5, np.ones((1, 4, 4, 4), bool))   # whole bricks on / off
+    a4 = scenes.nested_aabbs(4)
+    zero, inf = np.zeros(200, np.float32), np.full(200, np.inf, np.float32)
+    for grid in (bins4, blocks, blocks & bins4):
+        _compare(sim, orc, ro2, rd2, grid, a4, zero, inf, 2e-3, multi=True)
+        _compare(sim, orc, ro2, rd2, grid[:1], a4[:1], zero, inf, 3e-3, accel=1)
+    _compare(sim, orc, ro2, rd2, rng.random((2, 30, 17, 5)) > 0.3, a4[:2], zero, inf, 4e-3, multi=True)
+    full = np.ones((1, 16, 16, 16), bool)
+    _compare(sim, orc, ro2, rd2, full, a4[:1], zero, inf, 1e-2, accel=1)
+    _compare(sim, orc, ro2, rd2, full, a4[:1], rng.random(200).astype(np.float32), (1 + rng.random(200) * 3).astype(np.float32), 1e-2)
