@@ -14,7 +14,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libnerfacc_b200.so")
+LIB_PATH = os.environ.get("NFA_LIB") or os.path.join(_HERE, "csrc", "libnerfacc_b200.so")  # NFA_LIB: kernel-variant A/B runs
 
 _c_i32, _c_i64, _c_f32, _c_ptr = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 

@@ -714,18 +714,11 @@ __device__ __forceinline__ void hot_store4(float* base, int g, const float x[4],
     }
 }
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 4) composite_fwd_hot_kernel(const CompositeParams p, int n_total)
+__global__ void __launch_bounds__(kWarpsPerCta * 32) composite_fwd_hot_kernel(const CompositeParams p, int n_total)
 {
     const int lane = threadIdx.x & 31;
-    const int stride = gridDim.x * kWarpsPerCta;
-    int r = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-    // The segment of the NEXT ray of this warp is fetched while the current one is processed: read at the top of
-    // the loop it was a dependent load (~0.6 us) in front of every ray's sample loads, with nothing in flight.
-    longlong2 pi_next = make_longlong2(0, 0);
-    if (r < p.n_rays) pi_next = __ldg(reinterpret_cast<const longlong2*>(p.packed_info) + r);
-    for (; r < p.n_rays; r += stride) {
-        const longlong2 pi = pi_next;
-        if (r + stride < p.n_rays) pi_next = __ldg(reinterpret_cast<const longlong2*>(p.packed_info) + (r + stride));
+    for (int r = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); r < p.n_rays; r += gridDim.x * kWarpsPerCta) {
+        const longlong2 pi = *reinterpret_cast<const longlong2*>(p.packed_info + 2 * (int64_t)r);
         const int start = (int)pi.x, end = (int)(pi.x + pi.y);
         float carry = 0.f, aO = 0.f, aD = 0.f, aC0 = 0.f, aC1 = 0.f, aC2 = 0.f;
         if (end > start) {
@@ -778,40 +771,20 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) composite_fwd_hot_kernel
 }
 
 // backward of the above for upstream gradients on colours / opacities / depths only
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 4) composite_bwd_hot_kernel(const CompositeParams p, int n_total)
+__global__ void __launch_bounds__(kWarpsPerCta * 32) composite_bwd_hot_kernel(const CompositeParams p, int n_total)
 {
     const int lane = threadIdx.x & 31;
-    const int stride = gridDim.x * kWarpsPerCta;
-    int r = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-    // per-ray inputs of the NEXT ray of this warp (segment, upstream gradients, saved sums) are fetched while the
-    // current ray is processed, so no dependent load sits in front of a ray's sample loads
-    struct RayIn {
-        longlong2 pi;
-        float gc0, gc1, gc2, go, gd, r0, r1, r2, rO, rD;
-    };
-    auto fetch = [&](int q) {
-        RayIn x;
-        x.pi = __ldg(reinterpret_cast<const longlong2*>(p.packed_info) + q);
-        x.gc0 = x.gc1 = x.gc2 = x.go = x.gd = 0.f;
-        if (p.gC) {
-            x.gc0 = __ldg(p.gC + 3 * (int64_t)q); x.gc1 = __ldg(p.gC + 3 * (int64_t)q + 1); x.gc2 = __ldg(p.gC + 3 * (int64_t)q + 2);
-        }
-        if (p.gO) x.go = __ldg(p.gO + q);
-        if (p.gD) x.gd = __ldg(p.gD + q);
-        const float* rw = p.raw + 5 * (int64_t)q;
-        x.r0 = __ldg(rw); x.r1 = __ldg(rw + 1); x.r2 = __ldg(rw + 2); x.rO = __ldg(rw + 3); x.rD = __ldg(rw + 4);
-        return x;
-    };
-    RayIn nxt = {};
-    if (r < p.n_rays) nxt = fetch(r);
-    for (; r < p.n_rays; r += stride) {
-        const RayIn cur = nxt;
-        if (r + stride < p.n_rays) nxt = fetch(r + stride);
-        const longlong2 pi = cur.pi;
+    for (int r = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); r < p.n_rays; r += gridDim.x * kWarpsPerCta) {
+        const longlong2 pi = *reinterpret_cast<const longlong2*>(p.packed_info + 2 * (int64_t)r);
         const int start = (int)pi.x, end = (int)(pi.x + pi.y);
         if (end <= start) continue;
-        float gc0 = cur.gc0, gc1 = cur.gc1, gc2 = cur.gc2, go = cur.go, gd = cur.gd;
-        const float raw[5] = {cur.r0, cur.r1, cur.r2, cur.rO, cur.rD};
+        float gc0 = 0.f, gc1 = 0.f, gc2 = 0.f, go = 0.f, gd = 0.f;
+        if (p.gC) {
+            gc0 = p.gC[3 * (int64_t)r]; gc1 = p.gC[3 * (int64_t)r + 1]; gc2 = p.gC[3 * (int64_t)r + 2];
+        }
+        if (p.gO) go = p.gO[r];
+        if (p.gD) gd = p.gD[r];
+        const float* raw = p.raw + 5 * (int64_t)r;
         const float rO = raw[3], rD = raw[4];
         if (p.bkgd) go -= gc0 * p.bkgd[0] + gc1 * p.bkgd[1] + gc2 * p.bkgd[2];
         if (p.expected_depths && p.gD) {

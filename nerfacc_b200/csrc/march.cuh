@@ -29,6 +29,12 @@
 #ifndef NFA_BRICK_STEPS
 #define NFA_BRICK_STEPS 0
 #endif
+// NFA_LOOP_VARIANT: 2 (shipped) = cell loop without branches (selects + one predicated load); 1 = the same loop
+// written with if / else (what the host build of tests/host_sim always uses).  Measured on a B200, config 2:
+// 57.4 us against 61.4 us -- each branch region costs a lone warp more than the instructions it skips.
+#ifndef NFA_LOOP_VARIANT
+#define NFA_LOOP_VARIANT 2
+#endif
 #if NFA_BRICK_STEPS
 #define NFA_IF_CLASSES(yes, no) yes
 #else
@@ -441,7 +447,40 @@ NFA_HD void walk_run(Walk& w, const Boxes& boxes, const OccView& occ, Buf& buf, 
         while (in_seg && n_desc < cap) {
             // ---------------- cell loop: while the brick is mixed (or brick steps are off)
             while (in_seg && n_desc < cap && (cls == kBrickMixed || a_off)) {
+                NFA_COUNT(0);
                 const float tt = f_min(f_min(tdx, f_min(tdy, tdz)), seg_hi);  // grid.cu:185-186
+                // --- the DDA step first (utils_grid.cuh:116-142: x only if strictly smallest, else y if strictly
+                // below z, else z).  It does not depend on the occupancy, and the brick word that the previous pass
+                // may have requested has these ~30 instructions to arrive before the bit test below reads it.
+                // The occupancy cursor moves along the stepped axis: add inside the axis' 2-bit field of `bit`; a
+                // carry / borrow out of the field means the step left the brick.
+                const bool mx = tdx < tdy && tdx < tdz;
+                const bool my = !mx && (tdy < tdz);
+#if NFA_LOOP_VARIANT >= 2
+                const bool mz = !mx && !my;
+                tdx = mx ? f_add(tdx, dlx) : tdx;
+                tdy = my ? f_add(tdy, dly) : tdy;
+                tdz = mz ? f_add(tdz, dlz) : tdz;
+                remx -= mx ? 1 : 0;
+                remy -= my ? 1 : 0;
+                remz -= mz ? 1 : 0;
+                const int db = mx ? dbx : (my ? dby : dbz);
+                const int mk = mx ? 0x30 : (my ? 0x0c : 0x03);
+                const int sb = mx ? sbx : (my ? sby : sbz);
+#else
+                int db, mk, sb;
+                if (mx) { tdx = f_add(tdx, dlx); --remx; db = dbx; mk = 0x30; sb = sbx; }
+                else if (my) { tdy = f_add(tdy, dly); --remy; db = dby; mk = 0x0c; sb = sby; }
+                else { tdz = f_add(tdz, dlz); --remz; db = dbz; mk = 0x03; sb = sbz; }
+#endif
+                const int nb = bit + db;
+                const bool crossed = ((nb ^ bit) & ~mk) != 0;
+                const int bit_next = (bit & ~mk) | (nb & mk);
+                // only the stepped counter changed and all three were positive: one of them is 0 <=> that one is
+                const int rem_min = remx < remy ? (remx < remz ? remx : remz) : (remy < remz ? remy : remz);
+                const bool stop = rem_min == 0 || tt >= t_stop;  // overflow index / grid edge, or past the occupied box
+
+                // --- the cell just left: OCC(tt) / EMPTY(tt)
                 const int occd = (int)((uint32_t)(word >> bit) & 1u);
                 if (occd != open) {  // a stretch opens (its pend is frozen from here on) or closes
                     if (open) {      // EMPTY(tt) closes the stretch
@@ -452,32 +491,34 @@ NFA_HD void walk_run(Walk& w, const Boxes& boxes, const OccView& occ, Buf& buf, 
                     }
                     open = occd;
                 }
-                // OCC(tt): the stretch grows; EMPTY(tt): the skip target moves on
-                if (occd) d_open = tt;
-                else pend = f_max(pend, tt);
-                // utils_grid.cuh:116-142: x only if strictly smallest, else y if strictly below z, else z.
-                // The occupancy cursor moves along the stepped axis: add inside the axis' 2-bit field of `bit`; a
-                // carry / borrow out of the field means the step left the brick.
-                const bool mx = tdx < tdy && tdx < tdz;
-                const bool my = !mx && (tdy < tdz);
-                int db, mk, sb;
-                if (mx) { tdx = f_add(tdx, dlx); --remx; db = dbx; mk = 0x30; sb = sbx; }
-                else if (my) { tdy = f_add(tdy, dly); --remy; db = dby; mk = 0x0c; sb = sby; }
-                else { tdz = f_add(tdz, dlz); --remz; db = dbz; mk = 0x03; sb = sbz; }
-                const int nb = bit + db;
-                const bool crossed = ((nb ^ bit) & ~mk) != 0;
-                bit = (bit & ~mk) | (nb & mk);
-                // only the stepped counter changed and all three were positive: one of them is 0 <=> that one is
-                const int rem_min = remx < remy ? (remx < remz ? remx : remz) : (remy < remz ? remy : remz);
-                if (rem_min == 0 || tt >= t_stop) {
-                    in_seg = 0;  // overflow index / grid edge reached, or (accelerated) past the occupied box
+                if (occd) d_open = tt;             // the stretch grows
+                else pend = f_max(pend, tt);       // the skip target moves on
+
+                // --- commit the step
+                bit = bit_next;
+#if NFA_LOOP_VARIANT == 2 && !NFA_BRICK_STEPS && defined(__CUDA_ARCH__)
+                in_seg = stop ? 0 : 1;
+                brick += crossed ? sb : 0;
+                {   // predicated load: a branch here costs more than the load it skips
+                    const uint64_t* src = occ.words + brick;
+                    asm volatile("{\n.reg .pred p;\nsetp.ne.s32 p, %2, 0;\n@p ld.global.nc.u64 %0, [%1];\n}"
+                                 : "+l"(word) : "l"(src), "r"((int)(crossed && !stop)));
+                }
+#else
+                if (stop) {
+                    in_seg = 0;
                 } else if (crossed) {
                     brick += sb;
                     NFA_IF_CLASSES(
-                        cls = occ_class(occ.coarse, brick);
-                        word = cls == kBrickMixed ? occ.words[brick] : (cls == kBrickFull ? ~0ull : 0ull);,
+                        if (a_off) {  // no brick steps for this ray any more: the class is of no use
+                            word = occ.words[brick];
+                        } else {
+                            cls = occ_class(occ.coarse, brick);
+                            word = cls == kBrickMixed ? occ.words[brick] : (cls == kBrickFull ? ~0ull : 0ull);
+                        },
                         word = occ.words[brick];)
                 }
+#endif
             }
             if (!NFA_BRICK_STEPS || !in_seg || n_desc >= cap) break;
 

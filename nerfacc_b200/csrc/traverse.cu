@@ -237,7 +237,7 @@ struct MarchParams {
     const int64_t* t_indices;
     const uint8_t* hits;
     float step_size;
-    int32_t brick_steps;  // 0: cell loop only (NFA_MARCH_BRICK_STEPS=0 in the environment; measurement aid)
+    int32_t brick_steps;  // warps per tile (the longest rays) that may take whole bricks; needs -DNFA_BRICK_STEPS=1
     Workspace ws;
     int64_t* totals;
     int64_t* totals_host;  // optional host-visible mirror (pinned memory), saves a D2H copy node
@@ -422,7 +422,9 @@ __global__ void __launch_bounds__(kMaxTileRays) march_kernel(const MarchParams p
     w.done = active ? 0 : 1;
     // nothing after the last occupied cell is observable without a terminate plane on one level
     w.accel = (kSingle && p.terminate == nullptr) ? 1 : 0;
-    w.brick_steps = p.brick_steps;
+    // whole-brick steps (when compiled in) only for the tile's longest rays: after the sort these sit in the last
+    // warps, pass near the middle of the occupied region and so cross the same kinds of brick together
+    w.brick_steps = (p.brick_steps > 0 && tid >= T - 32 * p.brick_steps) ? 1 : 0;
     SmemBuf buf;
     buf.pend = s_pend;
     buf.open = s_open;
@@ -1023,9 +1025,9 @@ int32_t nfa_march(int32_t n_rays, const float* rays_o, const float* rays_d, cons
     p.t_indices = have_sorted ? t_indices : nullptr;
     p.hits = have_sorted ? hits : nullptr;
     p.step_size = step_size;
-    static const int brick_steps = [] {
-        const char* e = getenv("NFA_MARCH_BRICK_STEPS");
-        return (e && e[0] == '0') ? 0 : 1;
+    static const int brick_steps = [] {  // number of (longest-ray) warps per tile that take whole bricks
+        const char* e = getenv("NFA_MARCH_BRICK_WARPS");
+        return e ? atoi(e) : 2;
     }();
     p.brick_steps = brick_steps;
     p.ws = ws_view(workspace, n_rays, run_capacity);

@@ -140,6 +140,94 @@ t = timed(lambda: pn.sampling([prop_fn], [64], 32, n_rays=R4, near_plane=0.2, fa
 emit(config="4: PropNetEstimator.sampling 262144 rays, one proposal level 64 -> 32 final", ms=t * 1e3,
      gsamples_per_s=R4 * 32 / t / 1e9)
 
+# ---------------------------------------------------------------- standalone scans at config-2 size (K5: CUB by-key vs ours)
+est2 = nf.OccGridEstimator(torch.from_numpy(scenes.ROI_AABB), resolution=128).to(dev)
+est2.binaries = torch.from_numpy(scenes.ball_grid(128)).to(dev)
+with torch.no_grad():
+    ri2, ts2, te2 = est2.sampling(tro2, trd2, render_step_size=scenes.BALL_STEP)
+N2 = ri2.numel()
+x2 = torch.rand(N2, device=dev)
+ri_plain = ri2.clone()  # carries no stashed segments: the key-addressed kernels run
+pi2 = nf.pack_info(ri_plain, R2)
+emit(config="scans: N = 8.5 M samples in 65536 segments", n=N2,
+     exclusive_sum_indices_us=timed(lambda: nf.exclusive_sum(x2, indices=ri_plain), 30, 5) * 1e6,
+     inclusive_sum_indices_us=timed(lambda: nf.inclusive_sum(x2, indices=ri_plain), 30, 5) * 1e6,
+     exclusive_prod_indices_us=timed(lambda: nf.exclusive_prod(x2, indices=ri_plain), 30, 5) * 1e6,
+     exclusive_sum_packed_us=timed(lambda: nf.exclusive_sum(x2, packed_info=pi2), 30, 5) * 1e6,
+     pack_info_us=timed(lambda: nf.pack_info(ri_plain, R2), 30, 5) * 1e6,
+     note="8 B/sample algorithmic (read + write f32) + 8 B/sample of int64 keys on the `indices` route")
+
+# ---------------------------------------------------------------- f3: test-mode marching with early termination
+# the loop of /root/reference/examples/utils.py:267-439 (render_image_with_occgrid_test) on config-2 rays, through
+# the public API only: traverse_grids(limit, over_allocate, rays_mask) -> render_weight_from_density(prefix_trans)
+# -> 3 x accumulate_along_rays_
+def test_mode_render(estimator, rays_o, rays_d, step, sigma_const=20.0, early_stop_eps=1e-4, max_samples=1024):
+    n = rays_o.shape[0]
+    opacity = torch.zeros(n, 1, device=dev)
+    depth = torch.zeros(n, 1, device=dev)
+    rgb = torch.zeros(n, 3, device=dev)
+    ray_mask = torch.ones(n, device=dev).bool()
+    near_planes = torch.zeros(n, device=dev)
+    far_planes = torch.full((n,), 1e10, device=dev)
+    t_mins, t_maxs, hits = nf.ray_aabb_intersect(rays_o, rays_d, estimator.aabbs)
+    t_sorted = torch.cat([t_mins, t_maxs], -1)
+    t_indices = torch.arange(0, 2, device=dev, dtype=torch.int64).expand(n, 2)
+    opc_thre = 1 - early_stop_eps
+    iter_samples = total = rounds = 0
+    while iter_samples < max_samples:
+        n_alive = int(ray_mask.sum().item())
+        if n_alive == 0:
+            break
+        n_samples = max(min(n // n_alive, 64), 1)
+        iter_samples += n_samples
+        intervals, samples, term = nf.traverse_grids(rays_o, rays_d, estimator.binaries, estimator.aabbs, near_planes,
+                                                     far_planes, step, 0.0, n_samples, True, ray_mask, t_sorted,
+                                                     t_indices, hits)
+        t_starts = intervals.vals[intervals.is_left]
+        t_ends = intervals.vals[intervals.is_right]
+        ray_indices = samples.ray_indices[samples.is_valid]
+        sigmas = torch.full_like(t_starts, sigma_const)
+        rgbs = torch.sigmoid(t_starts)[:, None].expand(-1, 3)
+        weights, _, _ = nf.render_weight_from_density(t_starts, t_ends, sigmas, ray_indices=ray_indices, n_rays=n,
+                                                      prefix_trans=1 - opacity[ray_indices].squeeze(-1))
+        nf.accumulate_along_rays_(weights, values=rgbs, ray_indices=ray_indices, outputs=rgb)
+        nf.accumulate_along_rays_(weights, values=None, ray_indices=ray_indices, outputs=opacity)
+        nf.accumulate_along_rays_(weights, values=(t_starts + t_ends)[..., None] / 2.0, ray_indices=ray_indices,
+                                  outputs=depth)
+        near_planes = term
+        ray_mask = torch.logical_and(opacity.view(-1) <= opc_thre, samples.packed_info[:, 1] == n_samples)
+        total += ray_indices.shape[0]
+        rounds += 1
+    return rgb, opacity, total, rounds
+
+
+with torch.no_grad():
+    rgb_t, op_t, total_t, rounds_t = test_mode_render(est2, tro2, trd2, scenes.BALL_STEP)
+    t_tm = timed(lambda: test_mode_render(est2, tro2, trd2, scenes.BALL_STEP), 5, 2)
+    one = timed(lambda: nf.traverse_grids(tro2, trd2, est2.binaries, est2.aabbs, torch.zeros(R2, device=dev),
+                                          torch.full((R2,), 1e10, device=dev), scenes.BALL_STEP, 0.0, 4, True,
+                                          torch.ones(R2, dtype=torch.bool, device=dev)), 20, 3)
+emit(config="f3: test-mode rendering loop (bounded marching + prefix_trans + in-place accumulate), 65536 rays, sigma = 20",
+     total_samples=total_t, rounds=rounds_t, loop_ms=t_tm * 1e3, checksum_rgb=float(rgb_t.double().sum()),
+     checksum_opacity=float(op_t.double().sum()), one_bounded_traverse_call_us=one * 1e6)
+
+# ---------------------------------------------------------------- f4: grid maintenance (128^3, one level)
+est4 = nf.OccGridEstimator(torch.from_numpy(scenes.ROI_AABB), resolution=128).to(dev)
+est4.train()
+
+
+def occ_eval_fn(x):
+    return torch.exp(-6.0 * (x * x).sum(-1, keepdim=True)) * 0.05
+
+
+est4._update(step=0, occ_eval_fn=occ_eval_fn)
+t_warm = timed(lambda: est4._update(step=0, occ_eval_fn=occ_eval_fn), 10, 2)
+t_samp = timed(lambda: est4._update(step=1000, occ_eval_fn=occ_eval_fn), 10, 2)
+t_next = timed(lambda: (est4._update(step=1000, occ_eval_fn=occ_eval_fn),
+                        est4.sampling(tro2, trd2, render_step_size=scenes.BALL_STEP)), 10, 2)
+emit(config="f4: OccGridEstimator._update, 128^3", all_cells_us=t_warm * 1e6, sampled_cells_us=t_samp * 1e6,
+     update_then_sampling_us=t_next * 1e6, occupied=int(est4.binaries.sum()))
+
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 with open(os.path.join(ROOT, "gpurun_out", f"extra_configs_{impl}.json"), "w") as f:
     for ln in lines:

@@ -936,7 +936,7 @@ def test_estimator_update_native_path_feeds_sampling():
         return torch.exp(-6.0 * (x * x).sum(-1, keepdim=True)) * 0.05
 
     for step in (0, 300):
-        before = est.occs.clone()
+        before, bins_before = est.occs.clone(), est.binaries
         state = torch.cuda.get_rng_state()
         est._update(step=step, occ_eval_fn=occ_eval_fn, occ_thre=0.01, ema_decay=0.95, warmup_steps=256)
         got_occs, got_bins = est.occs.clone(), est.binaries.clone()
@@ -944,7 +944,9 @@ def test_estimator_update_native_path_feeds_sampling():
         # replay with the reference's op sequence (occ_grid.py:367-404) on the same random draws
         torch.cuda.set_rng_state(state)
         est.occs.copy_(before)
+        kernel_bins, est.binaries = est.binaries, bins_before          # the cell draw looks at the OLD grid
         per_level = est._get_all_cells() if step < 256 else est._sample_uniform_and_occupied_cells(est.cells_per_lvl // 4)
+        est.binaries = kernel_bins
         for lvl, indices in enumerate(per_level):
             coords = est.grid_coords[indices]
             x = (coords + torch.rand_like(coords, dtype=torch.float32)) / est.resolution
