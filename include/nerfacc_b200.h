@@ -28,7 +28,7 @@ extern "C" {
 #define NFA_ERR_ARG (-1)         /* null pointer / negative size / inconsistent sizes */
 #define NFA_ERR_UNSUPPORTED (-2) /* valid request outside what this build implements */
 
-#define NFA_ABI_VERSION 9
+#define NFA_ABI_VERSION 10
 
 typedef void* nfa_stream_t; /* cudaStream_t */
 
@@ -83,6 +83,11 @@ int64_t nfa_occ_threshold_workspace_bytes(int64_t n_cells);
 int32_t nfa_occ_threshold_pack(int32_t n_grids, int32_t rx, int32_t ry, int32_t rz, const float* occs, float occ_thre,
                                uint8_t* binaries, uint64_t* words, uint32_t* coarse, int32_t* bounds, void* workspace,
                                nfa_stream_t stream);
+
+/* packed_info = [exclusive cumsum(counts), counts] for int64 per-ray counts (the chunk_starts / chunk_cnts pair of
+ * data_spec.hpp:86-96 after a one-pass traversal).  workspace: nfa_pack_info_workspace_bytes(n_rays) bytes. */
+int32_t nfa_counts_to_packed_info(int32_t n_rays, const int64_t* counts, int64_t* packed_info, void* workspace,
+                                  nfa_stream_t stream);
 
 /* ----------------------------------------------------------------------- */
 /* Grid traversal, constant step (cone_angle == 0, step_size > 0)           */
@@ -145,12 +150,17 @@ int32_t nfa_expand_intervals(int32_t n_rays, int64_t run_capacity, const void* w
  *   fixed strides of over_allocate), skipping rays whose count is 0, then stores the actual counts.
  *   Flag / value arrays must be zero-filled by the caller, as data_spec.hpp:62-84 does.
  *   rays_mask (bool bytes) may be NULL; the crossings t_sorted / t_indices / hits are required. */
+/* `slots` (nullable; needs fill != 0 and traverse_steps_limit > 0): over-allocation in one pass (grid.cu:364-404).
+ * slots[r] = number of unmasked rays before ray r; ray r writes its edges at slots[r] * 2 * limit and its samples at
+ * slots[r] * limit, `iv_starts` / `sm_starts` are not read, and iv_cnts / sm_cnts receive the counts of every ray
+ * (0 for masked rays). */
 int32_t nfa_traverse_generic(int32_t n_rays, const float* rays_o, const float* rays_d, const uint8_t* rays_mask,
                              const float* near_planes, const float* far_planes,
                              int32_t n_grids, int32_t rx, int32_t ry, int32_t rz,
                              const uint64_t* words, const uint32_t* coarse, const float* aabbs,
                              const float* t_sorted, const int64_t* t_indices, const uint8_t* hits,
                              float step_size, float cone_angle, int32_t traverse_steps_limit, int32_t fill,
+                             const int64_t* slots,
                              const int64_t* iv_starts, int64_t* iv_cnts, float* iv_vals, int64_t* iv_ray_indices,
                              uint8_t* iv_is_left, uint8_t* iv_is_right,
                              const int64_t* sm_starts, int64_t* sm_cnts, float* sm_vals, int64_t* sm_ray_indices,

@@ -41,7 +41,8 @@ SIGNATURES = {
     "nfa_expand_intervals": (_c_i32, [_c_i32, _c_i64, _c_ptr, _c_ptr, _c_f32, _c_i64, _c_i64] + [_c_ptr] * 10),
     "nfa_traverse_generic": (_c_i32, [_c_i32, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32, _c_i32,
                                       _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_f32, _c_f32, _c_i32, _c_i32]
-                             + [_c_ptr] * 13),
+                             + [_c_ptr] * 14),
+    "nfa_counts_to_packed_info": (_c_i32, [_c_i32, _c_ptr, _c_ptr, _c_ptr, _c_ptr]),
     "nfa_composite_fwd": (_c_i32, [_c_i32, _c_i64, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_ptr, _c_ptr, _c_ptr,
                                    _c_i32] + [_c_ptr] * 8),
     "nfa_composite_bwd": (_c_i32, [_c_i32, _c_i64, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_ptr, _c_ptr, _c_ptr,
@@ -70,7 +71,7 @@ SIGNATURES = {
     "nfa_pack_info": (_c_i32, [_c_i64, _c_ptr, _c_i32, _c_ptr, _c_ptr, _c_ptr]),
 }
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 _lib = None
 launches = 0  # number of native kernel-launching calls made through this module (bench.py reports it)

@@ -184,6 +184,108 @@ __global__ void __launch_bounds__(kIsWarps * 32) importance_sampling_warp_kernel
     }
 }
 
+// ---------------------------------------------------------------------------
+// Batched input AND output (the proposal-network shapes, BASELINE config 4: [n_rays, 65] -> 32 samples): the hot
+// flavour.  Same arithmetic as resample_ray (pdf.cuh), but
+//   * a warp takes `chunk` consecutive rays and keeps TWO staging buffers: the CDF / edge rows of ray i+1 are copied
+//     global -> shared with cp.async (LDGSTS, no register round trip, no scoreboard wait) while ray i is resampled;
+//   * every per-ray quantity that the generic kernel derives from the packed / batched switch is a pointer that
+//     advances by a constant.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async_f32(float* dst_smem, const float* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
+}
+
+template <bool kStratified, bool kMapT>
+__global__ void __launch_bounds__(kIsWarps * 32) importance_sampling_batched_kernel(IsParams p, int32_t n_in, int32_t n,
+                                                                                   int32_t chunk)
+{
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // per warp: stage[2][2 * n_in] (cdf row, then edge-position row) and the n sample centres
+    float* const base = smem + (size_t)warp * (4 * n_in + n);
+    float* const ts = base + 4 * n_in;
+    const float quiet_nan = __int_as_float(0x7fc00000);
+
+    auto stage_ray = [&](int64_t ray, int buf) {  // asynchronous: completes at the next wait
+        const float* c = p.cdfs + ray * n_in;
+        const float* v = p.vals + ray * n_in;
+        float* d = base + buf * 2 * n_in;
+        for (int i = lane; i < n_in; i += 32) {
+            cp_async_f32(d + i, c + i);
+            cp_async_f32(d + n_in + i, v + i);
+        }
+        cp_async_commit();
+    };
+
+    for (int64_t ray0 = ((int64_t)blockIdx.x * kIsWarps + warp) * chunk; ray0 < p.n_rays;
+         ray0 += (int64_t)gridDim.x * kIsWarps * chunk) {
+        const int cnt = (int)min((int64_t)chunk, p.n_rays - ray0);
+        float jitter = 0.5f;
+        if (kStratified && lane < cnt) jitter = philox_uniform(p.seed, (uint64_t)(ray0 + lane), p.offset);
+        stage_ray(ray0, 0);
+        float* out_s = p.sample_vals + ray0 * n;
+        float* out_e = p.iv_vals + ray0 * (n + 1);
+        float* out_a = kMapT ? p.t_starts + ray0 * n : nullptr;
+        float* out_b = kMapT ? p.t_ends + ray0 * n : nullptr;
+        for (int i = 0; i < cnt; ++i) {
+            const int buf = i & 1;
+            if (i + 1 < cnt) {
+                stage_ray(ray0 + i + 1, buf ^ 1);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncwarp();
+            const float* cdf = base + buf * 2 * n_in;
+            const float* val = cdf + n_in;
+            const float bias = kStratified ? __shfl_sync(0xffffffffu, jitter, i) : 0.5f;
+            const float t_min = val[0], t_max = val[n_in - 1];
+            const float u_floor = cdf[0], u_ceil = cdf[n_in - 1];
+            const float u_step = f_div(f_sub(u_ceil, u_floor), (float)n);
+            for (int sid = lane; sid < n; sid += 32) {
+                const float t = is_invert<int32_t>(cdf, val, 0, n_in - 1, is_u<int32_t>(u_floor, u_step, sid, bias));
+                ts[sid] = t;
+                out_s[sid] = t;
+                if (p.sample_ray) p.sample_ray[(ray0 + i) * n + sid] = ray0 + i;
+            }
+            __syncwarp();
+            for (int k = lane; k < n; k += 32) {
+                const float e = is_edge<int32_t>(ts, n, k, t_min, t_max);
+                out_e[k] = e;
+                const bool closes = k == n - 1;
+                float e_close = 0.f;
+                if (closes) {
+                    e_close = is_edge<int32_t>(ts, n, n, t_min, t_max);
+                    out_e[n] = e_close;
+                }
+                if (kMapT) {
+                    const float t = stot(e, p.s_min, p.s_max, p.lindisp != 0);
+                    out_a[k] = t;
+                    if (k > 0) out_b[k - 1] = t;
+                    if (closes) out_b[k] = stot(e_close, p.s_min, p.s_max, p.lindisp != 0);
+                }
+            }
+            __syncwarp();  // `ts` and this stage are free again
+            out_s += n;
+            out_e += n + 1;
+            if (kMapT) {
+                out_a += n;
+                out_b += n;
+            }
+        }
+    }
+    (void)quiet_nan;
+}
+
 struct SearchParams {
     int64_t n_query;
     const float* q_vals;
@@ -276,6 +378,21 @@ int32_t nfa_importance_sampling(int32_t n_rays, const float* vals, const float* 
     const int64_t out_cap = out_packed_info ? max_out : n_out;
     const int64_t floats = 2 * in_cap + out_cap;
     cudaStream_t s = (cudaStream_t)stream;
+    if (!in_packed_info && !out_packed_info && in_edges >= 2 && n_out >= 1 && 4 * in_edges + n_out <= kWarpRayFloats) {
+        // batched rows in, batched rows out (proposal-network shapes): double-buffered warp-per-ray kernel.  A warp
+        // walks `chunk` consecutive rays (the next ray's rows are in flight while this one is resampled)
+        const int64_t fl = 4 * in_edges + n_out;
+        const size_t bytes = (size_t)fl * kIsWarps * sizeof(float);
+        int64_t chunk = (int64_t)n_rays / (148 * 8 * kIsWarps);
+        chunk = chunk < 1 ? 1 : (chunk > 32 ? 32 : chunk);
+        const int64_t want = ((int64_t)n_rays + chunk * kIsWarps - 1) / (chunk * kIsWarps);
+        const unsigned grid = (unsigned)(want < (1 << 20) ? want : (1 << 20));
+#define NFA_IS_BATCHED(S, M) importance_sampling_batched_kernel<S, M><<<grid, kIsWarps * 32, bytes, s>>>(p, (int32_t)in_edges, (int32_t)n_out, (int32_t)chunk)
+        if (stratified) { if (t_starts) NFA_IS_BATCHED(true, true); else NFA_IS_BATCHED(true, false); }
+        else { if (t_starts) NFA_IS_BATCHED(false, true); else NFA_IS_BATCHED(false, false); }
+#undef NFA_IS_BATCHED
+        return (int32_t)cudaGetLastError();
+    }
     if (floats <= kWarpRayFloats) {
         // short rays: a warp each; persistent CTAs sized to fill the machine
         const size_t bytes = (size_t)floats * kIsWarps * sizeof(float);

@@ -10,8 +10,8 @@
 // Packed flavour: one warp per ray, shuffle scan per 32-element tile with a
 // running carry; no shared memory and no block barriers (the reference's
 // Blelloch-in-smem kernel syncs under divergent control flow).
-// Key flavour: tile-local segmented scan + tiny carry pass + fix-up of each
-// tile's leading open segment (one pass over the data plus a few elements).
+// Key flavour: single pass, tile-local segmented scan + decoupled look-back for
+// the value carried into each tile (one tile deep in practice).
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -72,18 +72,24 @@ __global__ void __launch_bounds__(kScanWarps * 32) scan_packed_kernel(int32_t n_
 }
 
 // ---------------------------------------------------------------------------
-// key (ray index) flavour: a segment is a maximal run of equal consecutive keys
+// key (ray index) flavour: a segment is a maximal run of equal consecutive keys.
+// ONE pass over the data (the reference: cub::DeviceScan::*ByKey, scan_cub.cu:18-56): every CTA scans a tile of
+// 2048 elements and gets the value carried into it by decoupled look-back.  Tiles are claimed through an atomic
+// ticket (so a tile's predecessors are always running or done), publish the aggregate of their trailing open
+// segment as one 64-bit word (value | has-a-head | status), and look back only until a tile that contains a
+// segment head -- with ~130 samples per ray that is the tile right before, so nothing ever waits on a chain.
 // ---------------------------------------------------------------------------
 constexpr int kKeyThreads = 256;
-constexpr int kKeyItems = 8;
+#ifndef NFA_KEY_ITEMS
+#define NFA_KEY_ITEMS 8
+#endif
+constexpr int kKeyItems = NFA_KEY_ITEMS;  // 4 or 8 consecutive elements per thread
 constexpr int kKeyTile = kKeyThreads * kKeyItems;
 
-struct KeyTileState {
-    float agg;        // scan value of the tile's trailing open segment
-    int32_t has_head; // tile contains a segment head
-    int32_t lead;     // number of leading elements that belong to the previous tile's segment
-    int32_t pad;
-};
+// tile descriptor: bits 0-31 value, bit 32 "the tile contains a segment head", bits 62-63 status
+constexpr unsigned long long kStAggregate = 1ull << 62;  // value = this tile alone (no head in it): keep looking back
+constexpr unsigned long long kStPrefix = 2ull << 62;     // value = everything a successor needs: stop here
+constexpr unsigned long long kStMask = 3ull << 62;
 
 template <bool kProd>
 struct SegPair {
@@ -99,52 +105,78 @@ __device__ __forceinline__ SegPair<kProd> seg_combine(SegPair<kProd> a, SegPair<
     return r;
 }
 
-// pass 1: tile-local segmented scan (logical order; physical index = n-1-j when reversed)
-template <bool kProd, bool kInclusive, bool kReverse>
-__global__ void __launch_bounds__(kKeyThreads) scan_bykey_tile_kernel(int64_t n, const int64_t* __restrict__ keys,
-                                                                      const float* __restrict__ in,
-                                                                      float* __restrict__ out,
-                                                                      KeyTileState* __restrict__ tiles)
+__device__ __forceinline__ unsigned long long tile_word(float v, int has_head, unsigned long long status)
+{
+    return (unsigned long long)__float_as_uint(v) | ((unsigned long long)(has_head ? 1 : 0) << 32) | status;
+}
+
+// workspace: [0,8) ticket counter, [16, 16 + 8 n_tiles) tile descriptors; zeroed by the launcher
+template <bool kProd, bool kInclusive, bool kReverse, bool kVec>
+__global__ void __launch_bounds__(kKeyThreads) scan_bykey_kernel(int64_t n, const int64_t* __restrict__ keys,
+                                                                 const float* __restrict__ in, float* __restrict__ out,
+                                                                 unsigned int* __restrict__ ticket,
+                                                                 unsigned long long* __restrict__ desc)
 {
     __shared__ float s_v[kKeyThreads / 32];
     __shared__ int s_f[kKeyThreads / 32];
+    __shared__ long long s_last_key[kKeyThreads / 32];
     __shared__ int s_first_head;
+    __shared__ unsigned int s_tile;
+    __shared__ float s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t tile0 = (int64_t)blockIdx.x * kKeyTile;
-    const int64_t j0 = tile0 + (int64_t)tid * kKeyItems;
-    if (tid == 0) s_first_head = kKeyTile;
-    __syncthreads();
-
-    float x[kKeyItems];
-    int head[kKeyItems];
-    int64_t prev_key = 0;
-    bool have_prev = false;
-    if (j0 > 0 && j0 - 1 < n) {
-        prev_key = keys[kReverse ? n - 1 - (j0 - 1) : (j0 - 1)];
-        have_prev = true;
+    if (tid == 0) {
+        s_tile = atomicAdd(ticket, 1u);
+        s_first_head = kKeyTile;
     }
+    __syncthreads();
+    const unsigned int tile = s_tile;
+    const int64_t tile0 = (int64_t)tile * kKeyTile;
+    const int64_t j0 = tile0 + (int64_t)tid * kKeyItems;  // logical index of this thread's first element
+
+    // ---- load 8 consecutive (logical) elements per thread
+    float x[kKeyItems];
+    long long key[kKeyItems];
+    if (kVec && j0 + kKeyItems <= n) {  // forward, 16-byte aligned arrays: two float4 + four longlong2 per thread
+#pragma unroll
+        for (int q = 0; q < kKeyItems / 4; ++q) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(in + j0) + q);
+            x[4 * q] = a.x; x[4 * q + 1] = a.y; x[4 * q + 2] = a.z; x[4 * q + 3] = a.w;
+        }
+#pragma unroll
+        for (int q = 0; q < kKeyItems / 2; ++q) {
+            const longlong2 kk = __ldg(reinterpret_cast<const longlong2*>(keys + j0) + q);
+            key[2 * q] = kk.x;
+            key[2 * q + 1] = kk.y;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < kKeyItems; ++e) {
+            const int64_t j = j0 + e;
+            const int64_t k = kReverse ? n - 1 - j : j;
+            x[e] = j < n ? __ldg(in + k) : op_identity<kProd>();
+            key[e] = j < n ? __ldg(keys + k) : (long long)0x7fffffffffffffffll;
+        }
+    }
+    // key of the element before this thread's first one: previous lane, previous warp (shared), previous tile (global)
+    long long prev = __shfl_up_sync(kFullMask, key[kKeyItems - 1], 1);
+    if (lane == 31) s_last_key[warp] = key[kKeyItems - 1];
+    __syncthreads();
+    if (lane == 0) {
+        if (warp > 0) prev = s_last_key[warp - 1];
+        else if (tile0 > 0) prev = __ldg(keys + (kReverse ? n - 1 - (tile0 - 1) : tile0 - 1));
+    }
+    // ---- thread-local segmented inclusive scan
+    int head[kKeyItems];
+    float res[kKeyItems];
     SegPair<kProd> acc;
     acc.v = op_identity<kProd>();
     acc.f = 0;
-    float res[kKeyItems];
     int first_head_local = kKeyTile;
 #pragma unroll
     for (int e = 0; e < kKeyItems; ++e) {
         const int64_t j = j0 + e;
-        if (j < n) {
-            const int64_t k = kReverse ? n - 1 - j : j;
-            const int64_t key = keys[k];
-            x[e] = in[k];
-            head[e] = (!have_prev || key != prev_key) ? 1 : 0;
-            if (j == 0) head[e] = 1;
-            prev_key = key;
-            have_prev = true;
-        } else {
-            x[e] = op_identity<kProd>();
-            head[e] = 0;
-        }
+        head[e] = (j < n && (j == 0 || key[e] != (e ? key[e - 1] : prev))) ? 1 : 0;
         if (head[e] && first_head_local == kKeyTile) first_head_local = tid * kKeyItems + e;
-        // thread-local segmented inclusive scan
         if (head[e]) {
             acc.v = x[e];
             acc.f = 1;
@@ -153,7 +185,7 @@ __global__ void __launch_bounds__(kKeyThreads) scan_bykey_tile_kernel(int64_t n,
         }
         res[e] = acc.v;
     }
-    // block-level segmented inclusive scan of the per-thread aggregates
+    // ---- block-level segmented scan of the per-thread aggregates
     SegPair<kProd> incl = acc;
 #pragma unroll
     for (int s = 1; s < 32; s <<= 1) {
@@ -168,8 +200,7 @@ __global__ void __launch_bounds__(kKeyThreads) scan_bykey_tile_kernel(int64_t n,
     }
     if (first_head_local != kKeyTile) atomicMin(&s_first_head, first_head_local);
     __syncthreads();
-    // exclusive prefix (over threads) = combine of previous warps, then previous lanes
-    SegPair<kProd> pre;
+    SegPair<kProd> pre;  // exclusive prefix over the threads of the tile
     pre.v = op_identity<kProd>();
     pre.f = 0;
     for (int w = 0; w < warp; ++w) {
@@ -184,111 +215,58 @@ __global__ void __launch_bounds__(kKeyThreads) scan_bykey_tile_kernel(int64_t n,
         y.f = __shfl_up_sync(kFullMask, incl.f, 1);
         if (lane > 0) pre = seg_combine<kProd>(pre, y);
     }
-    // write results: elements before the thread's first head continue `pre`
-    bool open = true;  // still in the segment carried in from the previous thread
-    float run_prev = pre.v;  // inclusive value just before the current element within its segment
-#pragma unroll
-    for (int e = 0; e < kKeyItems; ++e) {
-        const int64_t j = j0 + e;
-        if (j >= n) break;
-        const int64_t k = kReverse ? n - 1 - j : j;
-        if (head[e]) open = false;
-        float incl_v;
-        if (open) incl_v = op_apply<kProd>(pre.v, res[e]);
-        else incl_v = res[e];
-        float outv;
-        if (kInclusive) outv = incl_v;
-        else outv = head[e] ? op_identity<kProd>() : run_prev;
-        out[k] = outv;
-        run_prev = incl_v;
-    }
-    // tile state: aggregate of the trailing open segment
+    // ---- publish this tile, look back for the value carried in (one thread; the chain is one tile deep in practice)
     if (tid == kKeyThreads - 1) {
         const SegPair<kProd> tot = seg_combine<kProd>(pre, acc);
-        KeyTileState st;
-        st.agg = tot.v;
-        st.has_head = tot.f;
-        st.lead = 0;
-        st.pad = 0;
-        tiles[blockIdx.x].agg = st.agg;
-        tiles[blockIdx.x].has_head = st.has_head;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        const int64_t remaining = n - tile0;
-        const int in_tile = remaining < kKeyTile ? (int)remaining : kKeyTile;
-        tiles[blockIdx.x].lead = s_first_head < in_tile ? s_first_head : in_tile;
-    }
-}
-
-// pass 2: carry into each tile (single CTA, serial over tiles in chunks; n_tiles = N/2048)
-template <bool kProd>
-__global__ void __launch_bounds__(1024) scan_bykey_carry_kernel(int32_t n_tiles, const KeyTileState* __restrict__ tiles,
-                                                                float* __restrict__ carry)
-{
-    __shared__ float s_v[32];
-    __shared__ int s_f[32];
-    __shared__ float s_run_v;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_run_v = op_identity<kProd>();
-    __syncthreads();
-    for (int base = 0; base < n_tiles; base += 1024) {
-        const int t = base + tid;
-        SegPair<kProd> me;
-        me.v = op_identity<kProd>();
-        me.f = 0;
-        if (t < n_tiles) {
-            me.v = tiles[t].agg;
-            me.f = tiles[t].has_head;
+        float carry = op_identity<kProd>();
+        volatile unsigned long long* d = desc;
+        if (tile == 0 || tot.f) {
+            d[tile] = tile_word(tot.v, tot.f, kStPrefix);  // a head inside (or nothing before): complete for successors
+        } else {
+            d[tile] = tile_word(tot.v, 0, kStAggregate);
         }
-        SegPair<kProd> incl = me;
+        if (tile > 0) {
+            for (long long t = (long long)tile - 1; t >= 0; --t) {
+                unsigned long long w;
+                do {
+                    w = d[t];
+                } while ((w & kStMask) == 0ull);
+                carry = op_apply<kProd>(__uint_as_float((unsigned int)w), carry);
+                if ((w & kStMask) == kStPrefix) break;
+            }
+            if (!tot.f) {
+                __threadfence();
+                d[tile] = tile_word(op_apply<kProd>(carry, tot.v), 0, kStPrefix);
+            }
+        }
+        s_carry = carry;
+    }
+    __syncthreads();
+    const float carry = s_carry;
+    const int lead = s_first_head;  // elements of the tile before its first head continue the previous tile's segment
+    // ---- results: elements before the thread's first head continue `pre`; those before the tile's first head also `carry`
+    float o[kKeyItems];
+    bool open = true;
+    // inclusive value of the element just before this thread's first one (pre.v is the identity for thread 0)
+    float run_prev = pre.f ? pre.v : op_apply<kProd>(carry, pre.v);
 #pragma unroll
-        for (int s = 1; s < 32; s <<= 1) {
-            SegPair<kProd> y;
-            y.v = __shfl_up_sync(kFullMask, incl.v, s);
-            y.f = __shfl_up_sync(kFullMask, incl.f, s);
-            if (lane >= s) incl = seg_combine<kProd>(y, incl);
-        }
-        if (lane == 31) {
-            s_v[warp] = incl.v;
-            s_f[warp] = incl.f;
-        }
-        __syncthreads();
-        SegPair<kProd> pre;
-        pre.v = s_run_v;
-        pre.f = 0;
-        for (int w = 0; w < warp; ++w) {
-            SegPair<kProd> y;
-            y.v = s_v[w];
-            y.f = s_f[w];
-            pre = seg_combine<kProd>(pre, y);
-        }
-        SegPair<kProd> y;
-        y.v = __shfl_up_sync(kFullMask, incl.v, 1);
-        y.f = __shfl_up_sync(kFullMask, incl.f, 1);
-        if (lane > 0) pre = seg_combine<kProd>(pre, y);
-        if (t < n_tiles) carry[t] = pre.v;  // value carried INTO tile t
-        __syncthreads();
-        if (tid == 1023) s_run_v = seg_combine<kProd>(pre, me).v;
-        __syncthreads();
+    for (int e = 0; e < kKeyItems; ++e) {
+        if (head[e]) open = false;
+        float incl_v = open ? op_apply<kProd>(pre.v, res[e]) : res[e];
+        if (tid * kKeyItems + e < lead) incl_v = op_apply<kProd>(carry, incl_v);
+        o[e] = kInclusive ? incl_v : (head[e] ? op_identity<kProd>() : run_prev);
+        run_prev = incl_v;
     }
-}
-
-// pass 3: fold the carry into each tile's leading open segment
-template <bool kProd, bool kReverse>
-__global__ void __launch_bounds__(kKeyThreads) scan_bykey_fix_kernel(int64_t n, const KeyTileState* __restrict__ tiles,
-                                                                     const float* __restrict__ carry,
-                                                                     float* __restrict__ out)
-{
-    const int t = blockIdx.x;
-    if (t == 0) return;
-    const int lead = tiles[t].lead;
-    const float c = carry[t];
-    const int64_t tile0 = (int64_t)t * kKeyTile;
-    for (int e = threadIdx.x; e < lead; e += kKeyThreads) {
-        const int64_t j = tile0 + e;
-        const int64_t k = kReverse ? n - 1 - j : j;
-        out[k] = op_apply<kProd>(c, out[k]);
+    if (kVec && j0 + kKeyItems <= n) {
+#pragma unroll
+        for (int q = 0; q < kKeyItems / 4; ++q)
+            reinterpret_cast<float4*>(out + j0)[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+    } else {
+#pragma unroll
+        for (int e = 0; e < kKeyItems; ++e) {
+            const int64_t j = j0 + e;
+            if (j < n) out[kReverse ? n - 1 - j : j] = o[e];
+        }
     }
 }
 
@@ -522,13 +500,12 @@ template <bool kProd, bool kInclusive, bool kReverse>
 static void launch_bykey(int64_t n, const int64_t* keys, const float* in, float* out, void* workspace, cudaStream_t s)
 {
     const int n_tiles = (int)((n + kKeyTile - 1) / kKeyTile);
-    KeyTileState* tiles = (KeyTileState*)workspace;
-    float* carry = (float*)((char*)workspace + (((int64_t)n_tiles * (int64_t)sizeof(KeyTileState) + 15) & ~(int64_t)15));
-    scan_bykey_tile_kernel<kProd, kInclusive, kReverse><<<n_tiles, kKeyThreads, 0, s>>>(n, keys, in, out, tiles);
-    if (n_tiles > 1) {
-        scan_bykey_carry_kernel<kProd><<<1, 1024, 0, s>>>(n_tiles, tiles, carry);
-        scan_bykey_fix_kernel<kProd, kReverse><<<n_tiles, kKeyThreads, 0, s>>>(n, tiles, carry, out);
-    }
+    unsigned int* ticket = (unsigned int*)workspace;
+    unsigned long long* desc = (unsigned long long*)((char*)workspace + 16);
+    cudaMemsetAsync(workspace, 0, 16 + (size_t)n_tiles * 8, s);
+    const bool vec = !kReverse && ((((uintptr_t)keys) | ((uintptr_t)in) | ((uintptr_t)out)) & 15u) == 0;
+    if (vec) scan_bykey_kernel<kProd, kInclusive, kReverse, true><<<n_tiles, kKeyThreads, 0, s>>>(n, keys, in, out, ticket, desc);
+    else scan_bykey_kernel<kProd, kInclusive, kReverse, false><<<n_tiles, kKeyThreads, 0, s>>>(n, keys, in, out, ticket, desc);
 }
 
 extern "C" {
@@ -556,7 +533,7 @@ int64_t nfa_scan_by_key_workspace_bytes(int64_t n)
 {
     if (n <= 0) return 16;
     const int64_t n_tiles = (n + kKeyTile - 1) / kKeyTile;
-    return ((n_tiles * (int64_t)sizeof(KeyTileState) + 15) & ~(int64_t)15) + ((n_tiles * 4 + 15) & ~(int64_t)15);
+    return 16 + ((n_tiles * 8 + 15) & ~(int64_t)15);
 }
 
 int32_t nfa_scan_by_key(int64_t n, const int64_t* keys, const float* in, float* out, int32_t op_prod,
@@ -584,6 +561,22 @@ int64_t nfa_pack_info_workspace_bytes(int32_t n_rays)
     if (n_rays <= 0) return 16;
     const int64_t tiles = (n_rays + kPackTile - 1) / kPackTile;
     return (int64_t)n_rays * 8 + tiles * 8 + 16;
+}
+
+int32_t nfa_counts_to_packed_info(int32_t n_rays, const int64_t* counts, int64_t* packed_info, void* workspace,
+                                  nfa_stream_t stream)
+{
+    if (n_rays < 0) return NFA_ERR_ARG;
+    if (n_rays == 0) return NFA_OK;
+    if (!counts || !packed_info || !workspace) return NFA_ERR_ARG;
+    if ((((uintptr_t)packed_info) & 15u) != 0) return NFA_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int tiles = (n_rays + kPackTile - 1) / kPackTile;
+    unsigned long long* tile_sums = (unsigned long long*)workspace;
+    const unsigned long long* c = reinterpret_cast<const unsigned long long*>(counts);
+    pack_tilesum_kernel<<<tiles, kPackTile, 0, s>>>(n_rays, c, tile_sums);
+    pack_scan_kernel<<<tiles, kPackTile, 0, s>>>(n_rays, c, tile_sums, packed_info, nullptr, nullptr);
+    return launch_status_s();
 }
 
 int32_t nfa_pack_info(int64_t n, const int64_t* ray_indices, int32_t n_rays, int64_t* packed_info, void* workspace,

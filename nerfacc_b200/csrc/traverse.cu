@@ -787,6 +787,7 @@ struct GenericParams {
     float step_size, cone_angle;
     int32_t limit;
     int32_t fill;
+    const int64_t* slots;  // over-allocation: index of the ray among the unmasked ones (its fixed-stride slot), or null
     const int64_t* iv_starts;
     int64_t* iv_cnts;
     float* iv_vals;
@@ -805,8 +806,11 @@ __global__ void __launch_bounds__(128) generic_traverse_kernel(const GenericPara
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= p.n_rays) return;
-    if (p.rays_mask && !p.rays_mask[r]) return;                       // reference grid.cu:100
-    if (p.fill && (p.iv_cnts[r] == 0 || p.sm_cnts[r] == 0)) return;  // grid.cu:103-106
+    if (p.rays_mask && !p.rays_mask[r]) {  // reference grid.cu:100
+        if (p.slots) p.iv_cnts[r] = p.sm_cnts[r] = 0;
+        return;
+    }
+    if (p.fill && !p.slots && (p.iv_cnts[r] == 0 || p.sm_cnts[r] == 0)) return;  // grid.cu:103-106
     OccView occ;
     occ.words = p.words;
     occ.coarse = p.coarse;
@@ -817,8 +821,9 @@ __global__ void __launch_bounds__(128) generic_traverse_kernel(const GenericPara
     out.ray = r;
     out.want_iv = true;
     out.want_sm = true;
-    out.iv_base = p.fill ? p.iv_starts[r] : 0;
-    out.sm_base = p.fill ? p.sm_starts[r] : 0;
+    // fixed-stride slots (over_allocate, grid.cu:364-404): 2 * limit edges and limit samples per unmasked ray
+    out.iv_base = p.slots ? p.slots[r] * 2 * p.limit : (p.fill ? p.iv_starts[r] : 0);
+    out.sm_base = p.slots ? p.slots[r] * p.limit : (p.fill ? p.sm_starts[r] : 0);
     out.iv_vals = p.iv_vals; out.iv_ray = p.iv_ray; out.iv_left = p.iv_left; out.iv_right = p.iv_right;
     out.sm_vals = p.sm_vals; out.sm_ray = p.sm_ray; out.sm_valid = p.sm_valid;
     out.n_edges = 0;
@@ -1135,8 +1140,8 @@ int32_t nfa_traverse_generic(int32_t n_rays, const float* rays_o, const float* r
                              const float* near_planes, const float* far_planes, int32_t n_grids, int32_t rx, int32_t ry,
                              int32_t rz, const uint64_t* words, const uint32_t* coarse, const float* aabbs,
                              const float* t_sorted, const int64_t* t_indices, const uint8_t* hits, float step_size,
-                             float cone_angle, int32_t traverse_steps_limit, int32_t fill, const int64_t* iv_starts,
-                             int64_t* iv_cnts, float* iv_vals, int64_t* iv_ray_indices, uint8_t* iv_is_left,
+                             float cone_angle, int32_t traverse_steps_limit, int32_t fill, const int64_t* slots,
+                             const int64_t* iv_starts, int64_t* iv_cnts, float* iv_vals, int64_t* iv_ray_indices, uint8_t* iv_is_left,
                              uint8_t* iv_is_right, const int64_t* sm_starts, int64_t* sm_cnts, float* sm_vals,
                              int64_t* sm_ray_indices, uint8_t* sm_is_valid, float* terminate_planes, nfa_stream_t stream)
 {
@@ -1145,7 +1150,8 @@ int32_t nfa_traverse_generic(int32_t n_rays, const float* rays_o, const float* r
     if (!rays_o || !rays_d || !near_planes || !far_planes || !words || !coarse || !aabbs || !t_sorted || !t_indices ||
         !hits || !iv_cnts || !sm_cnts)
         return NFA_ERR_ARG;
-    if (fill && (!iv_starts || !sm_starts)) return NFA_ERR_ARG;
+    if (fill && !slots && (!iv_starts || !sm_starts)) return NFA_ERR_ARG;
+    if (slots && !(fill && traverse_steps_limit > 0)) return NFA_ERR_ARG;
     GenericParams p;
     p.n_rays = n_rays;
     p.rays_o = rays_o;
@@ -1164,6 +1170,7 @@ int32_t nfa_traverse_generic(int32_t n_rays, const float* rays_o, const float* r
     p.cone_angle = cone_angle;
     p.limit = traverse_steps_limit;
     p.fill = fill;
+    p.slots = slots;
     p.iv_starts = iv_starts; p.iv_cnts = iv_cnts; p.iv_vals = iv_vals; p.iv_ray = iv_ray_indices;
     p.iv_left = iv_is_left; p.iv_right = iv_is_right;
     p.sm_starts = sm_starts; p.sm_cnts = sm_cnts; p.sm_vals = sm_vals; p.sm_ray = sm_ray_indices;

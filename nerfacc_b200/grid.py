@@ -380,23 +380,21 @@ def _traverse_generic(rays_o, rays_d, binaries, aabbs, near_planes, far_planes, 
             mask = mask != 0
     term = torch.empty(n_rays, dtype=torch.float32, device=device)
 
-    def run(fill, use_mask, iv_s, iv_c, sm_s, sm_c, arrays):
+    def run(fill, use_mask, iv_s, iv_c, sm_s, sm_c, arrays, slots=None):
         if n_rays == 0:
             return
         _lib.call("nfa_traverse_generic", device, n_rays, _lib.ptr(rays_o), _lib.ptr(rays_d),
                   _lib.ptr(mask) if use_mask else None, _lib.ptr(near_planes), _lib.ptr(far_planes), n_grids, rx, ry, rz,
                   _lib.ptr(occ.words), _lib.ptr(occ.coarse), _lib.ptr(aabbs), _lib.ptr(t_sorted), _lib.ptr(t_indices),
-                  _lib.ptr(hits), step_size, cone_angle, limit, int(fill), _lib.ptr(iv_s), _lib.ptr(iv_c),
+                  _lib.ptr(hits), step_size, cone_angle, limit, int(fill), _lib.ptr(slots), _lib.ptr(iv_s), _lib.ptr(iv_c),
                   *[_lib.ptr(a) for a in arrays[:4]], _lib.ptr(sm_s), _lib.ptr(sm_c),
                   *[_lib.ptr(a) for a in arrays[4:]], _lib.ptr(term) if fill else None)
 
     if over_allocate:
-        m = torch.ones(n_rays, dtype=torch.int64, device=device) if mask is None else mask.to(torch.int64)
-        iv_cnts, sm_cnts = 2 * limit * m, limit * m
-    else:
-        iv_cnts = torch.zeros(n_rays, dtype=torch.int64, device=device)
-        sm_cnts = torch.zeros(n_rays, dtype=torch.int64, device=device)
-        run(False, False, None, iv_cnts, None, sm_cnts, [None] * 7)
+        return _traverse_bounded(run, device, n_rays, limit, mask, term)
+    iv_cnts = torch.zeros(n_rays, dtype=torch.int64, device=device)
+    sm_cnts = torch.zeros(n_rays, dtype=torch.int64, device=device)
+    run(False, False, None, iv_cnts, None, sm_cnts, [None] * 7)
     iv_starts = torch.cumsum(iv_cnts, 0) - iv_cnts
     sm_starts = torch.cumsum(sm_cnts, 0) - sm_cnts
     n_edges = int(iv_cnts.sum().item()) if n_rays else 0
@@ -408,15 +406,51 @@ def _traverse_generic(rays_o, rays_d, binaries, aabbs, near_planes, far_planes, 
     sm_vals = torch.zeros(n_samples, dtype=torch.float32, device=device)
     sm_ray = torch.zeros(n_samples, dtype=torch.int64, device=device)
     sm_valid = torch.zeros(n_samples, dtype=torch.bool, device=device)
-    run(True, over_allocate, iv_starts, iv_cnts, sm_starts, sm_cnts,
+    run(True, False, iv_starts, iv_cnts, sm_starts, sm_cnts,
         [iv_vals, iv_ray, iv_left, iv_right, sm_vals, sm_ray, sm_valid])
-    if over_allocate:  # reference grid.cu:402-404: starts recomputed from the actual counts
-        iv_starts = torch.cumsum(iv_cnts, 0) - iv_cnts
-        sm_starts = torch.cumsum(sm_cnts, 0) - sm_cnts
     intervals = RayIntervals(vals=iv_vals, packed_info=torch.stack([iv_starts, iv_cnts], -1), ray_indices=iv_ray,
                              is_left=iv_left, is_right=iv_right)
     samples = RaySamples(vals=sm_vals, packed_info=torch.stack([sm_starts, sm_cnts], -1), ray_indices=sm_ray,
                          is_valid=sm_valid)
+    return intervals, samples, term
+
+
+def _traverse_bounded(run, device, n_rays: int, limit: int, mask: Optional[Tensor], term: Tensor):
+    """`traverse_steps_limit` + `over_allocate` (+ `rays_mask`): one pass into fixed-stride slots (reference
+    grid.cu:364-404) -- the call the test-mode rendering loop makes once per round (examples/utils.py:340-375), so
+    its cost is host work: one zero-filled arena carved into the seven output arrays (one memset instead of seven),
+    one synchronisation (the number of unmasked rays; none without a mask), the slot offsets computed in the
+    kernel from the rays' rank among the unmasked ones, packed_info of the actual counts by a native scan."""
+    lib = _lib.load()
+    if mask is None:
+        n_alive = n_rays
+        slots = torch.arange(n_rays, dtype=torch.int64, device=device)
+    else:
+        csum = torch.cumsum(mask, 0, dtype=torch.int64)
+        n_alive = int(csum[-1].item()) if n_rays else 0
+        slots = csum - mask.to(torch.int64)
+    n_edges, n_samples = 2 * limit * n_alive, limit * n_alive
+    # arena: int64 arrays first (8-byte aligned), then float32, then the three flag arrays
+    sizes = (8 * n_edges, 8 * n_samples, 4 * n_edges, 4 * n_samples, n_edges, n_edges, n_samples)
+    arena = torch.zeros(sum(sizes), dtype=torch.uint8, device=device)
+    parts, at = [], 0
+    for nbytes in sizes:
+        parts.append(arena[at:at + nbytes])
+        at += nbytes
+    iv_ray, sm_ray = parts[0].view(torch.int64), parts[1].view(torch.int64)
+    iv_vals, sm_vals = parts[2].view(torch.float32), parts[3].view(torch.float32)
+    iv_left, iv_right, sm_valid = parts[4].view(torch.bool), parts[5].view(torch.bool), parts[6].view(torch.bool)
+    cnts = torch.empty((2, n_rays), dtype=torch.int64, device=device)
+    run(True, mask is not None, None, cnts[0], None, cnts[1],
+        [iv_vals, iv_ray, iv_left, iv_right, sm_vals, sm_ray, sm_valid], slots=slots)
+    # reference grid.cu:402-404: starts recomputed from the actual counts
+    packed = torch.empty((2, n_rays, 2), dtype=torch.int64, device=device)
+    if n_rays:
+        ws = torch.empty(lib.nfa_pack_info_workspace_bytes(n_rays), dtype=torch.uint8, device=device)
+        for k in (0, 1):
+            _lib.call("nfa_counts_to_packed_info", device, n_rays, _lib.ptr(cnts[k]), _lib.ptr(packed[k]), _lib.ptr(ws))
+    intervals = RayIntervals(vals=iv_vals, packed_info=packed[0], ray_indices=iv_ray, is_left=iv_left, is_right=iv_right)
+    samples = RaySamples(vals=sm_vals, packed_info=packed[1], ray_indices=sm_ray, is_valid=sm_valid)
     return intervals, samples, term
 
 

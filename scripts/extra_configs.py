@@ -25,18 +25,26 @@ if impl == "reference-cuda":
     from nerfacc.data_specs import RayIntervals
     from nerfacc.estimators.prop_net import PropNetEstimator
     from nerfacc.pdf import importance_sampling
+    from nerfacc.volrend import accumulate_along_rays_
 else:
     sys.path.insert(0, ROOT)
     import nerfacc_b200 as nf
     from nerfacc_b200.data_specs import RayIntervals
     from nerfacc_b200.estimators.prop_net import PropNetEstimator
     from nerfacc_b200.pdf import importance_sampling
+    from nerfacc_b200.volrend import accumulate_along_rays_
 _spec = importlib.util.spec_from_file_location("scenes", os.path.join(ROOT, "nerfacc_b200", "scenes.py"))
 scenes = importlib.util.module_from_spec(_spec)
 _spec.loader.exec_module(scenes)
 
 dev = torch.device("cuda:0")
 lines = []
+ONLY = [x for x in os.environ.get("NFA_EXTRA_ONLY", "").split(",") if x]
+
+
+def want(tag):
+    return not ONLY or tag in ONLY
+
 
 
 def timed(fn, iters=20, warmup=3):
@@ -83,62 +91,64 @@ emit(config="2 + f1: sampling with sigma_fn visibility filter (early_stop_eps=1e
 del est2, ri2, rv2
 torch.cuda.empty_cache()
 
-# ---------------------------------------------------------------- config 3
-R3, G3 = 1 << 20, 256
-ro, rd = scenes.ball_rays(R3, seed=7)
-est = nf.OccGridEstimator(torch.from_numpy(scenes.ROI_AABB), resolution=G3).to(dev)
-est.binaries = torch.from_numpy(scenes.ball_grid(G3)).to(dev)
-tro, trd = torch.from_numpy(ro).to(dev), torch.from_numpy(rd).to(dev)
-step3 = 2.6e-3  # half of config 2's step on a grid twice as fine
-with torch.no_grad():
-    ri, ts, te = est.sampling(tro, trd, render_step_size=step3)
-    N3 = ri.numel()
-    sig = 5 * torch.rand(N3, device=dev)
-    rgb = torch.rand(N3, 3, device=dev)
+if want('c3'):
+    # ---------------------------------------------------------------- config 3
+    R3, G3 = 1 << 20, 256
+    ro, rd = scenes.ball_rays(R3, seed=7)
+    est = nf.OccGridEstimator(torch.from_numpy(scenes.ROI_AABB), resolution=G3).to(dev)
+    est.binaries = torch.from_numpy(scenes.ball_grid(G3)).to(dev)
+    tro, trd = torch.from_numpy(ro).to(dev), torch.from_numpy(rd).to(dev)
+    step3 = 2.6e-3  # half of config 2's step on a grid twice as fine
+    with torch.no_grad():
+        ri, ts, te = est.sampling(tro, trd, render_step_size=step3)
+        N3 = ri.numel()
+        sig = 5 * torch.rand(N3, device=dev)
+        rgb = torch.rand(N3, 3, device=dev)
 
-    def infer():
-        ri_, ts_, te_ = est.sampling(tro, trd, render_step_size=step3)
-        return nf.rendering(ts_, te_, ri_, n_rays=R3, rgb_sigma_fn=lambda a, b, c: (rgb, sig))
+        def infer():
+            ri_, ts_, te_ = est.sampling(tro, trd, render_step_size=step3)
+            return nf.rendering(ts_, te_, ri_, n_rays=R3, rgb_sigma_fn=lambda a, b, c: (rgb, sig))
 
-    def samp():
-        return est.sampling(tro, trd, render_step_size=step3)
+        def samp():
+            return est.sampling(tro, trd, render_step_size=step3)
 
-    def comp():
-        return nf.rendering(ts, te, ri, n_rays=R3, rgb_sigma_fn=lambda a, b, c: (rgb, sig))
+        def comp():
+            return nf.rendering(ts, te, ri, n_rays=R3, rgb_sigma_fn=lambda a, b, c: (rgb, sig))
 
-    t_all, t_s, t_c = timed(infer, 10), timed(samp, 10), timed(comp, 10)
-emit(config="3: 256^3 occ-grid, 1048576 rays, inference-only", n_samples=N3, samples_per_ray=N3 / R3,
-     step_ms=t_all * 1e3, sampling_ms=t_s * 1e3, compositing_ms=t_c * 1e3, gsamples_per_s=N3 / t_all / 1e9)
-del ri, ts, te, sig, rgb
-torch.cuda.empty_cache()
+        t_all, t_s, t_c = timed(infer, 10), timed(samp, 10), timed(comp, 10)
+    emit(config="3: 256^3 occ-grid, 1048576 rays, inference-only", n_samples=N3, samples_per_ray=N3 / R3,
+         step_ms=t_all * 1e3, sampling_ms=t_s * 1e3, compositing_ms=t_c * 1e3, gsamples_per_s=N3 / t_all / 1e9)
+    del ri, ts, te, sig, rgb
+    torch.cuda.empty_cache()
 
-# ---------------------------------------------------------------- config 4
-R4 = 262144
-torch.manual_seed(3)
-edges = torch.sort(torch.rand(R4, 65, device=dev), -1)[0]
-edges[:, 0], edges[:, -1] = 0.0, 1.0
-w = torch.rand(R4, 64, device=dev) ** 4 + 1e-3
-cdfs = torch.cat([torch.zeros(R4, 1, device=dev), torch.cumsum(w, -1)], -1)
-cdfs = (cdfs / cdfs[:, -1:]).contiguous()
-iv_in = RayIntervals(vals=edges)
-for strat in (False, True):
-    t = timed(lambda: importance_sampling(iv_in, cdfs, 32, strat), 50, 5)
-    # algorithmic bytes: read edges + cdfs (2 x 65 floats), write 32 centres + 33 edges, per ray
-    by = R4 * 4 * (2 * 65 + 32 + 33)
-    emit(config="4: importance_sampling 262144 rays x 64 -> 32", stratified=strat, us=t * 1e6,
-         gsamples_per_s=R4 * 32 / t / 1e9, algorithmic_gb_per_s=by / t / 1e9)
-
-
-def prop_fn(t_starts, t_ends):
-    mid = (t_starts + t_ends) * 0.5
-    return 4.0 * torch.exp(-((mid - 3.0) / 1.0) ** 2)
+if want('c4'):
+    # ---------------------------------------------------------------- config 4
+    R4 = 262144
+    torch.manual_seed(3)
+    edges = torch.sort(torch.rand(R4, 65, device=dev), -1)[0]
+    edges[:, 0], edges[:, -1] = 0.0, 1.0
+    w = torch.rand(R4, 64, device=dev) ** 4 + 1e-3
+    cdfs = torch.cat([torch.zeros(R4, 1, device=dev), torch.cumsum(w, -1)], -1)
+    cdfs = (cdfs / cdfs[:, -1:]).contiguous()
+    iv_in = RayIntervals(vals=edges)
+    for strat in (False, True):
+        t = timed(lambda: importance_sampling(iv_in, cdfs, 32, strat), 50, 5)
+        # algorithmic bytes: read edges + cdfs (2 x 65 floats), write 32 centres + 33 edges, per ray
+        by = R4 * 4 * (2 * 65 + 32 + 33)
+        emit(config="4: importance_sampling 262144 rays x 64 -> 32", stratified=strat, us=t * 1e6,
+             gsamples_per_s=R4 * 32 / t / 1e9, algorithmic_gb_per_s=by / t / 1e9)
 
 
-pn = PropNetEstimator().to(dev)
-t = timed(lambda: pn.sampling([prop_fn], [64], 32, n_rays=R4, near_plane=0.2, far_plane=50.0, sampling_type="lindisp",
-                              stratified=True), 20, 3)
-emit(config="4: PropNetEstimator.sampling 262144 rays, one proposal level 64 -> 32 final", ms=t * 1e3,
-     gsamples_per_s=R4 * 32 / t / 1e9)
+    def prop_fn(t_starts, t_ends):
+        mid = (t_starts + t_ends) * 0.5
+        return 4.0 * torch.exp(-((mid - 3.0) / 1.0) ** 2)
+
+
+    pn = PropNetEstimator().to(dev)
+    t = timed(lambda: pn.sampling([prop_fn], [64], 32, n_rays=R4, near_plane=0.2, far_plane=50.0, sampling_type="lindisp",
+                                  stratified=True), 20, 3)
+    emit(config="4: PropNetEstimator.sampling 262144 rays, one proposal level 64 -> 32 final", ms=t * 1e3,
+         gsamples_per_s=R4 * 32 / t / 1e9)
 
 # ---------------------------------------------------------------- standalone scans at config-2 size (K5: CUB by-key vs ours)
 est2 = nf.OccGridEstimator(torch.from_numpy(scenes.ROI_AABB), resolution=128).to(dev)
@@ -190,9 +200,9 @@ def test_mode_render(estimator, rays_o, rays_d, step, sigma_const=20.0, early_st
         rgbs = torch.sigmoid(t_starts)[:, None].expand(-1, 3)
         weights, _, _ = nf.render_weight_from_density(t_starts, t_ends, sigmas, ray_indices=ray_indices, n_rays=n,
                                                       prefix_trans=1 - opacity[ray_indices].squeeze(-1))
-        nf.accumulate_along_rays_(weights, values=rgbs, ray_indices=ray_indices, outputs=rgb)
-        nf.accumulate_along_rays_(weights, values=None, ray_indices=ray_indices, outputs=opacity)
-        nf.accumulate_along_rays_(weights, values=(t_starts + t_ends)[..., None] / 2.0, ray_indices=ray_indices,
+        accumulate_along_rays_(weights, values=rgbs, ray_indices=ray_indices, outputs=rgb)
+        accumulate_along_rays_(weights, values=None, ray_indices=ray_indices, outputs=opacity)
+        accumulate_along_rays_(weights, values=(t_starts + t_ends)[..., None] / 2.0, ray_indices=ray_indices,
                                   outputs=depth)
         near_planes = term
         ray_mask = torch.logical_and(opacity.view(-1) <= opc_thre, samples.packed_info[:, 1] == n_samples)

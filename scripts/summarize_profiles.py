@@ -14,15 +14,15 @@ for row in rows:
     v = v / 1e3 if u in ("ns", "nsecond") else v * 1e3 if u in ("ms", "msecond") else v * 1e6 if u in ("s", "second") else v
     agg.setdefault(name, []).append(v)
 tot = sum(sum(v) for v in agg.values())
-P(f"# {tag}: ncu launch list of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline`")
+P(f"# {tag}: ncu launch list of `NFA_BENCH_CLOCK_LOAD_STEPS=0 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-reference-cuda`")
 P("(`ncu --metrics gpu__time_duration.sum --clock-control none`; serialised, cold-cache: compare SHARES)\n")
 P("| kernel | launches | mean us | share |"); P("|---|---:|---:|---:|")
 for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
     P(f"| `{k}` | {len(v)} | {sum(v)/len(v):.1f} | {100*sum(v)/tot:.1f}% |")
 P("\nNotes: the launch list covers the whole bench command -- 5 steps of the value arm (2 timed + 3 warm-up), 2+2 of")
-P("the e2e arm, and the per-kernel roofline timings (11 direct launches of each compositing kernel and 11 sampling calls,")
-P("each preceded by the 256 MB `FillFunctor<unsigned char>` L2 flush, which is not part of a step).  Per step: march,")
-P("offsets, expand, composite fwd, ATen's mse / mean / mse-backward / fill, composite bwd.")
+P("the e2e arm, 5 of the pipelined arm, and the per-kernel roofline timings (11 direct launches of each of the four")
+P("kernels and 11 sampling calls, each preceded by the 256 MB `FillFunctor<unsigned char>` L2 flush, which is not part")
+P("of a step).  Per step: march, offsets, expand, composite fwd, ATen's mse / mean / mse-backward / fill, composite bwd.")
 # 2. full profiles
 import glob
 rr = []
@@ -42,7 +42,7 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__inst_executed.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
         "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "smsp__thread_inst_executed_per_inst_executed.ratio"]
-P(f"\n# {tag}: `ncu --set full --clock-control none` per kernel (one launch each, from scripts/profile_step.py)\n")
+P(f"\n# {tag}: `ncu --set full --clock-control none` per kernel (one launch each, from scripts/profile_kernels.py)\n")
 seen = set()
 for vals in rr[2:]:
     kn = re.sub(r"\(.*", "", vals[hdr.index("Kernel Name")]).replace("void ", "")

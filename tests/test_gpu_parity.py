@@ -968,3 +968,45 @@ def test_estimator_update_native_path_feeds_sampling():
     est2.binaries = got_bins.clone()
     b = est2.sampling(T(ro), T(rd), render_step_size=1e-2)
     assert a[0].numel() > 0 and all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+def test_by_key_scan_single_pass_many_tiles():
+    """The key-addressed scans run one tile of 2048 elements per CTA with decoupled look-back: segments that cross
+    tile boundaries, segments longer than several tiles (the look-back chain), unaligned views (scalar loads), the
+    reverse direction (autograd of the sum scans) -- against float64 cumulative sums / products per segment."""
+    torch.manual_seed(5)
+    cnts = torch.cat([torch.randint(0, 300, (400,)), torch.tensor([5000, 1, 0, 9000, 2047, 2048, 2049, 3]),
+                      torch.randint(0, 64, (300,))]).to(dev)
+    keys = torch.repeat_interleave(torch.arange(len(cnts), device=dev), cnts)
+    n = keys.numel()
+    assert n > 40 * 2048
+    xs = torch.rand(n + 3, device=dev) * 0.2 + 0.9           # around 1: products stay in range
+    starts = torch.cumsum(cnts, 0) - cnts
+    for off in (0, 1):                                       # off = 1: 4-byte aligned views -> scalar path
+        x = xs[off:off + n]
+        k = keys.clone() if off == 0 else torch.cat([keys.new_zeros(1), keys])[1:]
+        xd = x.double()
+        cs = torch.cumsum(xd, 0)
+        base = torch.where(starts > 0, cs[(starts - 1).clamp(min=0)], torch.zeros_like(cs[:1]))
+        incl_sum = cs - torch.repeat_interleave(base, cnts)
+        lg = torch.cumsum(torch.log(xd), 0)
+        lbase = torch.where(starts > 0, lg[(starts - 1).clamp(min=0)], torch.zeros_like(lg[:1]))
+        incl_prod = torch.exp(lg - torch.repeat_interleave(lbase, cnts))
+        first = torch.zeros(n, dtype=torch.bool, device=dev)
+        first[starts[cnts > 0]] = True
+        excl_sum = torch.where(first, torch.zeros_like(incl_sum), torch.roll(incl_sum, 1))
+        excl_prod = torch.where(first, torch.ones_like(incl_prod), torch.roll(incl_prod, 1))
+        for name, want, tol in (("inclusive_sum", incl_sum, 2e-5), ("exclusive_sum", excl_sum, 2e-5),
+                                ("inclusive_prod", incl_prod, 5e-4), ("exclusive_prod", excl_prod, 5e-4)):
+            got = getattr(nfa, name)(x, indices=k)
+            torch.testing.assert_close(got.double(), want, rtol=tol, atol=tol * 50, msg=f"{name} off={off}")
+        # reverse direction through autograd: d/dx of sum(inclusive_sum * g) is the reverse inclusive sum of g
+        xg = x.clone().requires_grad_(True)
+        g = torch.rand(n, device=dev)
+        (nfa.inclusive_sum(xg, indices=k) * g).sum().backward()
+        gd = g.double()
+        rcs = torch.flip(torch.cumsum(torch.flip(gd, [0]), 0), [0])
+        ends = starts + cnts
+        rbase = torch.where(ends < n, rcs[ends.clamp(max=n - 1)], torch.zeros_like(rcs[:1]))
+        want_grad = rcs - torch.repeat_interleave(rbase, cnts)
+        torch.testing.assert_close(xg.grad.double(), want_grad, rtol=2e-5, atol=1e-3)
