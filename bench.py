@@ -539,7 +539,9 @@ def main():
         loss_route = ("NVLink peer mailbox (csrc/peer.cu)" if mb is not None else "NCCL all_reduce") + \
             f", deferred into the march wait, read {LOSS_LAG} step(s) late"
     value = n_samples / (ms * 1e-3)
-    ms_e2e, n_e2e, _, _ = timed(True, args.steps, 2)
+    # the e2e arm gets the same warm-up as the value arm plus a short untimed run-in: its first steps allocate the
+    # staging buffers, open the copy stream and re-size the allocator's pools
+    ms_e2e, n_e2e, _, _ = timed(True, args.steps, args.warmup, load_steps=min(CLOCK_LOAD_STEPS, 200))
     # extra, NOT the headline: the same step with sampling_begin / sampling_end (an extension of the drop-in API,
     # see OccGridEstimator.sampling_begin), the next batch's traversal queued before this batch's backward
     ms_pipe, n_pipe, _, _ = timed(False, args.steps, args.warmup, pipelined=True)

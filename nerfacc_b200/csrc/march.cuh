@@ -446,7 +446,16 @@ NFA_HD void walk_run(Walk& w, const Boxes& boxes, const OccView& occ, Buf& buf, 
         int in_seg = 1;
         while (in_seg && n_desc < cap) {
             // ---------------- cell loop: while the brick is mixed (or brick steps are off)
+#if NFA_LOOP_VARIANT >= 4 && !NFA_BRICK_STEPS
+            // the descriptor buffer can only fill up where a descriptor is written: the capacity test lives there
+            // (variant 5: two cells per pass of the compiled loop)
+#if NFA_LOOP_VARIANT == 5
+#pragma unroll 2
+#endif
+            while (in_seg) {
+#else
             while (in_seg && n_desc < cap && (cls == kBrickMixed || a_off)) {
+#endif
                 NFA_COUNT(0);
                 const float tt = f_min(f_min(tdx, f_min(tdy, tdz)), seg_hi);  // grid.cu:185-186
                 // --- the DDA step first (utils_grid.cuh:116-142: x only if strictly smallest, else y if strictly
@@ -482,10 +491,12 @@ NFA_HD void walk_run(Walk& w, const Boxes& boxes, const OccView& occ, Buf& buf, 
 
                 // --- the cell just left: OCC(tt) / EMPTY(tt)
                 const int occd = (int)((uint32_t)(word >> bit) & 1u);
+                bool full = false;
                 if (occd != open) {  // a stretch opens (its pend is frozen from here on) or closes
                     if (open) {      // EMPTY(tt) closes the stretch
                         buf.put(n_desc++, pend, d_open, joined != 0);
                         pend = -INFINITY;
+                        full = n_desc >= cap;
                     } else {
                         joined = 0;
                     }
@@ -496,7 +507,22 @@ NFA_HD void walk_run(Walk& w, const Boxes& boxes, const OccView& occ, Buf& buf, 
 
                 // --- commit the step
                 bit = bit_next;
-#if NFA_LOOP_VARIANT == 2 && !NFA_BRICK_STEPS && defined(__CUDA_ARCH__)
+#if NFA_LOOP_VARIANT >= 4 && !NFA_BRICK_STEPS
+                if (full) {  // flush the buffer (phase 2), then resume here: the step itself is committed below
+#if NFA_LOOP_VARIANT >= 2 && defined(__CUDA_ARCH__)
+                    in_seg = stop ? 0 : 1;
+                    brick += crossed ? sb : 0;
+                    if (crossed && !stop) word = occ.words[brick];
+#else
+                    if (stop) in_seg = 0;
+                    else if (crossed) { brick += sb; word = occ.words[brick]; }
+#endif
+                    break;
+                }
+#else
+                (void)full;
+#endif
+#if NFA_LOOP_VARIANT >= 2 && !NFA_BRICK_STEPS && defined(__CUDA_ARCH__)
                 in_seg = stop ? 0 : 1;
                 brick += crossed ? sb : 0;
                 {   // predicated load: a branch here costs more than the load it skips
