@@ -89,6 +89,10 @@ int32_t nfa_occ_threshold_pack(int32_t n_grids, int32_t rx, int32_t ry, int32_t 
 int32_t nfa_counts_to_packed_info(int32_t n_rays, const int64_t* counts, int64_t* packed_info, void* workspace,
                                   nfa_stream_t stream);
 
+/* Measurement aid (scripts/march_trace.py), not used by the product path: per-warp time stamps of the following
+ * nfa_march launches are written to `buffer` (8 x uint64 per warp, n_tiles x 16 warps); null switches it off. */
+void nfa_debug_set_march_trace(void* buffer);
+
 /* ----------------------------------------------------------------------- */
 /* Grid traversal, constant step (cone_angle == 0, step_size > 0)           */
 /* ----------------------------------------------------------------------- */

@@ -32,6 +32,7 @@ SIGNATURES = {
     "nfa_occ_ema_update": (_c_i32, [_c_i64, _c_ptr, _c_ptr, _c_f32, _c_ptr, _c_ptr, _c_ptr]),
     "nfa_occ_threshold_workspace_bytes": (_c_i64, [_c_i64]),
     "nfa_occ_threshold_pack": (_c_i32, [_c_i32] * 4 + [_c_ptr, _c_f32] + [_c_ptr] * 6),
+    "nfa_debug_set_march_trace": (None, [_c_ptr]),
     "nfa_march_workspace_bytes": (_c_i64, [_c_i32, _c_i64]),
     "nfa_march": (_c_i32, [_c_i32, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_f32, _c_f32, _c_i32, _c_i32, _c_i32, _c_i32,
                            _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_f32, _c_i64, _c_ptr, _c_ptr,

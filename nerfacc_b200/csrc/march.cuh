@@ -207,6 +207,11 @@ struct Walk {
     // empty-space acceleration (single level, no terminate plane wanted): see walk_open_segment
     int accel;
     float t_stop;
+    // ray splitting (march kernel, longest rays of a tile): 0 = whole ray, 1 = this thread walks the part of the
+    // occupied box before its middle, 2 = the part from the middle on; split_ok turns 0 when the split could not be
+    // set up exactly (the pair then falls back to one thread walking the whole ray).  seg_lo: start of the segment.
+    int split_half, split_ok;
+    float seg_lo;
     // stretch under construction.  `pend` is the skip target: while no stretch is open it
     // accumulates (max) the exits of empty cells / segment starts; once a stretch opens it is
     // frozen and becomes that stretch's pend.  `d_open` is the exit of the stretch's last occupied
@@ -244,6 +249,9 @@ NFA_HD void walk_init(Walk& w, const float o[3], const float d[3], float near, f
     w.done = 0;
     w.accel = 0;
     w.t_stop = INFINITY;
+    w.split_half = 0;
+    w.split_ok = 1;
+    w.seg_lo = 0.f;
     w.pend = -INFINITY;
     w.d_open = -INFINITY;
 }
@@ -275,7 +283,9 @@ NFA_HD void walk_open_segment(Walk& w, const OccView& occ, int level, float lo, 
     dda_begin(s, w.o, w.d, w.inv, lo, hi, box, occ.g.res);
     w.level = level;
     w.seg_hi = hi;
+    w.seg_lo = lo;
     w.t_stop = INFINITY;
+    bool split_done = false;
     int remx = walk_steps_left(s.cur[0], s.ov[0] - s.st[0], s.st[0], occ.g.res[0]);
     int remy = walk_steps_left(s.cur[1], s.ov[1] - s.st[1], s.st[1], occ.g.res[1]);
     int remz = walk_steps_left(s.cur[2], s.ov[2] - s.st[2], s.st[2], occ.g.res[2]);
@@ -310,6 +320,17 @@ NFA_HD void walk_open_segment(Walk& w, const OccView& occ, int level, float lo, 
                 dead = true;
             }
         }
+        // Two threads per ray: both compute the same middle of the occupied box; the first stops at the cell that
+        // contains it (`tt >= t_stop`), the second jumps to that very cell (the same closed-form seeks as the jump to
+        // the box), so the cell is walked by both and the two stretch lists join there (traverse.cu).
+        if (w.split_half && !dead) {
+            const float t_mid = f_mul(f_add(t_in, t_out), 0.5f);
+            if (t_mid > t_in && t_mid < t_out) {
+                if (w.split_half == 1) t_out = t_mid;
+                else t_in = t_mid;
+                split_done = true;
+            }
+        }
         if (!dead && t_in > lo) {
             float t[3] = {s.td[0], s.td[1], s.td[2]};
             uint32_t n[3] = {0u, 0u, 0u};
@@ -320,6 +341,7 @@ NFA_HD void walk_open_segment(Walk& w, const OccView& occ, int level, float lo, 
                 La.half = 0.0f;  // plain "first chain value >= target"
                 ok = ok && lat_seek(La, t[a], t_in, n[a]);
             }
+            if (!ok) split_done = false;  // no exact jump: a second half cannot start in the middle
             if (ok) {
                 if (n[0] >= (uint32_t)remx || n[1] >= (uint32_t)remy || n[2] >= (uint32_t)remz) {
                     dead = true;  // the walk ends before it reaches the occupied region
@@ -338,6 +360,7 @@ NFA_HD void walk_open_segment(Walk& w, const OccView& occ, int level, float lo, 
         }
         w.t_stop = t_out;
     }
+    if (w.split_half && !split_done) w.split_ok = 0;
     w.tdx = s.td[0]; w.tdy = s.td[1]; w.tdz = s.td[2];
     w.dlx = s.dl[0]; w.dly = s.dl[1]; w.dlz = s.dl[2];
     w.dbx = s.st[0] * 16; w.dby = s.st[1] * 4; w.dbz = s.st[2];
@@ -446,16 +469,7 @@ NFA_HD void walk_run(Walk& w, const Boxes& boxes, const OccView& occ, Buf& buf, 
         int in_seg = 1;
         while (in_seg && n_desc < cap) {
             // ---------------- cell loop: while the brick is mixed (or brick steps are off)
-#if NFA_LOOP_VARIANT >= 4 && !NFA_BRICK_STEPS
-            // the descriptor buffer can only fill up where a descriptor is written: the capacity test lives there
-            // (variant 5: two cells per pass of the compiled loop)
-#if NFA_LOOP_VARIANT == 5
-#pragma unroll 2
-#endif
-            while (in_seg) {
-#else
             while (in_seg && n_desc < cap && (cls == kBrickMixed || a_off)) {
-#endif
                 NFA_COUNT(0);
                 const float tt = f_min(f_min(tdx, f_min(tdy, tdz)), seg_hi);  // grid.cu:185-186
                 // --- the DDA step first (utils_grid.cuh:116-142: x only if strictly smallest, else y if strictly
@@ -491,12 +505,10 @@ NFA_HD void walk_run(Walk& w, const Boxes& boxes, const OccView& occ, Buf& buf, 
 
                 // --- the cell just left: OCC(tt) / EMPTY(tt)
                 const int occd = (int)((uint32_t)(word >> bit) & 1u);
-                bool full = false;
                 if (occd != open) {  // a stretch opens (its pend is frozen from here on) or closes
                     if (open) {      // EMPTY(tt) closes the stretch
                         buf.put(n_desc++, pend, d_open, joined != 0);
                         pend = -INFINITY;
-                        full = n_desc >= cap;
                     } else {
                         joined = 0;
                     }
@@ -507,21 +519,6 @@ NFA_HD void walk_run(Walk& w, const Boxes& boxes, const OccView& occ, Buf& buf, 
 
                 // --- commit the step
                 bit = bit_next;
-#if NFA_LOOP_VARIANT >= 4 && !NFA_BRICK_STEPS
-                if (full) {  // flush the buffer (phase 2), then resume here: the step itself is committed below
-#if NFA_LOOP_VARIANT >= 2 && defined(__CUDA_ARCH__)
-                    in_seg = stop ? 0 : 1;
-                    brick += crossed ? sb : 0;
-                    if (crossed && !stop) word = occ.words[brick];
-#else
-                    if (stop) in_seg = 0;
-                    else if (crossed) { brick += sb; word = occ.words[brick]; }
-#endif
-                    break;
-                }
-#else
-                (void)full;
-#endif
 #if NFA_LOOP_VARIANT >= 2 && !NFA_BRICK_STEPS && defined(__CUDA_ARCH__)
                 in_seg = stop ? 0 : 1;
                 brick += crossed ? sb : 0;

@@ -136,7 +136,63 @@ static float march_one(const Boxes& boxes, const OccView& occ, const float* o, c
     return term;
 }
 
+// A ray walked by two "threads" (first / second half of the occupied box) whose stretch lists are joined the way
+// march_kernel joins them (csrc/traverse.cu); returns false where the kernel would fall back to one thread.
+struct BigBuf {
+    enum { K = 8 };  // the kernel's buffer: a half that needs more falls back
+    float pend[K], open[K];
+    bool joined[K];
+    void put(int j, float p, float o, bool jn) { pend[j] = p; open[j] = o; joined[j] = jn; }
+};
+
+static bool march_one_split(const OccView& occ, const float* box, const float* o, const float* d, float near, float far,
+                            const Lattice& L, LatState& m, std::vector<float>& vt, std::vector<uint32_t>& vn)
+{
+    SingleBox boxes{box};
+    Walk wa, wb;
+    BigBuf ba, bb;
+    int na = 0, nb = 0;
+    walk_init(wa, o, d, near, far);
+    walk_init(wb, o, d, near, far);
+    wa.accel = wb.accel = 1;
+    wa.split_half = 1;
+    wb.split_half = 2;
+    walk_run(wa, boxes, occ, ba, na, BigBuf::K);
+    walk_run(wb, boxes, occ, bb, nb, BigBuf::K);
+    const bool fin = wa.done && wa.split_ok && wb.done && wb.split_ok;
+    const bool b_starts_occ = nb > 0 && bb.pend[0] == wb.seg_lo;
+    const bool merge = wa.open != 0 && na > 0;
+    if (!fin || merge != b_starts_occ) return false;
+    lat_init(m, L, near);
+    RunOut out;
+    const int total = na + nb - (merge ? 1 : 0);
+    for (int j = 0; j < total; ++j) {
+        float pd, op;
+        bool jn;
+        if (j < na) {
+            pd = ba.pend[j]; op = ba.open[j]; jn = ba.joined[j];
+            if (merge && j == na - 1) op = bb.open[0];
+        } else {
+            const int jb = j - na + (merge ? 1 : 0);
+            pd = bb.pend[jb]; op = bb.open[jb]; jn = bb.joined[jb];
+        }
+        lat_consume(m, pd, op, jn, out);
+        if (out.valid) { vt.push_back(out.t_first); vn.push_back(out.n); }
+    }
+    lat_finish(m, -INFINITY, false, out);
+    if (out.valid) { vt.push_back(out.t_first); vn.push_back(out.n); }
+    return true;
+}
+
+static long g_split_taken, g_split_fallback;
+
 extern "C" {
+
+void sim_split_counts(long* out, int reset)
+{
+    out[0] = g_split_taken; out[1] = g_split_fallback;
+    if (reset) g_split_taken = g_split_fallback = 0;
+}
 
 // March all rays; per ray: n_samples, n_runs, terminate plane; runs appended to
 // flat arrays (caller passes capacity; returns total runs or -1 on overflow).
@@ -163,7 +219,18 @@ int64_t sim_march(int32_t n_rays, const float* rays_o, const float* rays_d,
         vn.clear();
         LatState m;
         float term;
-        if (t_sorted == nullptr) {
+        if (t_sorted == nullptr && accel == 2) {  // accel == 2: every ray split between two walkers, as the kernel's
+            term = 0.f;                           // longest rays are; where that is not possible, one walker
+            if (march_one_split(occ, aabbs, rays_o + 3 * r, rays_d + 3 * r, near_planes[r], far_planes[r], L, m, vt, vn)) {
+                ++g_split_taken;
+            } else {
+                ++g_split_fallback;
+                vt.clear();
+                vn.clear();
+                SingleBox b{aabbs};
+                term = march_one(b, occ, rays_o + 3 * r, rays_d + 3 * r, near_planes[r], far_planes[r], L, m, vt, vn, 1);
+            }
+        } else if (t_sorted == nullptr) {
             SingleBox b{aabbs};
             term = march_one(b, occ, rays_o + 3 * r, rays_d + 3 * r, near_planes[r], far_planes[r], L, m, vt, vn,
                              accel);

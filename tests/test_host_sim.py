@@ -317,3 +317,49 @@ def test_brick_loop_variant_is_bit_exact_and_actually_skips(host_sim_brick, orc)
     full = np.ones((1, 16, 16, 16), bool)
     _compare(sim, orc, ro2, rd2, full, a4[:1], zero, inf, 1e-2, accel=1)
     _compare(sim, orc, ro2, rd2, full, a4[:1], rng.random(200).astype(np.float32), (1 + rng.random(200) * 3).astype(np.float32), 1e-2)
+
+
+# ---------------------------------------------------------------- two walkers per ray (the kernel's longest rays)
+
+def test_split_rays_join_exactly(host_sim, orc):
+    """march_kernel gives the longest rays of a tile two threads: one walks the occupied box up to its middle, the
+    other from there, and the stretch lists are joined at the cell both walk.  Here EVERY ray is split (accel=2 in
+    the simulation) and the result must still be the oracle's, bit for bit; rays that cannot be split fall back."""
+    import ctypes as C
+    sim = host_sim
+    rng = np.random.default_rng(17)
+    R = 2048
+    ro, rd = scenes.ball_rays(R)
+    bins, aabbs = scenes.ball_grid(128), scenes.nested_aabbs(1)
+    near, far = np.zeros(R, np.float32), np.full(R, 1e10, np.float32)
+    cnt = (C.c_long * 2)()
+    sim.sim_split_counts(cnt, 1)
+    _compare(sim, orc, ro, rd, bins, aabbs, near, far, scenes.BALL_STEP, accel=2)
+    sim.sim_split_counts(cnt, 1)
+    assert cnt[0] > 0.95 * R                      # nearly every ray of the ball scene really is split
+    _compare(sim, orc, ro, rd, bins, aabbs, (rng.random(R) * scenes.BALL_STEP).astype(np.float32), far, scenes.BALL_STEP, accel=2)
+    frag = bins & (rng.random(bins.shape) > 0.5)  # many stretches: the 8-slot buffers overflow -> fall back
+    _compare(sim, orc, ro[:512], rd[:512], frag, aabbs, near[:512], far[:512], scenes.BALL_STEP, accel=2)
+    frag2 = bins & (rng.random(bins.shape) > 0.03)
+    _compare(sim, orc, ro[:1024], rd[:1024], frag2, aabbs, near[:1024], far[:1024], scenes.BALL_STEP, accel=2)
+    sim.sim_split_counts(cnt, 1)
+    assert cnt[0] > 0 and cnt[1] > 0
+    off_centre = np.zeros((1, 128, 128, 128), bool)
+    off_centre[0, 90:120, 5:9, 60:61] = True
+    off_centre[0, 97, 100, 3] = True
+    _compare(sim, orc, ro, rd, off_centre, aabbs, near, far, 3e-3, accel=2)
+    _compare(sim, orc, ro, rd, off_centre, aabbs, (rng.random(R) * 4).astype(np.float32),
+             (3 + rng.random(R) * 3).astype(np.float32), 3e-3, accel=2)
+    ro2 = rng.standard_normal((300, 3)).astype(np.float32)
+    rd2 = rng.standard_normal((300, 3)).astype(np.float32)
+    rd2 /= np.linalg.norm(rd2, axis=1, keepdims=True)
+    zero, inf = np.zeros(300, np.float32), np.full(300, np.inf, np.float32)
+    a1 = scenes.nested_aabbs(1)
+    for grid in (rng.random((1, 32, 32, 32)) > 0.5, rng.random((1, 30, 17, 5)) > 0.7, np.ones((1, 16, 16, 16), bool),
+                 np.kron(rng.random((1, 8, 8, 8)) > 0.5, np.ones((1, 4, 4, 4), bool))):
+        _compare(sim, orc, ro2, rd2, grid, a1, zero, inf, 3e-3, accel=2)
+        _compare(sim, orc, ro2, rd2, grid, a1, rng.random(300).astype(np.float32), (1 + rng.random(300) * 3).astype(np.float32), 1e-2, accel=2)
+    # axis-aligned and other degenerate rays
+    ro3 = np.array([[-2, 0.1, 0.2], [0.3, -3, 0.1], [0.01, 0.02, 5], [0, 0, 0], [9, 9, 9], [0.5, 0.5, 0.5]], np.float32)
+    rd3 = np.array([[1, 0, 0], [0, 1, 0], [0, 0, -1], [0, 0, 1], [1, 0, 0], [-0.6, 0.8, 0]], np.float32)
+    _compare(sim, orc, ro3, rd3, rng.random((1, 32, 32, 32)) > 0.5, a1, np.zeros(6, np.float32), np.full(6, np.inf, np.float32), 1e-2, accel=2)
