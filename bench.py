@@ -612,6 +612,11 @@ def main():
         job.sc.busy = False
         job.sc = None
         t_fwd, t_bwd, t_trav = time_call(k_fwd), time_call(k_bwd), time_call(k_trav)
+        # what this GPU does on a write-only stream of the expand kernel's size (ATen fill, timed the same way): the
+        # copy figure in MEASURED_PEAKS.json is read + write; a pure store stream is slower, and expand is one
+        wbuf = torch.empty(B_TRAVERSE * N, dtype=torch.uint8, device=dev)
+        t_fill = time_call(lambda _: wbuf.fill_(1))
+        del wbuf
         # parity of the direct launches with the public API (same kernels, same arguments)
         with torch.no_grad():
             chk = nfa.rendering(ts, te, ri, n_rays=R, rgb_sigma_fn=lambda a, b_, c: (cl, sg))
@@ -642,6 +647,9 @@ def main():
                 "stages_frac_algorithmic": {k: round(v[0] / v[2] / 1e9 / peak, 3) for k, v in stages.items()},
                 "stages_frac_dram": {k: round((load_traffic(k, N) or v[1]) / v[2] / 1e9 / peak, 3)
                                      for k, v in stages.items()},
+                "write_only": {"gbs": round(B_TRAVERSE * N / t_fill / 1e9, 1), "fill_us": round(t_fill * 1e6, 1),
+                               "how": "torch fill_ of 16 B x n_samples, timed like the stages",
+                               "expand_frac": round(t_fill / t_expand, 3)},
                 "sampling_call_us": round(t_trav * 1e6, 1),
                 "step_frac_of_roofline": ((B_TRAVERSE + B_FWD + B_BWD) * N + B_RAY * R) / (ms / args.steps * 1e-3) / 1e9 / peak}
         del flush

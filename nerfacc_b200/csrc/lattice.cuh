@@ -170,4 +170,46 @@ NFA_HD bool lat_seek(const Lattice& L, float& t, float target, uint32_t& k)
     return false;
 }
 
+// The climb from `near` to a ray's first stretch crosses every binade between them (~10 for near = 0 and a scene a few
+// units away), one piece each -- and with a uniform near plane it is the same climb for every ray.  So it is done once
+// per call, on the host: pts[i] = the first lattice point >= 2^(e0 + i - 127).  A seek may then start from the entry
+// one binade below its target: every earlier lattice point is below half the target, and (the table only covers
+// binades above dt's) so is dt/2, hence none of them can satisfy t + dt/2 >= target.
+constexpr int kLatTableMax = 40;
+struct LatTable {
+    float pts[kLatTableMax];
+    int32_t e0;  // biased exponent of entry 0
+    int32_t n;   // entries (0: no table -- per-ray near planes, a negative near plane, a stuck lattice)
+};
+
+NFA_HD void lat_table_build(const Lattice& L, float near, LatTable& T)
+{
+    T.n = 0;
+    T.e0 = 0;
+    if (!(near >= 0.0f) || L.ed == 0u || L.ed >= 255u) return;
+    const uint32_t e_near = f_bits(near) >> 23;
+    const uint32_t e0 = (e_near > L.ed ? e_near : L.ed) + 1u;
+    T.e0 = (int32_t)e0;
+    Lattice L0 = L;
+    L0.half = 0.0f;  // plain "first lattice point >= target"
+    float t = near;
+    for (int i = 0; i < kLatTableMax && e0 + (uint32_t)i < 255u; ++i) {
+        uint32_t k = 0;
+        if (!lat_seek(L0, t, f_from_bits((e0 + (uint32_t)i) << 23), k)) break;
+        T.pts[i] = t;
+        T.n = i + 1;
+    }
+}
+
+// Move t forward to the table entry below `target`'s binade, if that is ahead of t.
+NFA_HD void lat_table_jump(const LatTable& T, float target, float& t)
+{
+    if (T.n <= 0 || !(target > 0.0f)) return;
+    int idx = (int)(f_bits(target) >> 23) - 1 - T.e0;
+    if (idx >= T.n) idx = T.n - 1;
+    if (idx < 0) return;
+    const float pt = T.pts[idx];
+    if (pt > t) t = pt;
+}
+
 }  // namespace nfa

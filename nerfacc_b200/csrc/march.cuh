@@ -207,11 +207,6 @@ struct Walk {
     // empty-space acceleration (single level, no terminate plane wanted): see walk_open_segment
     int accel;
     float t_stop;
-    // ray splitting (march kernel, longest rays of a tile): 0 = whole ray, 1 = this thread walks the part of the
-    // occupied box before its middle, 2 = the part from the middle on; split_ok turns 0 when the split could not be
-    // set up exactly (the pair then falls back to one thread walking the whole ray).  seg_lo: start of the segment.
-    int split_half, split_ok;
-    float seg_lo;
     // stretch under construction.  `pend` is the skip target: while no stretch is open it
     // accumulates (max) the exits of empty cells / segment starts; once a stretch opens it is
     // frozen and becomes that stretch's pend.  `d_open` is the exit of the stretch's last occupied
@@ -249,9 +244,6 @@ NFA_HD void walk_init(Walk& w, const float o[3], const float d[3], float near, f
     w.done = 0;
     w.accel = 0;
     w.t_stop = INFINITY;
-    w.split_half = 0;
-    w.split_ok = 1;
-    w.seg_lo = 0.f;
     w.pend = -INFINITY;
     w.d_open = -INFINITY;
 }
@@ -283,9 +275,7 @@ NFA_HD void walk_open_segment(Walk& w, const OccView& occ, int level, float lo, 
     dda_begin(s, w.o, w.d, w.inv, lo, hi, box, occ.g.res);
     w.level = level;
     w.seg_hi = hi;
-    w.seg_lo = lo;
     w.t_stop = INFINITY;
-    bool split_done = false;
     int remx = walk_steps_left(s.cur[0], s.ov[0] - s.st[0], s.st[0], occ.g.res[0]);
     int remy = walk_steps_left(s.cur[1], s.ov[1] - s.st[1], s.st[1], occ.g.res[1]);
     int remz = walk_steps_left(s.cur[2], s.ov[2] - s.st[2], s.st[2], occ.g.res[2]);
@@ -320,17 +310,6 @@ NFA_HD void walk_open_segment(Walk& w, const OccView& occ, int level, float lo, 
                 dead = true;
             }
         }
-        // Two threads per ray: both compute the same middle of the occupied box; the first stops at the cell that
-        // contains it (`tt >= t_stop`), the second jumps to that very cell (the same closed-form seeks as the jump to
-        // the box), so the cell is walked by both and the two stretch lists join there (traverse.cu).
-        if (w.split_half && !dead) {
-            const float t_mid = f_mul(f_add(t_in, t_out), 0.5f);
-            if (t_mid > t_in && t_mid < t_out) {
-                if (w.split_half == 1) t_out = t_mid;
-                else t_in = t_mid;
-                split_done = true;
-            }
-        }
         if (!dead && t_in > lo) {
             float t[3] = {s.td[0], s.td[1], s.td[2]};
             uint32_t n[3] = {0u, 0u, 0u};
@@ -341,7 +320,6 @@ NFA_HD void walk_open_segment(Walk& w, const OccView& occ, int level, float lo, 
                 La.half = 0.0f;  // plain "first chain value >= target"
                 ok = ok && lat_seek(La, t[a], t_in, n[a]);
             }
-            if (!ok) split_done = false;  // no exact jump: a second half cannot start in the middle
             if (ok) {
                 if (n[0] >= (uint32_t)remx || n[1] >= (uint32_t)remy || n[2] >= (uint32_t)remz) {
                     dead = true;  // the walk ends before it reaches the occupied region
@@ -360,7 +338,6 @@ NFA_HD void walk_open_segment(Walk& w, const OccView& occ, int level, float lo, 
         }
         w.t_stop = t_out;
     }
-    if (w.split_half && !split_done) w.split_ok = 0;
     w.tdx = s.td[0]; w.tdy = s.td[1]; w.tdz = s.td[2];
     w.dlx = s.dl[0]; w.dly = s.dl[1]; w.dlz = s.dl[2];
     w.dbx = s.st[0] * 16; w.dby = s.st[1] * 4; w.dbz = s.st[2];
@@ -709,6 +686,53 @@ NFA_HD void lat_consume(LatState& m, float pend, float open, bool joined, RunOut
     k = 0;
     m.ok = lat_seek(m.L, m.t, open, k);
     m.run_n += k;
+}
+
+// Phase 2 by stretch (one grid level).  There every stretch follows an EMPTY cell, so it is its own run, and the run's
+// first sample and length depend only on the ray's lattice and the stretch's two times: the first lattice point with
+// t + dt/2 >= target is the same whichever earlier lattice point the search starts from, and targets only grow along
+// a ray.  So a ray's stretches need not be taken one after the other: lat_anchor() climbs to the first one (the long
+// seek from `near`), lat_stretch() handles any stretch from that anchor (any lane may do it), and lat_take() adds the
+// results up in order.  Same runs as lat_consume() on the same descriptors (tests/test_host_sim.py).
+constexpr uint32_t kStretchFailed = 0xffffffffu;
+
+NFA_HD void lat_anchor(LatState& m, const LatTable& table, float pend0)
+{
+    if (!m.ok) return;
+    lat_table_jump(table, pend0, m.t);
+    uint32_t k = 0;
+    m.ok = lat_seek(m.L, m.t, pend0, k);
+}
+
+NFA_HD void lat_stretch(const Lattice& L, float anchor, bool ok, float pend, float open, float& first, uint32_t& n,
+                        float& after)
+{
+    float t = anchor;
+    uint32_t k = 0;
+    ok = ok && lat_seek(L, t, pend, k);
+    first = t;
+    k = 0;
+    ok = ok && lat_seek(L, t, open, k);
+    n = ok ? k : kStretchFailed;
+    after = t;
+}
+
+NFA_HD void lat_take(LatState& m, float first, uint32_t n, RunOut& out)
+{
+    out.valid = false;
+    if (!m.ok) return;
+    if (n == kStretchFailed) {
+        m.ok = false;
+        return;
+    }
+    if (n == 0u) return;
+    out.valid = true;
+    out.t_first = first;
+    out.n = n;
+    out.sample_off = m.n_samples;
+    out.run_idx = m.n_runs;
+    m.n_samples += n;
+    m.n_runs += 1;
 }
 
 // End of ray: close the open run and (optionally) apply the trailing skip.

@@ -38,7 +38,11 @@
 namespace nfa {
 
 constexpr int kMaxTileRays = 512;   // rays per CTA in the march / offsets kernels: march_tile_rays(), <= this
-constexpr int kDescSlots = 8;       // stretch descriptors buffered per ray between the two march phases
+#ifndef NFA_POOL_ONE_ATOMIC
+#define NFA_POOL_ONE_ATOMIC 1
+#endif
+constexpr int kDescSlots = 8;       // stretch descriptors buffered per ray between the two march phases ...
+constexpr int kDescSlotsWide = 16;  // ... and when one wave holds every ray (shared memory to spare): no second round
 constexpr int kSortBuckets = 256;   // counting sort of a tile's rays by expected walk length
 
 // Rays per march CTA (= threads).  All CTAs of a batch this size are resident at once, so the kernel takes as
@@ -237,8 +241,8 @@ struct MarchParams {
     const int64_t* t_indices;
     const uint8_t* hits;
     float step_size;
+    LatTable lat_table;   // lattice points at the binade starts, from the uniform near plane (n = 0: none)
     int32_t brick_steps;  // warps per tile (the longest rays) that may take whole bricks; needs -DNFA_BRICK_STEPS=1
-    int32_t split_rays;   // the tile's this many longest rays get two threads each (blockDim = tile rays + split_rays)
     unsigned long long* trace;  // measurement aid (nfa_debug_set_march_trace): 8 x u64 per warp, or null
     Workspace ws;
     int64_t* totals;
@@ -248,7 +252,7 @@ struct MarchParams {
 
 // descriptor buffer: one shared-memory column per thread, joined flags in a register
 struct SmemBuf {
-    float* pend;   // [kDescSlots][tile]
+    float* pend;   // [slots][tile]
     float* open;
     uint32_t joined_mask;
     int tid, tile;
@@ -280,13 +284,13 @@ __device__ __forceinline__ void emit_runs(const RunOut& out, uint32_t ray, const
 }
 
 // dynamic shared memory of the march kernel (tile = blockDim.x rays):
-//   [class mip (kSmemCoarse)] [o: 3 tile f32] [d: 3 tile f32] [pend: 8 tile] [open: 8 tile] [order: tile u32]
-__host__ __device__ inline size_t march_smem_bytes(int tile, size_t coarse_bytes)
+//   [class mip (kSmemCoarse)] [o: 3 tile f32] [d: 3 tile f32] [pend: slots tile] [open: slots tile] [order: tile u32]
+__host__ __device__ inline size_t march_smem_bytes(int tile, size_t coarse_bytes, int slots)
 {
-    return coarse_bytes + (size_t)tile * 4 * (3 + 3 + 2 * kDescSlots + 1);
+    return coarse_bytes + (size_t)tile * 4 * (3 + 3 + 2 * slots + 1);
 }
 
-template <bool kSingle, bool kSmemCoarse>
+template <bool kSingle, bool kSmemCoarse, int kSlots>
 __global__ void __launch_bounds__(kMaxTileRays) march_kernel(const MarchParams p)
 {
     extern __shared__ __align__(16) uint32_t s_dyn[];
@@ -296,7 +300,7 @@ __global__ void __launch_bounds__(kMaxTileRays) march_kernel(const MarchParams p
     __shared__ bool s_last;
     __shared__ uint32_t s_hist[kSortBuckets];
 
-    const int T = blockDim.x;            // threads; the tile holds TR = T - K rays
+    const int T = blockDim.x;            // threads = rays of a (full) tile
     const int tid = threadIdx.x, lane = tid & 31;
     unsigned long long tr_t0 = 0, tr_c0 = 0, tr_c1 = 0, tr_c2 = 0, tr_c3 = 0, tr_w = 0;
     int tr_first = 1, tr_loops = 0;
@@ -305,16 +309,17 @@ __global__ void __launch_bounds__(kMaxTileRays) march_kernel(const MarchParams p
         tr_c0 = clock64();
     }
     const int tile = blockIdx.x;
-    const int K = kSingle ? p.split_rays : 0;
-    const int TR = T - K;
-    const int r0 = tile * TR;
-    const int nr = min(TR, p.n_rays - r0);
+    const int r0 = tile * T;
+    const int nr = min(T, p.n_rays - r0);
     uint32_t* s_coarse = s_dyn;
     float* s_o = reinterpret_cast<float*>(s_dyn + (kSmemCoarse ? p.coarse_words : 0));
     float* s_d = s_o + 3 * T;
     float* s_pend = s_d + 3 * T;
-    float* s_open = s_pend + kDescSlots * T;
-    uint32_t* s_sort = reinterpret_cast<uint32_t*>(s_open + kDescSlots * T);
+    constexpr int S = kSlots;  // stretch descriptors buffered per ray
+    float* s_open = s_pend + S * T;
+    uint32_t* s_sort = reinterpret_cast<uint32_t*>(s_open + S * T);
+    float* s_tail = reinterpret_cast<float*>(s_sort);  // lattice point after a ray's last stretch: each thread has read
+                                                       // its s_sort slot long before a lane of its warp writes here
 
     // ---- stage the ray tile (and the class mip) into shared memory: TMA bulk copies + mbarrier
     const float* g_o = p.rays_o + (int64_t)r0 * 3;
@@ -411,21 +416,6 @@ __global__ void __launch_bounds__(kMaxTileRays) march_kernel(const MarchParams p
         __syncthreads();
         rt = (int)s_sort[tid];
     }
-    // Two threads for each of the tile's K longest rays (full tiles only): the kernel is as slow as its longest
-    // ray, so those are cut in the middle of the occupied box (march.cuh, walk_open_segment) and walked by the two
-    // halves of a warp: lane l < 16 takes the first part of a ray, lane l + 16 the second.  With the K rayless
-    // threads sorted in front, ranks K .. T-K-1 are the other rays (one thread each, the first T-2K threads).
-    int half = 0;
-    const bool split_tile = K > 0 && nr == TR;
-    if (split_tile) {
-        if (tid < T - 2 * K) {
-            rt = (int)s_sort[tid + K];
-        } else {
-            const int q = tid - (T - 2 * K);
-            rt = (int)s_sort[T - K + (q >> 5) * 16 + (q & 15)];
-            half = ((q >> 4) & 1) + 1;
-        }
-    }
     const int r = r0 + rt;
     bool active = rt < nr;
     float near = 0.f, far = 0.f;
@@ -454,7 +444,6 @@ __global__ void __launch_bounds__(kMaxTileRays) march_kernel(const MarchParams p
     // whole-brick steps (when compiled in) only for the tile's longest rays: after the sort these sit in the last
     // warps, pass near the middle of the occupied region and so cross the same kinds of brick together
     w.brick_steps = (p.brick_steps > 0 && tid >= T - 32 * p.brick_steps) ? 1 : 0;
-    w.split_half = half;
     SmemBuf buf;
     buf.pend = s_pend;
     buf.open = s_open;
@@ -467,69 +456,10 @@ __global__ void __launch_bounds__(kMaxTileRays) march_kernel(const MarchParams p
     const SingleBox single{p.aabbs};
     const SortedBoxes sorted{p.aabbs, G, kSingle ? nullptr : p.t_sorted + rr * 2 * G,
                              kSingle ? nullptr : p.t_indices + rr * 2 * G, kSingle ? nullptr : p.hits + rr * G};
-    if (kSingle && split_tile && tid >= T - 2 * K) {  // whole warps: T - 2K is a multiple of 32
-        // ---- split rays: both halves walk, then the first half's lane joins the two stretch lists and turns them
-        // into runs.  The cell that contains the middle is walked by both: if it is occupied, the first list's last
-        // stretch (open at its end) and the second list's first one (its pend is still the segment start) are ONE
-        // stretch.  Anything unexpected -- a buffer that filled up, a split that could not be set up exactly, the
-        // two lists disagreeing about the shared cell -- and the pair falls back: the first lane walks the whole
-        // ray again through the ordinary loop below.
-        walk_run(w, single, occ, buf, n_desc, kDescSlots);
-        __syncwarp();  // the halves read each other's buffer columns
-        const bool is_b = half == 2;
-        const int fin = (w.done && w.split_ok) ? 1 : 0;
-        const int n_other = __shfl_xor_sync(0xffffffffu, n_desc, 16);
-        const int fin_other = __shfl_xor_sync(0xffffffffu, fin, 16);
-        const int open_other = __shfl_xor_sync(0xffffffffu, w.open, 16);
-        const int col_b = is_b ? tid : tid + 16;              // the second half's column of the buffers
-        const int n_a = is_b ? n_other : n_desc, n_b = is_b ? n_desc : n_other;
-        const int open_a = is_b ? open_other : w.open;
-        const unsigned jm_other = __shfl_xor_sync(0xffffffffu, buf.joined_mask, 16);
-        const bool b_starts_occ = n_b > 0 && s_pend[col_b] == w.seg_lo;
-        const bool merge = open_a != 0 && n_a > 0;
-        const bool pair_ok = fin && fin_other && (merge == b_starts_occ);
-        if (pair_ok) {
-            const int total = is_b ? 0 : n_a + n_b - (merge ? 1 : 0);
-            const int maxd = __reduce_max_sync(0xffffffffu, total);
-            for (int j = 0; j < maxd; ++j) {
-                RunOut out;
-                out.valid = false;
-                if (j < total) {
-                    float pd, op;
-                    bool jn;
-                    if (j < n_a) {
-                        pd = s_pend[j * T + tid];
-                        op = s_open[j * T + tid];
-                        jn = (buf.joined_mask >> j) & 1u;
-                        if (merge && j == n_a - 1) op = s_open[col_b];  // ... continues into the second half
-                    } else {
-                        const int jb = j - n_a + (merge ? 1 : 0);
-                        pd = s_pend[jb * T + col_b];
-                        op = s_open[jb * T + col_b];
-                        jn = (jm_other >> jb) & 1u;
-                    }
-                    lat_consume(m, pd, op, jn, out);
-                }
-                emit_runs(out, (uint32_t)r, p.ws, lane);
-            }
-            w.done = 1;
-        } else if (!is_b) {
-            walk_init(w, o, d, near, far);  // again, as a whole
-            w.accel = 1;
-            w.brick_steps = 0;
-            lat_init(m, L, near);
-        } else {
-            w.done = 1;
-        }
-        if (is_b) active = false;  // the ray's outputs are the first lane's
-        n_desc = 0;
-        buf.joined_mask = 0u;
-        __syncwarp();
-    }
     for (;;) {
         // phase 1: DDA only (divergent, cheap)
-        if (kSingle) walk_run(w, single, occ, buf, n_desc, kDescSlots);
-        else walk_run(w, sorted, occ, buf, n_desc, kDescSlots);
+        if (kSingle) walk_run(w, single, occ, buf, n_desc, S);
+        else walk_run(w, sorted, occ, buf, n_desc, S);
         if (p.trace) {
             if (tr_first) tr_w = clock64();  // first walk pass of this warp done
             tr_first = 0;
@@ -537,12 +467,107 @@ __global__ void __launch_bounds__(kMaxTileRays) march_kernel(const MarchParams p
         }
         // phase 2: lattice seeks, all lanes in step
         const int maxd = __reduce_max_sync(0xffffffffu, n_desc);
-        for (int j = 0; j < maxd; ++j) {
-            RunOut out;
-            out.valid = false;
-            if (j < n_desc)
-                lat_consume(m, s_pend[j * T + tid], s_open[j * T + tid], (buf.joined_mask >> j) & 1u, out);
-            emit_runs(out, (uint32_t)r, p.ws, lane);
+        if (kSingle && !__any_sync(0xffffffffu, buf.joined_mask != 0u)) {
+            // One level: the stretches of the warp's 32 rays are independent (march.cuh, lat_stretch), so they are
+            // dealt out to the lanes -- most rays have one, a ray that grazes the surface up to 8, and a lane that
+            // took its ray's stretches one after the other made the warp with the grazing rays the tile's slowest.
+            if (__any_sync(0xffffffffu, m.run_n > 0u)) {  // (only after a round that went the other way)
+                RunOut out;
+                lat_close(m, out);
+                emit_runs(out, (uint32_t)r, p.ws, lane);
+            }
+            if (n_desc > 0) lat_anchor(m, p.lat_table, s_pend[tid]);
+            const float anchor = m.t;
+            int incl = n_desc;
+#pragma unroll
+            for (int sft = 1; sft < 32; sft <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, incl, sft);
+                if (lane >= sft) incl += y;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            const int excl = incl - n_desc;
+            for (int base = 0; base < total; base += 32) {
+                const int i = min(base + lane, total - 1);
+                int o = 0;  // owner of stretch i: the first lane whose inclusive count exceeds i
+#pragma unroll
+                for (int sft = 16; sft > 0; sft >>= 1) {
+                    const int v = __shfl_sync(0xffffffffu, incl, o + sft - 1);
+                    if (v <= i) o += sft;
+                }
+                const int j = i - __shfl_sync(0xffffffffu, excl, o);
+                const float a_o = __shfl_sync(0xffffffffu, anchor, o);
+                const int ok_o = __shfl_sync(0xffffffffu, m.ok ? 1 : 0, o);
+                const int nd_o = __shfl_sync(0xffffffffu, n_desc, o);
+                if (base + lane < total) {
+                    const int col = tid - lane + o;
+                    float first, after;
+                    uint32_t n;
+                    lat_stretch(L, a_o, ok_o != 0, s_pend[j * T + col], s_open[j * T + col], first, n, after);
+                    s_pend[j * T + col] = first;
+                    s_open[j * T + col] = __uint_as_float(n);
+                    if (j == nd_o - 1) s_tail[col] = after;
+                }
+            }
+            __syncwarp();
+#if NFA_POOL_ONE_ATOMIC
+            // back to one lane per ray: count the ray's runs (stretches that hold a sample), take the pool slots of the
+            // whole warp with ONE atomic (its round trip to L2 per stretch index was a fifth of this phase), then
+            // add up the offsets and write the records -- plain per-lane loops, no warp-wide step inside
+            uint32_t mine = 0;
+            {
+                bool still_ok = m.ok;
+                for (int j = 0; j < n_desc; ++j) {
+                    const uint32_t n = __float_as_uint(s_open[j * T + tid]);
+                    if (n == kStretchFailed) still_ok = false;
+                    mine += (still_ok && n != 0u) ? 1u : 0u;
+                }
+            }
+            uint32_t upto = mine;
+#pragma unroll
+            for (int sft = 1; sft < 32; sft <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, upto, sft);
+                if (lane >= sft) upto += y;
+            }
+            const uint32_t all = __shfl_sync(0xffffffffu, upto, 31);
+            if (all != 0u) {
+                uint32_t slot = 0;
+                if (lane == 0) slot = atomicAdd(p.ws.cursor, all);
+                slot = __shfl_sync(0xffffffffu, slot, 0) + upto - mine;
+                for (int j = 0; j < n_desc; ++j) {
+                    RunOut out;
+                    lat_take(m, s_pend[j * T + tid], __float_as_uint(s_open[j * T + tid]), out);
+                    if (out.valid) {
+                        if ((int64_t)slot < p.ws.run_capacity) {
+                            uint4* dst = reinterpret_cast<uint4*>(p.ws.pool + slot);
+                            dst[0] = make_uint4((uint32_t)r, out.sample_off, out.n, __float_as_uint(out.t_first));
+                            dst[1] = make_uint4(out.run_idx, 0u, 0u, 0u);
+                        }
+                        ++slot;
+                    }
+                }
+            } else {
+                for (int j = 0; j < n_desc; ++j) {  // nothing to write; a failed seek still has to be noted
+                    RunOut out;
+                    lat_take(m, s_pend[j * T + tid], __float_as_uint(s_open[j * T + tid]), out);
+                }
+            }
+#else
+            for (int j = 0; j < maxd; ++j) {
+                RunOut out;
+                out.valid = false;
+                if (j < n_desc) lat_take(m, s_pend[j * T + tid], __float_as_uint(s_open[j * T + tid]), out);
+                emit_runs(out, (uint32_t)r, p.ws, lane);
+            }
+#endif
+            if (n_desc > 0 && m.ok) m.t = s_tail[tid];
+        } else {
+            for (int j = 0; j < maxd; ++j) {
+                RunOut out;
+                out.valid = false;
+                if (j < n_desc)
+                    lat_consume(m, s_pend[j * T + tid], s_open[j * T + tid], (buf.joined_mask >> j) & 1u, out);
+                emit_runs(out, (uint32_t)r, p.ws, lane);
+            }
         }
         n_desc = 0;
         buf.joined_mask = 0u;
@@ -738,7 +763,6 @@ struct ExpandParams {
     const int64_t* totals;  // device copy of the march totals ([1] = number of runs)
     float step_size;
     int64_t sample_capacity;
-    int32_t lanes_log2;  // samples-only kernel: lanes per run = 1 << this; 0 = from the mean run length
     const int64_t* sm_packed_info;
     int64_t* ray_indices;
     float* t_starts;
@@ -817,31 +841,18 @@ __global__ void __launch_bounds__(kExpandThreads) expand_runs_kernel(const Expan
     }
 }
 
-// Samples-only expansion with 128-bit stores.  A run is written by a GROUP of 4 / 8 / 16 / 32 lanes: what has to be
-// done once per run and once per binade piece (pool record, the ray's offset, lat_piece with its division) costs a
-// few hundred instructions, against ~25 for a lane's four samples, so with ~110-sample runs a whole warp per run
-// spends 90 % of its issue slots on work every lane repeats.  With 4 or 8 runs per warp that work is shared by
-// 4 or 8 runs per instruction; a group still stores 64 / 128 contiguous bytes per array and instruction.
-// Output is produced in aligned groups of four samples [4g, 4g+3] -- a float4 of starts, a float4 of ends, two
-// longlong2 of ray ids -- and scalar stores where a piece begins or ends inside such a group.  Same values as the
-// scalar kernel.  The group size follows the mean run length (device-side, from the totals).
+// Samples-only expansion with 128-bit stores: a piece (lattice.cuh) of a run is written as an
+// unaligned head (< 4 samples), a body of output groups [4G, 4G+3] -- one lane per group: a float4 of
+// starts, a float4 of ends, two longlong2 of ray ids -- and a tail.  Same values as the scalar kernel.
 __global__ void __launch_bounds__(kExpandThreads) expand_runs_vec_kernel(const ExpandParams p)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * kExpandThreads + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * kExpandThreads) >> 5;
     int64_t n_runs = p.totals[1];
-    int lg = p.lanes_log2;
-    if (lg == 0) {
-        const int64_t mean = n_runs > 0 ? p.totals[0] / n_runs : 0;  // samples per run
-        lg = mean < 64 ? 2 : (mean < 384 ? 3 : (mean < 1536 ? 4 : 5));
-    }
     if (n_runs > p.ws.run_capacity) n_runs = p.ws.run_capacity;
-    const int G = 1 << lg, sub = lane & (G - 1);
-    const int64_t slot0 = (warp0 << (5 - lg)) + (lane >> lg);
-    const int64_t n_slots = n_warps << (5 - lg);
     const Lattice L = lat_make(p.step_size);
-    for (int64_t q = slot0; q < n_runs; q += n_slots) {
+    for (int64_t q = warp0; q < n_runs; q += n_warps) {
         const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.ws.pool + q));
         const long long ray = a.x;
         int64_t off = p.sm_packed_info[2 * ray] + a.y;
@@ -852,33 +863,38 @@ __global__ void __launch_bounds__(kExpandThreads) expand_runs_vec_kernel(const E
             LatPiece pc;
             int64_t c = run_next_piece(L, it, pc);
             if (off + c > p.sample_capacity) c = p.sample_capacity > off ? p.sample_capacity - off : 0;
-            const int64_t end = off + c;
-            const int64_t g_last = (end - 1) >> 2;
-            for (int64_t g = (off >> 2) + sub; g <= g_last; g += G) {
-                const int64_t lo = 4 * g > off ? 4 * g : off;
-                const int64_t hi = 4 * g + 4 < end ? 4 * g + 4 : end;
-                const uint32_t j = (uint32_t)(lo - off);
-                if (hi - lo == 4) {
-                    float4 s4, e4;
-                    s4.x = piece_start(pc, j);     e4.x = f_add(s4.x, L.dt);
-                    s4.y = piece_start(pc, j + 1); e4.y = f_add(s4.y, L.dt);
-                    s4.z = piece_start(pc, j + 2); e4.z = f_add(s4.z, L.dt);
-                    s4.w = piece_start(pc, j + 3); e4.w = f_add(s4.w, L.dt);
-                    reinterpret_cast<float4*>(p.t_starts)[g] = s4;
-                    reinterpret_cast<float4*>(p.t_ends)[g] = e4;
-                    const longlong2 rr = make_longlong2(ray, ray);
-                    reinterpret_cast<longlong2*>(p.ray_indices)[2 * g] = rr;
-                    reinterpret_cast<longlong2*>(p.ray_indices)[2 * g + 1] = rr;
-                } else {
-                    for (int64_t k = lo; k < hi; ++k) {
-                        const float ts = piece_start(pc, (uint32_t)(k - off));
-                        p.ray_indices[k] = ray;
-                        p.t_starts[k] = ts;
-                        p.t_ends[k] = f_add(ts, L.dt);
-                    }
-                }
+            // head: bring `off` to a multiple of 4 (also covers short pieces entirely)
+            const int head = (int)min((int64_t)((4 - (off & 3)) & 3), c);
+            const int64_t body_groups = (c - head) >> 2;
+            const int tail = (int)(c - head - 4 * body_groups);
+            if (lane < head) {
+                const float ts = piece_start(pc, (uint32_t)lane);
+                p.ray_indices[off + lane] = ray;
+                p.t_starts[off + lane] = ts;
+                p.t_ends[off + lane] = f_add(ts, L.dt);
             }
-            off = end;
+            const int64_t g0 = (off + head) >> 2;
+            for (int64_t gi = lane; gi < body_groups; gi += 32) {
+                const uint32_t j = (uint32_t)(head + 4 * gi);
+                float4 s4, e4;
+                s4.x = piece_start(pc, j);     e4.x = f_add(s4.x, L.dt);
+                s4.y = piece_start(pc, j + 1); e4.y = f_add(s4.y, L.dt);
+                s4.z = piece_start(pc, j + 2); e4.z = f_add(s4.z, L.dt);
+                s4.w = piece_start(pc, j + 3); e4.w = f_add(s4.w, L.dt);
+                reinterpret_cast<float4*>(p.t_starts)[g0 + gi] = s4;
+                reinterpret_cast<float4*>(p.t_ends)[g0 + gi] = e4;
+                const longlong2 rr = make_longlong2(ray, ray);
+                reinterpret_cast<longlong2*>(p.ray_indices)[2 * (g0 + gi)] = rr;
+                reinterpret_cast<longlong2*>(p.ray_indices)[2 * (g0 + gi) + 1] = rr;
+            }
+            if (lane < tail) {
+                const int64_t k = off + head + 4 * body_groups + lane;
+                const float ts = piece_start(pc, (uint32_t)(head + 4 * body_groups + lane));
+                p.ray_indices[k] = ray;
+                p.t_starts[k] = ts;
+                p.t_ends[k] = f_add(ts, L.dt);
+            }
+            off += c;
         }
     }
 }
@@ -1157,44 +1173,59 @@ int32_t nfa_march(int32_t n_rays, const float* rays_o, const float* rays_d, cons
         return e ? atoi(e) : 2;
     }();
     p.brick_steps = brick_steps;
-    // split the tile's longest rays only where the kernel is latency-bound (one wave: every ray resident at once) and
-    // the walk is confined to the occupied box (single level, no terminate plane, bounds known)
-    static const int split_cfg = [] {
-        const char* e = getenv("NFA_MARCH_SPLIT");
-        return e ? atoi(e) : 0;  // off: measured no gain (profiles/r2_experiments.md)
-    }();
-    p.split_rays = 0;
     p.trace = g_march_trace;
+    p.lat_table.n = 0;
+    p.lat_table.e0 = 0;
+    if (near_planes == nullptr && step_size > 0.f) {  // the climb from the near plane, once per (step, near plane)
+        static thread_local LatTable cached;
+        static thread_local float cached_dt = 0.f, cached_near = 0.f;
+        static thread_local bool cached_valid = false;
+        if (!cached_valid || cached_dt != step_size || cached_near != near_plane) {
+            lat_table_build(lat_make(step_size), near_plane, cached);
+            cached_dt = step_size;
+            cached_near = near_plane;
+            cached_valid = true;
+        }
+        p.lat_table = cached;
+    }
     p.ws = ws_view(workspace, n_rays, run_capacity);
     p.totals = totals;
     p.totals_host = totals_host;
     p.terminate = terminate_planes;
     const int tiles = p.ws.n_tiles, tile_rays = p.ws.tile_rays;
-    if (!have_sorted && terminate_planes == nullptr && bounds != nullptr && split_cfg > 0 && split_cfg % 32 == 0 &&
-        (int64_t)n_rays <= (int64_t)148 * 2048 && tile_rays >= 128 && tile_rays % 32 == 0 && split_cfg <= tile_rays / 2 &&
-        tile_rays + split_cfg <= kMaxTileRays)
-        p.split_rays = split_cfg;
-    const int threads = tile_rays + p.split_rays;
+    const int threads = tile_rays;
     const size_t coarse_bytes = (size_t)p.coarse_words * 4;
     // keep the class mip in shared memory while it leaves room for the tile's own buffers (256^3: 64 KiB)
     const bool smem_coarse = NFA_BRICK_STEPS && coarse_bytes <= 128 * 1024;  // only the brick loop reads the mip
-    const size_t dyn = march_smem_bytes(threads, smem_coarse ? coarse_bytes : 0);
-#define NFA_LAUNCH_MARCH(S, C)                                                                          \
+    // one wave (every tile resident at once, at most two per SM): room for twice the descriptor slots
+    static const int slots_cfg = [] {  // measurement aid: NFA_MARCH_SLOTS=8|16 pins it
+        const char* e = getenv("NFA_MARCH_SLOTS");
+        return e ? atoi(e) : 0;
+    }();
+    const bool wide = slots_cfg ? slots_cfg == kDescSlotsWide : (tiles <= 2 * 148 && threads >= 224);
+    const size_t dyn = march_smem_bytes(threads, smem_coarse ? coarse_bytes : 0, wide ? kDescSlotsWide : kDescSlots);
+#define NFA_LAUNCH_MARCH(S, C, W)                                                                       \
     do {                                                                                                \
         static bool raised[64] = {}; /* once per instantiation and device: above the 48 KiB default */  \
         int dev_ = 0;                                                                                   \
         cudaGetDevice(&dev_);                                                                           \
         if (dyn > 40 * 1024 && !raised[dev_ & 63]) {                                                    \
-            cudaFuncSetAttribute(march_kernel<S, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+            cudaFuncSetAttribute(march_kernel<S, C, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
             raised[dev_ & 63] = true;                                                                   \
         }                                                                                               \
-        march_kernel<S, C><<<tiles, threads, dyn, s>>>(p);                                              \
+        march_kernel<S, C, W><<<tiles, threads, dyn, s>>>(p);                                           \
+    } while (0)
+#define NFA_LAUNCH_MARCH_SC(S, C)                                                  \
+    do {                                                                           \
+        if (wide) NFA_LAUNCH_MARCH(S, C, kDescSlotsWide);                          \
+        else NFA_LAUNCH_MARCH(S, C, kDescSlots);                                   \
     } while (0)
     if (!have_sorted) {
-        if (smem_coarse) NFA_LAUNCH_MARCH(true, true); else NFA_LAUNCH_MARCH(true, false);
+        if (smem_coarse) NFA_LAUNCH_MARCH_SC(true, NFA_BRICK_STEPS != 0); else NFA_LAUNCH_MARCH_SC(true, false);
     } else {
-        if (smem_coarse) NFA_LAUNCH_MARCH(false, true); else NFA_LAUNCH_MARCH(false, false);
+        if (smem_coarse) NFA_LAUNCH_MARCH_SC(false, NFA_BRICK_STEPS != 0); else NFA_LAUNCH_MARCH_SC(false, false);
     }
+#undef NFA_LAUNCH_MARCH_SC
 #undef NFA_LAUNCH_MARCH
     return launch_status();
 }
@@ -1228,12 +1259,6 @@ int32_t nfa_expand_samples(int32_t n_rays, int64_t run_capacity, const void* wor
         p.ray_indices = ray_indices;
         p.t_starts = t_starts;
         p.t_ends = t_ends;
-        static const int lanes_log2 = [] {  // measurement aid: NFA_EXPAND_LANES=4|8|16|32 pins the lanes per run
-            const char* e = getenv("NFA_EXPAND_LANES");
-            const int v = e ? atoi(e) : 0;
-            return v == 4 ? 2 : (v == 8 ? 3 : (v == 16 ? 4 : (v == 32 ? 5 : 0)));
-        }();
-        p.lanes_log2 = lanes_log2;
         const uintptr_t al = (uintptr_t)ray_indices | (uintptr_t)t_starts | (uintptr_t)t_ends;
         if ((al & 15u) == 0) expand_runs_vec_kernel<<<expand_grid(run_capacity), kExpandThreads, 0, s>>>(p);
         else expand_runs_kernel<false><<<expand_grid(run_capacity), kExpandThreads, 0, s>>>(p);

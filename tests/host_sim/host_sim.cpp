@@ -54,6 +54,22 @@ int sim_seek(float t0, float dt, float target, float* t_out, uint32_t* k_out)
     return ok ? 1 : 0;
 }
 
+// first lattice point with t + dt/2 >= target, from `near`: plainly, and through the binade table (lattice.cuh)
+int sim_seek_with_table(float dt, float near, float target, float* t_plain, float* t_table)
+{
+    const Lattice L = lat_make(dt);
+    LatTable T;
+    lat_table_build(L, near, T);
+    float a = near, b = near;
+    uint32_t ka = 0, kb = 0;
+    const bool oka = lat_seek(L, a, target, ka);
+    lat_table_jump(T, target, b);
+    const bool okb = lat_seek(L, b, target, kb);
+    *t_plain = a;
+    *t_table = b;
+    return (oka ? 1 : 0) | (okb ? 2 : 0) | (T.n << 2);
+}
+
 // expand one run into starts/ends
 void sim_expand_run(float t_first, float dt, uint32_t n, float* starts, float* ends)
 {
@@ -102,6 +118,8 @@ void sim_occ_pack(int n_grids, int rx, int ry, int rz, const uint8_t* binaries, 
 
 }  // extern "C"
 
+static long g_by_stretch_rounds, g_tables;
+
 // descriptor buffer with the same capacity as the device kernel's per-ray slots
 struct HostBuf {
     enum { K = 8 };
@@ -136,62 +154,66 @@ static float march_one(const Boxes& boxes, const OccView& occ, const float* o, c
     return term;
 }
 
-// A ray walked by two "threads" (first / second half of the occupied box) whose stretch lists are joined the way
-// march_kernel joins them (csrc/traverse.cu); returns false where the kernel would fall back to one thread.
-struct BigBuf {
-    enum { K = 8 };  // the kernel's buffer: a half that needs more falls back
-    float pend[K], open[K];
-    bool joined[K];
-    void put(int j, float p, float o, bool jn) { pend[j] = p; open[j] = o; joined[j] = jn; }
-};
-
-static bool march_one_split(const OccView& occ, const float* box, const float* o, const float* d, float near, float far,
-                            const Lattice& L, LatState& m, std::vector<float>& vt, std::vector<uint32_t>& vn)
+// The kernel's phase 2 for one grid level: a round's stretches handled independently from one anchor
+// (march.cuh: lat_anchor / lat_stretch / lat_take), the way march_kernel deals them out to the lanes of a warp.
+static float march_one_by_stretch(const OccView& occ, const float* box, const float* o, const float* d, float near,
+                                  float far, const Lattice& L, LatState& m, std::vector<float>& vt,
+                                  std::vector<uint32_t>& vn)
 {
     SingleBox boxes{box};
-    Walk wa, wb;
-    BigBuf ba, bb;
-    int na = 0, nb = 0;
-    walk_init(wa, o, d, near, far);
-    walk_init(wb, o, d, near, far);
-    wa.accel = wb.accel = 1;
-    wa.split_half = 1;
-    wb.split_half = 2;
-    walk_run(wa, boxes, occ, ba, na, BigBuf::K);
-    walk_run(wb, boxes, occ, bb, nb, BigBuf::K);
-    const bool fin = wa.done && wa.split_ok && wb.done && wb.split_ok;
-    const bool b_starts_occ = nb > 0 && bb.pend[0] == wb.seg_lo;
-    const bool merge = wa.open != 0 && na > 0;
-    if (!fin || merge != b_starts_occ) return false;
+    Walk w;
+    walk_init(w, o, d, near, far);
+    w.accel = 1;
     lat_init(m, L, near);
+    LatTable table;  // (the kernel gets it from the host, for a uniform near plane; here every ray builds its own)
+    lat_table_build(L, near, table);
+    if (table.n > 0) ++g_tables;
+    HostBuf buf;
+    int n_desc = 0;
     RunOut out;
-    const int total = na + nb - (merge ? 1 : 0);
-    for (int j = 0; j < total; ++j) {
-        float pd, op;
-        bool jn;
-        if (j < na) {
-            pd = ba.pend[j]; op = ba.open[j]; jn = ba.joined[j];
-            if (merge && j == na - 1) op = bb.open[0];
+    for (long guard = 0; guard < (1L << 26); ++guard) {
+        walk_run(w, boxes, occ, buf, n_desc, HostBuf::K);
+        bool any_joined = false;
+        for (int j = 0; j < n_desc; ++j) any_joined = any_joined || buf.joined[j];
+        if (any_joined) {
+            for (int j = 0; j < n_desc; ++j) {
+                lat_consume(m, buf.pend[j], buf.open[j], buf.joined[j], out);
+                if (out.valid) { vt.push_back(out.t_first); vn.push_back(out.n); }
+            }
         } else {
-            const int jb = j - na + (merge ? 1 : 0);
-            pd = bb.pend[jb]; op = bb.open[jb]; jn = bb.joined[jb];
+            ++g_by_stretch_rounds;
+            if (m.run_n > 0) {
+                lat_close(m, out);
+                if (out.valid) { vt.push_back(out.t_first); vn.push_back(out.n); }
+            }
+            if (n_desc > 0) lat_anchor(m, table, buf.pend[0]);
+            const float anchor = m.t;
+            const bool ok = m.ok;
+            float first[HostBuf::K], after[HostBuf::K];
+            uint32_t cnt[HostBuf::K];
+            for (int j = n_desc - 1; j >= 0; --j)  // any order: here the last one first
+                lat_stretch(L, anchor, ok, buf.pend[j], buf.open[j], first[j], cnt[j], after[j]);
+            for (int j = 0; j < n_desc; ++j) {
+                lat_take(m, first[j], cnt[j], out);
+                if (out.valid) { vt.push_back(out.t_first); vn.push_back(out.n); }
+            }
+            if (n_desc > 0 && m.ok) m.t = after[n_desc - 1];
         }
-        lat_consume(m, pd, op, jn, out);
-        if (out.valid) { vt.push_back(out.t_first); vn.push_back(out.n); }
+        n_desc = 0;
+        if (w.done) break;
     }
-    lat_finish(m, -INFINITY, false, out);
+    const float term = lat_finish(m, walk_tail_pend(w), false, out);
     if (out.valid) { vt.push_back(out.t_first); vn.push_back(out.n); }
-    return true;
+    return term;
 }
-
-static long g_split_taken, g_split_fallback;
 
 extern "C" {
 
-void sim_split_counts(long* out, int reset)
+void sim_by_stretch_counts(long* out, int reset)
 {
-    out[0] = g_split_taken; out[1] = g_split_fallback;
-    if (reset) g_split_taken = g_split_fallback = 0;
+    out[0] = g_by_stretch_rounds;
+    out[1] = g_tables;
+    if (reset) g_by_stretch_rounds = g_tables = 0;
 }
 
 // March all rays; per ray: n_samples, n_runs, terminate plane; runs appended to
@@ -219,17 +241,9 @@ int64_t sim_march(int32_t n_rays, const float* rays_o, const float* rays_d,
         vn.clear();
         LatState m;
         float term;
-        if (t_sorted == nullptr && accel == 2) {  // accel == 2: every ray split between two walkers, as the kernel's
-            term = 0.f;                           // longest rays are; where that is not possible, one walker
-            if (march_one_split(occ, aabbs, rays_o + 3 * r, rays_d + 3 * r, near_planes[r], far_planes[r], L, m, vt, vn)) {
-                ++g_split_taken;
-            } else {
-                ++g_split_fallback;
-                vt.clear();
-                vn.clear();
-                SingleBox b{aabbs};
-                term = march_one(b, occ, rays_o + 3 * r, rays_d + 3 * r, near_planes[r], far_planes[r], L, m, vt, vn, 1);
-            }
+        if (t_sorted == nullptr && accel == 2) {  // accel == 2: phase 2 by stretch, as march_kernel does it for one level
+            term = march_one_by_stretch(occ, aabbs, rays_o + 3 * r, rays_d + 3 * r, near_planes[r], far_planes[r], L, m, vt,
+                                        vn);
         } else if (t_sorted == nullptr) {
             SingleBox b{aabbs};
             term = march_one(b, occ, rays_o + 3 * r, rays_d + 3 * r, near_planes[r], far_planes[r], L, m, vt, vn,

@@ -319,12 +319,44 @@ def test_brick_loop_variant_is_bit_exact_and_actually_skips(host_sim_brick, orc)
     _compare(sim, orc, ro2, rd2, full, a4[:1], rng.random(200).astype(np.float32), (1 + rng.random(200) * 3).astype(np.float32), 1e-2)
 
 
-# ---------------------------------------------------------------- two walkers per ray (the kernel's longest rays)
+def test_binade_table_seek_is_the_plain_seek(host_sim):
+    """The march kernel starts a ray's first seek from a host-built table of lattice points at the binade starts
+    (lattice.cuh: LatTable).  The point it arrives at must be the one the plain climb from `near` arrives at."""
+    import ctypes as C
+    sim = host_sim
+    sim.sim_seek_with_table.argtypes = [C.c_float, C.c_float, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    sim.sim_seek_with_table.restype = C.c_int
+    rng = np.random.default_rng(5)
+    a, b = C.c_float(), C.c_float()
+    used = 0
+    for _ in range(4000):
+        dt = np.float32(10.0 ** rng.uniform(-4, 0.5))
+        near = np.float32(0.0 if rng.random() < 0.5 else 10.0 ** rng.uniform(-3, 1))
+        kind = rng.random()
+        if kind < 0.6:
+            target = np.float32(near + dt * rng.uniform(0, 3000))
+        elif kind < 0.8:   # exactly at / next to a power of two
+            e = int(rng.integers(-6, 8))
+            target = np.nextafter(np.float32(2.0 ** e), np.float32(rng.choice([-1e9, 1e9]))) if rng.random() < 0.7 else np.float32(2.0 ** e)
+        else:
+            target = np.float32(10.0 ** rng.uniform(-5, 3))
+        if target / dt > 3e5:
+            continue   # keeps the plain climb short
+        r = sim.sim_seek_with_table(dt, near, target, C.byref(a), C.byref(b))
+        assert (r & 1) == ((r >> 1) & 1)
+        if r & 1:
+            assert np.float32(a.value).tobytes() == np.float32(b.value).tobytes(), (dt, near, target, a.value, b.value)
+        used += (r >> 2) > 0
+    assert used > 1000
 
-def test_split_rays_join_exactly(host_sim, orc):
-    """march_kernel gives the longest rays of a tile two threads: one walks the occupied box up to its middle, the
-    other from there, and the stretch lists are joined at the cell both walk.  Here EVERY ray is split (accel=2 in
-    the simulation) and the result must still be the oracle's, bit for bit; rays that cannot be split fall back."""
+
+# ---------------------------------------------------------------- phase 2 by stretch (one level)
+
+def test_lattice_by_stretch_matches(host_sim, orc):
+    """march_kernel deals the stretches of a warp's rays out to the lanes: each is turned into its run from the ray's
+    anchor, independently of the ray's other stretches (march.cuh: lat_anchor / lat_stretch / lat_take).  accel=2 in
+    the simulation takes that path (last stretch first) and the result must be the oracle's, bit for bit -- also over
+    several buffer rounds, with per-ray near planes, and at step sizes where stretches hold no sample at all."""
     import ctypes as C
     sim = host_sim
     rng = np.random.default_rng(17)
@@ -333,17 +365,18 @@ def test_split_rays_join_exactly(host_sim, orc):
     bins, aabbs = scenes.ball_grid(128), scenes.nested_aabbs(1)
     near, far = np.zeros(R, np.float32), np.full(R, 1e10, np.float32)
     cnt = (C.c_long * 2)()
-    sim.sim_split_counts(cnt, 1)
+    sim.sim_by_stretch_counts(cnt, 1)
     _compare(sim, orc, ro, rd, bins, aabbs, near, far, scenes.BALL_STEP, accel=2)
-    sim.sim_split_counts(cnt, 1)
-    assert cnt[0] > 0.95 * R                      # nearly every ray of the ball scene really is split
+    sim.sim_by_stretch_counts(cnt, 1)
+    assert cnt[0] >= R and cnt[1] == R        # every ray took the by-stretch path, with a binade table
     _compare(sim, orc, ro, rd, bins, aabbs, (rng.random(R) * scenes.BALL_STEP).astype(np.float32), far, scenes.BALL_STEP, accel=2)
-    frag = bins & (rng.random(bins.shape) > 0.5)  # many stretches: the 8-slot buffers overflow -> fall back
+    frag = bins & (rng.random(bins.shape) > 0.5)  # many stretches: several rounds of the 8-slot buffer
     _compare(sim, orc, ro[:512], rd[:512], frag, aabbs, near[:512], far[:512], scenes.BALL_STEP, accel=2)
+    _compare(sim, orc, ro[:512], rd[:512], frag, aabbs, near[:512], far[:512], 0.05, accel=2)   # step > cell: empty runs
+    _compare(sim, orc, ro[:512], rd[:512], frag, aabbs, near[:512], far[:512], 0.3, accel=2)
     frag2 = bins & (rng.random(bins.shape) > 0.03)
     _compare(sim, orc, ro[:1024], rd[:1024], frag2, aabbs, near[:1024], far[:1024], scenes.BALL_STEP, accel=2)
-    sim.sim_split_counts(cnt, 1)
-    assert cnt[0] > 0 and cnt[1] > 0
+    _compare(sim, orc, ro[:1024], rd[:1024], frag2, aabbs, near[:1024], far[:1024], 7e-4, accel=2)
     off_centre = np.zeros((1, 128, 128, 128), bool)
     off_centre[0, 90:120, 5:9, 60:61] = True
     off_centre[0, 97, 100, 3] = True
