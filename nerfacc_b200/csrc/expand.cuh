@@ -19,10 +19,18 @@ struct RunIter {
 // start at piece_start(p, j) and end at start + dt (a real add).
 NFA_HD uint32_t run_next_piece(const Lattice& L, RunIter& it, LatPiece& p)
 {
-    p = lat_piece(L, it.t);
-    uint32_t c = 1u;
-    if (p.regular) c = it.left < p.jmax + 1u ? it.left : p.jmax + 1u;
-    const float last = lat_point(p, c - 1u);  // inc == 0 when irregular, so this is t
+    uint32_t M, c = 1u;
+    if (lat_piece_step(L, it.t, p, M)) {
+        const uint32_t room = 0xffffffu - M;
+        if ((uint64_t)(it.left - 1u) * p.inc <= room) {
+            c = it.left;  // the rest of the run lies inside this binade: no need for the piece's length
+        } else {
+            p.jmax = div_u24(room, p.inc);  // < it.left - 1
+            p.regular = p.jmax > 0u;
+            c = p.jmax + 1u;
+        }
+    }
+    const float last = lat_point(p, c - 1u);  // c == 1 when there is no closed form: this is t
     it.t = f_add(last, L.dt);
     it.left -= c;
     return c;

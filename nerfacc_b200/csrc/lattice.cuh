@@ -81,9 +81,10 @@ NFA_HD float div_estimate(float a, float b)
 #endif
 }
 
-NFA_HD LatPiece lat_piece(const Lattice& L, float t)
+// The piece at t without its length: fills base / inc / stuck and returns true when the per-step increment is
+// known (then M is t's 24-bit significand and the piece has floor((0xffffff - M) / inc) further points).
+NFA_HD bool lat_piece_step(const Lattice& L, float t, LatPiece& p, uint32_t& M)
 {
-    LatPiece p;
     const uint32_t b = f_bits(t);
     p.base = b;
     p.inc = 0;
@@ -91,15 +92,15 @@ NFA_HD LatPiece lat_piece(const Lattice& L, float t)
     p.regular = false;
     p.stuck = false;
     const uint32_t e = b >> 23;  // includes the sign bit: negative t => e >= 256
-    if (e == 0u || e >= 255u || e < L.ed || L.ed == 0u || L.ed == 255u) return p;
+    if (e == 0u || e >= 255u || e < L.ed || L.ed == 0u || L.ed == 255u) return false;
     const uint32_t s = e - L.ed;
-    const uint32_t M = (b & 0x7fffffu) | 0x800000u;
+    M = (b & 0x7fffffu) | 0x800000u;
     uint32_t I;
     if (s == 0u) {
         I = L.md;
     } else if (s > 24u) {
         p.stuck = true;
-        return p;
+        return false;
     } else {
         const uint32_t q = L.md >> s;
         const uint32_t rem = L.md & ((1u << s) - 1u);
@@ -109,17 +110,26 @@ NFA_HD LatPiece lat_piece(const Lattice& L, float t)
         else {
             // exact tie: round-half-even.  Once M is even it stays even and the
             // increment is the even one of {q, q+1}; with M odd take a real step.
-            if (M & 1u) return p;
+            if (M & 1u) return false;
             I = q + (q & 1u);
         }
         if (I == 0u) {
             p.stuck = true;
-            return p;
+            return false;
         }
     }
     p.inc = I;
-    p.jmax = div_u24(0xffffffu - M, I);
-    p.regular = p.jmax > 0u;
+    return true;
+}
+
+NFA_HD LatPiece lat_piece(const Lattice& L, float t)
+{
+    LatPiece p;
+    uint32_t M;
+    if (lat_piece_step(L, t, p, M)) {
+        p.jmax = div_u24(0xffffffu - M, p.inc);
+        p.regular = p.jmax > 0u;
+    }
     return p;
 }
 

@@ -844,8 +844,10 @@ __global__ void __launch_bounds__(kExpandThreads) expand_runs_kernel(const Expan
 // Samples-only expansion with 128-bit stores: a piece (lattice.cuh) of a run is written as an
 // unaligned head (< 4 samples), a body of output groups [4G, 4G+3] -- one lane per group: a float4 of
 // starts, a float4 of ends, two longlong2 of ray ids -- and a tail.  Same values as the scalar kernel.
+// (32-bit sample offsets and one division less per run were measured: no change -- the store stream bounds it.)
 __global__ void __launch_bounds__(kExpandThreads) expand_runs_vec_kernel(const ExpandParams p)
 {
+    using Idx = int64_t;
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * kExpandThreads + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * kExpandThreads) >> 5;
@@ -855,17 +857,19 @@ __global__ void __launch_bounds__(kExpandThreads) expand_runs_vec_kernel(const E
     for (int64_t q = warp0; q < n_runs; q += n_warps) {
         const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.ws.pool + q));
         const long long ray = a.x;
-        int64_t off = p.sm_packed_info[2 * ray] + a.y;
+        const int64_t off64 = p.sm_packed_info[2 * ray] + a.y;
         RunIter it;
         it.t = __uint_as_float(a.w);
         it.left = a.z;
+        if (off64 >= p.sample_capacity) it.left = 0;
+        else if (off64 + it.left > p.sample_capacity) it.left = (uint32_t)(p.sample_capacity - off64);
+        Idx off = (Idx)off64;
         while (it.left > 0) {
             LatPiece pc;
-            int64_t c = run_next_piece(L, it, pc);
-            if (off + c > p.sample_capacity) c = p.sample_capacity > off ? p.sample_capacity - off : 0;
+            const Idx c = (Idx)run_next_piece(L, it, pc);
             // head: bring `off` to a multiple of 4 (also covers short pieces entirely)
-            const int head = (int)min((int64_t)((4 - (off & 3)) & 3), c);
-            const int64_t body_groups = (c - head) >> 2;
+            const int head = (int)min((Idx)((4 - (off & 3)) & 3), c);
+            const Idx body_groups = (c - head) >> 2;
             const int tail = (int)(c - head - 4 * body_groups);
             if (lane < head) {
                 const float ts = piece_start(pc, (uint32_t)lane);
@@ -873,8 +877,8 @@ __global__ void __launch_bounds__(kExpandThreads) expand_runs_vec_kernel(const E
                 p.t_starts[off + lane] = ts;
                 p.t_ends[off + lane] = f_add(ts, L.dt);
             }
-            const int64_t g0 = (off + head) >> 2;
-            for (int64_t gi = lane; gi < body_groups; gi += 32) {
+            const Idx g0 = (off + head) >> 2;
+            for (Idx gi = lane; gi < body_groups; gi += 32) {
                 const uint32_t j = (uint32_t)(head + 4 * gi);
                 float4 s4, e4;
                 s4.x = piece_start(pc, j);     e4.x = f_add(s4.x, L.dt);
@@ -888,7 +892,7 @@ __global__ void __launch_bounds__(kExpandThreads) expand_runs_vec_kernel(const E
                 reinterpret_cast<longlong2*>(p.ray_indices)[2 * (g0 + gi) + 1] = rr;
             }
             if (lane < tail) {
-                const int64_t k = off + head + 4 * body_groups + lane;
+                const Idx k = off + head + 4 * body_groups + lane;
                 const float ts = piece_start(pc, (uint32_t)(head + 4 * body_groups + lane));
                 p.ray_indices[k] = ray;
                 p.t_starts[k] = ts;
@@ -1260,8 +1264,8 @@ int32_t nfa_expand_samples(int32_t n_rays, int64_t run_capacity, const void* wor
         p.t_starts = t_starts;
         p.t_ends = t_ends;
         const uintptr_t al = (uintptr_t)ray_indices | (uintptr_t)t_starts | (uintptr_t)t_ends;
-        if ((al & 15u) == 0) expand_runs_vec_kernel<<<expand_grid(run_capacity), kExpandThreads, 0, s>>>(p);
-        else expand_runs_kernel<false><<<expand_grid(run_capacity), kExpandThreads, 0, s>>>(p);
+        if ((al & 15u) != 0) expand_runs_kernel<false><<<expand_grid(run_capacity), kExpandThreads, 0, s>>>(p);
+        else expand_runs_vec_kernel<<<expand_grid(run_capacity), kExpandThreads, 0, s>>>(p);
     }
     return launch_status();
 }

@@ -7,13 +7,15 @@ import sys
 
 tag = sys.argv[1] if len(sys.argv) > 1 else "r2"
 n_samples = int(sys.argv[2]) if len(sys.argv) > 2 else 8513610
-raw = subprocess.run(["ncu", "-i", f"gpurun_out/{tag}_kernels.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+import os
+rep = f"gpurun_out/{tag}_step_kernels.ncu-rep" if os.path.exists(f"gpurun_out/{tag}_step_kernels.ncu-rep") else f"gpurun_out/{tag}_kernels.ncu-rep"
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units = rows[0], rows[1]
 names = {"march": "march_kernel", "expand": "expand_runs_vec_kernel", "composite_fwd": "composite_fwd_hot_kernel",
          "composite_bwd": "composite_bwd_hot_kernel"}
 scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-out = {"n_samples": n_samples, "source": f"ncu --set full --clock-control none, gpurun_out/{tag}_kernels.ncu-rep (scripts/profile_kernels.py)"}
+out = {"n_samples": n_samples, "source": f"ncu --set full --clock-control none, {rep} (scripts/profile_kernels.py)"}
 for key, kn in names.items():
     for r in rows[2:]:
         d = dict(zip(hdr, r))

@@ -26,7 +26,7 @@ def demangle(n):
 print("# SASS of", so, "(cuobjdump -sass, sm_100a)\n")
 for name, ins in funcs.items():
     d = demangle(name)
-    if not any(k in d for k in ("march_kernel<(bool)1, (bool)0>", "composite_fwd_hot", "composite_bwd_hot", "expand_runs_vec",
+    if not any(k in d for k in ("march_kernel<true, false, 16>", "march_kernel<(bool)1, (bool)0, (int)16>", "composite_fwd_hot", "composite_bwd_hot", "expand_runs_vec",
                                 "occ_threshold_pack", "vis_mask_kernel<(bool)0>")):
         continue
     hist = collections.Counter(re.sub(r"^@!?U?P\d+\s+", "", t).split()[0].split(".")[0] for _, t in ins)

@@ -26,9 +26,19 @@ P("of a step).  Per step: march, offsets, expand, composite fwd, ATen's mse / me
 # 2. full profiles
 import glob
 rr = []
-for rep in sorted(glob.glob(f"gpurun_out/{tag}_kernels*.ncu-rep")):  # config-2 step, then the PDF kernels
+base = lambda name: re.sub(r"[<(].*", "", name).replace("void ", "")
+refreshed = set()
+# the capture of the final kernels of a config-2 step (if the step's kernels changed after the full capture) first:
+# its rows replace the older ones of the same kernels
+reps = sorted(glob.glob(f"gpurun_out/{tag}_step_kernels*.ncu-rep")) + sorted(glob.glob(f"gpurun_out/{tag}_kernels*.ncu-rep"))
+for rep in reps:
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     part = list(csv.reader(raw.splitlines()))
+    ki = part[0].index("Kernel Name")
+    if "_step_kernels" in rep:
+        refreshed |= {base(r[ki]) for r in part[2:]}
+    else:
+        part = part[:2] + [r for r in part[2:] if base(r[ki]) not in refreshed]
     if not rr:
         rr = part
     elif part[0] == rr[0]:
@@ -42,7 +52,8 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__inst_executed.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
         "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "smsp__thread_inst_executed_per_inst_executed.ratio"]
-P(f"\n# {tag}: `ncu --set full --clock-control none` per kernel (one launch each, from scripts/profile_kernels.py)\n")
+P(f"\n# {tag}: `ncu --set full --clock-control none` per kernel (one launch each, from scripts/profile_kernels.py;")
+P("the kernels of the config-2 step -- march, offsets, expand, composite fwd / bwd -- from the capture of the final build)\n")
 seen = set()
 for vals in rr[2:]:
     kn = re.sub(r"\(.*", "", vals[hdr.index("Kernel Name")]).replace("void ", "")
