@@ -22,7 +22,8 @@ for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
 P("\nNotes: the launch list covers the whole bench command -- 5 steps of the value arm (2 timed + 3 warm-up), 2+2 of")
 P("the e2e arm, 5 of the pipelined arm, and the per-kernel roofline timings (11 direct launches of each of the four")
 P("kernels and 11 sampling calls, each preceded by the 256 MB `FillFunctor<unsigned char>` L2 flush, which is not part")
-P("of a step).  Per step: march, offsets, expand, composite fwd, ATen's mse / mean / mse-backward / fill, composite bwd.")
+P("of a step, and 11 `fill_` launches of 136 MB, the write-only reference for expand).  Per step: march, offsets, expand,")
+P("composite fwd, ATen's mse / mean / mse-backward / fill, composite bwd.")
 # 2. full profiles
 import glob
 rr = []
