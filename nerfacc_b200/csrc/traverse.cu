@@ -10,11 +10,12 @@
 //                     tile's rays are ordered by expected walk length so that the lanes
 //                     of a warp finish together.  Phase 1: pure DDA walk recording
 //                     occupied stretches (divergent but cheap); phase 2: closed-form
-//                     lattice seeks, all lanes in step (march.cuh).  Runs go to a pool through a warp-aggregated
-//                     atomic cursor; per-ray counts, per-tile sums and (last CTA) the
-//                     grand totals are written for the offsets pass.
-//   offsets_kernel    1 CTA / 128-ray tile: tile base from the tile sums + block scan
-//                     -> packed_info (ray-ordered offsets, so ray_indices stay sorted).
+//                     lattice seeks, a warp's stretches dealt out to its lanes (march.cuh).  Runs go to a pool
+//                     (one atomic per warp and round); per-ray counts, each ray's sample offset inside its tile,
+//                     per-tile sums and (last CTA) the tile bases + grand totals are left in the workspace.
+//   offsets_kernel    1 CTA / tile: tile base from the tile sums + block scan -> packed_info (ray-ordered
+//                     offsets, so ray_indices stay sorted).  Interval form and the scalar fallback only: the
+//                     vectorised samples kernel writes packed_info itself from (tile base, offset in tile).
 //   expand_runs_vec_kernel / expand_runs_kernel
 //                     one warp per run: lanes compute their samples from the lattice
 //                     closed form (expand.cuh) and store them coalesced, 128-bit stores
@@ -84,7 +85,8 @@ struct RunRec {
     uint32_t n;           // samples in the run
     uint32_t t_first;     // bit pattern of the first sample's start
     uint32_t run_idx;     // runs of the ray before this run (interval edges: +1 edge per run)
-    uint32_t pad[3];
+    uint32_t tile;        // march tile of the ray (its sample offsets are relative to the tile's base)
+    uint32_t pad[2];
 };
 
 struct TileSum {
@@ -97,6 +99,8 @@ struct TileSum {
 //   [0, 64)                 header: u32 done_counter, u32 pool_cursor
 //   tile_sums [n_tiles]     TileSum
 //   cnt_samples [R] u32, cnt_runs [R] u32
+//   loc_samples [R] u32     samples of the earlier rays of the same tile
+//   tile_base [n_tiles] u64 samples of the earlier tiles
 //   pool [run_capacity]     RunRec
 struct Workspace {
     uint32_t* done;
@@ -104,6 +108,8 @@ struct Workspace {
     TileSum* tiles;
     uint32_t* cnt_samples;
     uint32_t* cnt_runs;
+    uint32_t* loc_samples;
+    unsigned long long* tile_base;
     RunRec* pool;
     int n_tiles;
     int tile_rays;
@@ -116,7 +122,7 @@ inline int64_t ws_bytes(int32_t n_rays, int64_t run_capacity)
 {
     const int tile = march_tile_rays(n_rays);
     const int64_t nt = (n_rays + tile - 1) / tile;
-    return 64 + align16(nt * (int64_t)sizeof(TileSum)) + align16((int64_t)n_rays * 4) * 2 +
+    return 64 + align16(nt * (int64_t)sizeof(TileSum)) + align16((int64_t)n_rays * 4) * 3 + align16(nt * 8) +
            run_capacity * (int64_t)sizeof(RunRec);
 }
 
@@ -136,6 +142,10 @@ inline Workspace ws_view(void* base, int32_t n_rays, int64_t run_capacity)
     p += align16((int64_t)n_rays * 4);
     w.cnt_runs = (uint32_t*)p;
     p += align16((int64_t)n_rays * 4);
+    w.loc_samples = (uint32_t*)p;
+    p += align16((int64_t)n_rays * 4);
+    w.tile_base = (unsigned long long*)p;
+    p += align16((int64_t)w.n_tiles * 8);
     w.pool = (RunRec*)p;
     return w;
 }
@@ -265,7 +275,7 @@ struct SmemBuf {
 };
 
 // append the runs the lanes of a warp closed in this step: one atomic per warp
-__device__ __forceinline__ void emit_runs(const RunOut& out, uint32_t ray, const Workspace& ws, int lane)
+__device__ __forceinline__ void emit_runs(const RunOut& out, uint32_t ray, uint32_t tile, const Workspace& ws, int lane)
 {
     const unsigned mask = __ballot_sync(0xffffffffu, out.valid);
     if (mask == 0u) return;
@@ -278,7 +288,7 @@ __device__ __forceinline__ void emit_runs(const RunOut& out, uint32_t ray, const
         if ((int64_t)slot < ws.run_capacity) {
             uint4* dst = reinterpret_cast<uint4*>(ws.pool + slot);
             dst[0] = make_uint4(ray, out.sample_off, out.n, __float_as_uint(out.t_first));
-            dst[1] = make_uint4(out.run_idx, 0u, 0u, 0u);
+            dst[1] = make_uint4(out.run_idx, tile, 0u, 0u);
         }
     }
 }
@@ -296,7 +306,7 @@ __global__ void __launch_bounds__(kMaxTileRays) march_kernel(const MarchParams p
     extern __shared__ __align__(16) uint32_t s_dyn[];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ unsigned long long s_red_samples[kMaxTileRays / 32];
-    __shared__ uint32_t s_red_runs[kMaxTileRays / 32], s_red_flags[kMaxTileRays / 32];
+    __shared__ uint32_t s_red_runs[kMaxTileRays / 32], s_red_flags[kMaxTileRays / 32], s_wsum[kMaxTileRays / 32];
     __shared__ bool s_last;
     __shared__ uint32_t s_hist[kSortBuckets];
 
@@ -474,7 +484,7 @@ __global__ void __launch_bounds__(kMaxTileRays) march_kernel(const MarchParams p
             if (__any_sync(0xffffffffu, m.run_n > 0u)) {  // (only after a round that went the other way)
                 RunOut out;
                 lat_close(m, out);
-                emit_runs(out, (uint32_t)r, p.ws, lane);
+                emit_runs(out, (uint32_t)r, (uint32_t)tile, p.ws, lane);
             }
             if (n_desc > 0) lat_anchor(m, p.lat_table, s_pend[tid]);
             const float anchor = m.t;
@@ -540,7 +550,7 @@ __global__ void __launch_bounds__(kMaxTileRays) march_kernel(const MarchParams p
                         if ((int64_t)slot < p.ws.run_capacity) {
                             uint4* dst = reinterpret_cast<uint4*>(p.ws.pool + slot);
                             dst[0] = make_uint4((uint32_t)r, out.sample_off, out.n, __float_as_uint(out.t_first));
-                            dst[1] = make_uint4(out.run_idx, 0u, 0u, 0u);
+                            dst[1] = make_uint4(out.run_idx, (uint32_t)tile, 0u, 0u);
                         }
                         ++slot;
                     }
@@ -556,7 +566,7 @@ __global__ void __launch_bounds__(kMaxTileRays) march_kernel(const MarchParams p
                 RunOut out;
                 out.valid = false;
                 if (j < n_desc) lat_take(m, s_pend[j * T + tid], __float_as_uint(s_open[j * T + tid]), out);
-                emit_runs(out, (uint32_t)r, p.ws, lane);
+                emit_runs(out, (uint32_t)r, (uint32_t)tile, p.ws, lane);
             }
 #endif
             if (n_desc > 0 && m.ok) m.t = s_tail[tid];
@@ -566,7 +576,7 @@ __global__ void __launch_bounds__(kMaxTileRays) march_kernel(const MarchParams p
                 out.valid = false;
                 if (j < n_desc)
                     lat_consume(m, s_pend[j * T + tid], s_open[j * T + tid], (buf.joined_mask >> j) & 1u, out);
-                emit_runs(out, (uint32_t)r, p.ws, lane);
+                emit_runs(out, (uint32_t)r, (uint32_t)tile, p.ws, lane);
             }
         }
         n_desc = 0;
@@ -578,7 +588,7 @@ __global__ void __launch_bounds__(kMaxTileRays) march_kernel(const MarchParams p
         out.valid = false;
         float term = 0.f;
         if (active) term = lat_finish(m, walk_tail_pend(w), p.terminate != nullptr, out);
-        emit_runs(out, (uint32_t)r, p.ws, lane);
+        emit_runs(out, (uint32_t)r, (uint32_t)tile, p.ws, lane);
         if (active) {
             p.ws.cnt_samples[r] = m.n_samples;
             p.ws.cnt_runs[r] = m.n_runs;
@@ -620,7 +630,26 @@ __global__ void __launch_bounds__(kMaxTileRays) march_kernel(const MarchParams p
         const uint32_t prev = atomicAdd(p.ws.done, 1u);
         s_last = (prev == (uint32_t)(gridDim.x - 1));
     }
+    // Samples of the earlier rays of this tile, in RAY order (the threads hold the rays in sorted order): with the
+    // tile bases below this is every ray's packed_info start, so that no separate offsets pass has to run before the
+    // samples are expanded.  The descriptor buffers are free by now (barrier above): counts go through them.
+    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_pend);
+    if (active) s_cnt[rt] = m.n_samples;
     __syncthreads();
+    {
+        const uint32_t cs = tid < nr ? s_cnt[tid] : 0u;
+        uint32_t xs = cs;
+#pragma unroll
+        for (int sft = 1; sft < 32; sft <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, xs, sft);
+            if (lane >= sft) xs += y;
+        }
+        if (lane == 31) s_wsum[tid >> 5] = xs;
+        __syncthreads();
+        uint32_t before = xs - cs;
+        for (int k = 0; k < (tid >> 5); ++k) before += s_wsum[k];
+        if (tid < nr) p.ws.loc_samples[r0 + tid] = before;
+    }
     if (p.trace && lane == 0) {
         tr_c3 = clock64();  // past the tile's last barrier
         unsigned long long t1;
@@ -633,27 +662,44 @@ __global__ void __launch_bounds__(kMaxTileRays) march_kernel(const MarchParams p
     }
     if (s_last) {
         __threadfence();
+        // tile bases (exclusive scan of the tile sums: a contiguous chunk of tiles per thread) and the grand totals
+        const int n_tiles = p.ws.n_tiles;
+        const int chunk = (n_tiles + T - 1) / T;
+        const int i0 = min(tid * chunk, n_tiles), i1 = min(i0 + chunk, n_tiles);
         unsigned long long a = 0, b = 0, c = 0;
-        for (int i = tid; i < p.ws.n_tiles; i += T) {
+        for (int i = i0; i < i1; ++i) {
             const volatile unsigned long long* q = (const volatile unsigned long long*)&p.ws.tiles[i];
             const unsigned long long w0 = q[0], w1 = q[1];  // {samples}, {runs | stuck << 32}
             a += w0;
             b += (uint32_t)w1;
             c += w1 >> 32;
         }
+        unsigned long long xa = a;
+#pragma unroll
+        for (int sft = 1; sft < 32; sft <<= 1) {
+            const unsigned long long y = __shfl_up_sync(0xffffffffu, xa, sft);
+            if (lane >= sft) xa += y;
+        }
 #pragma unroll
         for (int sft = 16; sft > 0; sft >>= 1) {
-            a += __shfl_xor_sync(0xffffffffu, a, sft);
             b += __shfl_xor_sync(0xffffffffu, b, sft);
             c += __shfl_xor_sync(0xffffffffu, c, sft);
         }
         __shared__ unsigned long long s_tot[3][kMaxTileRays / 32];
+        if (lane == 31) s_tot[0][tid >> 5] = xa;
         if (lane == 0) {
-            s_tot[0][tid >> 5] = a;
             s_tot[1][tid >> 5] = b;
             s_tot[2][tid >> 5] = c;
         }
         __syncthreads();
+        {
+            unsigned long long base = xa - a;
+            for (int k = 0; k < (tid >> 5); ++k) base += s_tot[0][k];
+            for (int i = i0; i < i1; ++i) {
+                p.ws.tile_base[i] = base;
+                base += *(const volatile unsigned long long*)&p.ws.tiles[i];
+            }
+        }
         if (tid < 3) {
             unsigned long long v = 0;
             for (int k = 0; k < n_warps; ++k) v += s_tot[tid][k];
@@ -760,10 +806,12 @@ __global__ void __launch_bounds__(kMaxTileRays) offsets_kernel(int32_t n_rays, W
 // ---------------------------------------------------------------------------
 struct ExpandParams {
     Workspace ws;
+    int32_t n_rays;
     const int64_t* totals;  // device copy of the march totals ([1] = number of runs)
     float step_size;
     int64_t sample_capacity;
     const int64_t* sm_packed_info;
+    int64_t* packed_out;  // samples-only vectorised kernel: packed_info is written here, not read
     int64_t* ray_indices;
     float* t_starts;
     float* t_ends;
@@ -854,10 +902,21 @@ __global__ void __launch_bounds__(kExpandThreads) expand_runs_vec_kernel(const E
     int64_t n_runs = p.totals[1];
     if (n_runs > p.ws.run_capacity) n_runs = p.ws.run_capacity;
     const Lattice L = lat_make(p.step_size);
+    // packed_info of every ray = [base of the ray's march tile + samples of the tile's earlier rays, count]: the march
+    // kernel left both parts in the workspace, so no offsets pass runs in front of this kernel.  The runs below take
+    // their offsets from the same two arrays, not from packed_info (another CTA may not have written it yet).
+    for (int64_t r = (int64_t)blockIdx.x * kExpandThreads + threadIdx.x; r < p.n_rays;
+         r += (int64_t)gridDim.x * kExpandThreads) {
+        longlong2 v;
+        v.x = (long long)(p.ws.tile_base[r / p.ws.tile_rays] + p.ws.loc_samples[r]);
+        v.y = (long long)p.ws.cnt_samples[r];
+        *reinterpret_cast<longlong2*>(p.packed_out + 2 * r) = v;
+    }
     for (int64_t q = warp0; q < n_runs; q += n_warps) {
         const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.ws.pool + q));
+        const uint32_t run_tile = __ldg(&p.ws.pool[q].tile);
         const long long ray = a.x;
-        const int64_t off64 = p.sm_packed_info[2 * ray] + a.y;
+        const int64_t off64 = (int64_t)(p.ws.tile_base[run_tile] + p.ws.loc_samples[ray]) + a.y;
         RunIter it;
         it.t = __uint_as_float(a.w);
         it.left = a.z;
@@ -1252,18 +1311,23 @@ int32_t nfa_expand_samples(int32_t n_rays, int64_t run_capacity, const void* wor
     if ((((uintptr_t)packed_info) & 15u) != 0) return NFA_ERR_ARG;
     const Workspace ws = ws_view(const_cast<void*>(workspace), n_rays, run_capacity);
     cudaStream_t s = (cudaStream_t)stream;
-    offsets_kernel<false><<<ws.n_tiles, ws.tile_rays, 0, s>>>(n_rays, ws, packed_info, nullptr);
-    if (capacity > 0 && run_capacity > 0) {
+    const uintptr_t al = (uintptr_t)ray_indices | (uintptr_t)t_starts | (uintptr_t)t_ends;
+    const bool expand = capacity > 0 && run_capacity > 0;
+    // the vectorised kernel writes packed_info itself (from what the march left in the workspace); the offsets pass
+    // only runs in front of the scalar fallback (unaligned outputs) or when there is nothing to expand
+    if (!expand || (al & 15u) != 0) offsets_kernel<false><<<ws.n_tiles, ws.tile_rays, 0, s>>>(n_rays, ws, packed_info, nullptr);
+    if (expand) {
         ExpandParams p = {};
         p.ws = ws;
+        p.n_rays = n_rays;
         p.totals = totals;
         p.step_size = step_size;
         p.sample_capacity = capacity;
         p.sm_packed_info = packed_info;
+        p.packed_out = packed_info;
         p.ray_indices = ray_indices;
         p.t_starts = t_starts;
         p.t_ends = t_ends;
-        const uintptr_t al = (uintptr_t)ray_indices | (uintptr_t)t_starts | (uintptr_t)t_ends;
         if ((al & 15u) != 0) expand_runs_kernel<false><<<expand_grid(run_capacity), kExpandThreads, 0, s>>>(p);
         else expand_runs_vec_kernel<<<expand_grid(run_capacity), kExpandThreads, 0, s>>>(p);
     }
