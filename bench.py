@@ -605,7 +605,7 @@ def main():
         def k_march(_):
             job._launch_march()
 
-        def k_expand(_):  # offsets + expand
+        def k_expand(_):  # expand (writes packed_info as well: no separate offsets pass on this route)
             job._expand_samples(N)
 
         def k_trav(_):

@@ -47,7 +47,7 @@ for name, res, R, stratified in (("config2 128^3 65536 rays", 128, 65536, False)
         far = torch.full((R,), 1e10, device=dev)
     job = _MarchJob(ro, rd, est.binaries, est.aabbs, near, far, scenes.BALL_STEP, None, None, None,
                     want_intervals=False, want_terminate=False, near_plane=0.0, far_plane=1e10)
-    out = {"case": name, "n_samples": N, "march": timed(job._launch_march), "offsets+expand": timed(lambda: job._expand_samples(N)),
+    out = {"case": name, "n_samples": N, "march": timed(job._launch_march), "expand (+packed_info)": timed(lambda: job._expand_samples(N)),
            "sampling()": timed(lambda: est.sampling(ro, rd, render_step_size=scenes.BALL_STEP))}
     job.sc.busy = False
     print(json.dumps(out), flush=True)
