@@ -41,7 +41,8 @@ def pack_info(ray_indices: Tensor, n_rays: Optional[int] = None) -> Tensor:
     assert ray_indices.dim() == 1, "ray_indices must be a 1D tensor with shape (n_samples)."
     if not ray_indices.is_cuda:
         raise NotImplementedError("Only support cuda inputs.")
-    cached = _stashed_packed_info(ray_indices, n_rays)
+    # (with n_rays=None the reference returns max + 1 rows, which the stash -- one row per ray -- need not have)
+    cached = _stashed_packed_info(ray_indices, n_rays) if n_rays is not None else None
     if cached is not None:
         return cached if cached.dtype == ray_indices.dtype else cached.to(ray_indices.dtype)
     if n_rays is None:
