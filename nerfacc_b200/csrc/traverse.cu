@@ -488,6 +488,7 @@ __global__ void __launch_bounds__(kMaxTileRays) march_kernel(const MarchParams p
             }
             if (n_desc > 0) lat_anchor(m, p.lat_table, s_pend[tid]);
             const float anchor = m.t;
+            __syncwarp();  // the first stretch's slot is rewritten below, possibly by another lane
             int incl = n_desc;
 #pragma unroll
             for (int sft = 1; sft < 32; sft <<= 1) {
