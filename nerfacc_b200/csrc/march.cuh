@@ -15,7 +15,10 @@
 //  phase 2 (lat_*)   turns stretches into runs (t_first, n) of consecutive lattice
 //                    samples with two closed-form seeks each (lattice.cuh).  All
 //                    lanes do this at the same time, so the expensive integer
-//                    code is not serialised by divergence.
+//                    code is not serialised by divergence; on one grid level the
+//                    stretches of a warp's rays are independent and are dealt out
+//                    to the lanes (lat_anchor / lat_stretch / lat_take), nested
+//                    levels take a ray's stretches in order (lat_consume).
 //
 // The per-sample arrays are produced later by the expand kernel from the runs.
 // The code is host+device so that tests/host_sim can run the very same logic on
