@@ -126,6 +126,7 @@ class _MarchScratch:
         self.workspace = None
         self.totals_dev = torch.zeros(4, dtype=torch.int64, device=device)
         self.totals_host = torch.zeros(4, dtype=torch.int64).pin_memory()
+        self.totals_np = self.totals_host.numpy()  # same pinned memory: reading it costs no dispatcher call
         self.event = torch.cuda.Event()
         self.busy = False
 
@@ -228,7 +229,8 @@ class _MarchJob:
         if _lib.idle_tasks:
             _lib.run_idle_tasks()  # deferred host work fills the wait for the march
         self.sc.event.synchronize()
-        n, runs, _, stuck = (int(v) for v in self.sc.totals_host.tolist())
+        tot = self.sc.totals_np
+        n, runs, stuck = int(tot[0]), int(tot[1]), int(tot[3])
         if stuck:
             raise RuntimeError(
                 f"traverse_grids: step_size={self.step_size} is below the float32 resolution of the marching "
@@ -268,7 +270,11 @@ class _MarchJob:
                 if self.bufs is None or n > self.cap:
                     self.bufs = self._expand_samples(n)
                 ri, ts, te = self.bufs
-                res.ray_indices, res.t_starts, res.t_ends = ri[:n], ts[:n], te[:n]
+                if ri.shape[0] != n:  # the speculative buffers are longer: shrink the views in place (no new tensors)
+                    ri.resize_(n)
+                    ts.resize_(n)
+                    te.resize_(n)
+                res.ray_indices, res.t_starts, res.t_ends = ri, ts, te
             else:
                 e = n + runs
                 iv_pi = torch.empty((n_rays, 2), dtype=torch.int64, device=device)

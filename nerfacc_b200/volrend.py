@@ -27,7 +27,8 @@ from .scan import exclusive_prod, exclusive_sum
 def _f32c(t: Optional[Tensor]) -> Optional[Tensor]:
     if t is None:
         return None
-    t = t.contiguous()
+    if not t.is_contiguous():
+        t = t.contiguous()
     if t.dtype != torch.float32:
         raise RuntimeError("nerfacc_b200 rendering kernels support float32 inputs only.")
     return t
