@@ -45,6 +45,20 @@ def test_version_and_error_strings_without_gpu():
     assert lib.nfa_scan_by_key_workspace_bytes(1 << 20) > 0
 
 
+def test_march_workspace_size_covers_its_parts():
+    """nfa_march_workspace_bytes: header + tile sums and bases + three per-ray u32 arrays (sample / run counts,
+    sample offset inside the tile) + the run pool of 32-byte records; grows with both arguments (pure host code)."""
+    from nerfacc_b200 import _lib
+    lib = _lib.load()
+    for n_rays in (1, 31, 448, 65536, 1 << 20):
+        for runs in (0, 1000, 3 * n_rays + 1024):
+            b = lib.nfa_march_workspace_bytes(n_rays, runs)
+            assert b >= 64 + 3 * 4 * n_rays + 32 * runs
+            assert lib.nfa_march_workspace_bytes(n_rays, runs + 1) >= b + 32
+            assert lib.nfa_march_workspace_bytes(n_rays + 512, runs) > b
+    assert lib.nfa_march_workspace_bytes(-1, 0) == 0 and lib.nfa_march_workspace_bytes(4, -1) == 0
+
+
 def test_argument_errors_do_not_need_a_gpu():
     from nerfacc_b200 import _lib
     lib = _lib.load()
